@@ -1,0 +1,172 @@
+/*
+ * upd_b200.h -- C ABI of the B200-native uncertainty-inference hot path
+ * (conditional reverse-diffusion sampling + MPV / gx reduction).
+ *
+ * The reference has no FFI layer: its boundary is the Python surface between
+ * evaluation_and_analysis/diffusion_model_uncertainy.py and models/Diffusion_model/*.
+ * Each entry point below replaces one reference function at that surface; the reference
+ * file:line it stands in for is cited per function.  INTEGRATION.md shows the ctypes stub a
+ * reference maintainer would add.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  Every `*_dev` pointer is CUDA device memory owned by the
+ *     caller; the library never allocates, frees, or keeps state between calls (re-entrant per
+ *     stream; one process per GPU can run concurrently).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All work is
+ *     enqueued asynchronously on it; nothing synchronises the device.
+ *   - Return value: 0 = UPD_OK, otherwise a UPD_ERR_* code; upd_error_string() names it.  The
+ *     Python host layer raises RuntimeError on non-zero.
+ *   - All arithmetic is fp32 ("dtype f32").  Tensor-core contractions use an fp16 hi/lo split with
+ *     three tcgen05 passes per product and fp32 accumulation (see DESIGN.md "Numerics").
+ */
+#ifndef UPD_B200_H
+#define UPD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+  UPD_OK = 0,
+  UPD_ERR_BAD_ARG = 1,       /* NULL pointer, non-positive size, inconsistent sizes            */
+  UPD_ERR_UNSUPPORTED = 2,   /* shape outside what the kernels are built for (see each call)   */
+  UPD_ERR_CUDA = 3,          /* a CUDA runtime call failed; see upd_last_cuda_error()          */
+  UPD_ERR_NO_DEVICE = 4      /* not an sm_100 device                                           */
+};
+
+/* Denoiser families sharing the fused sampler. */
+enum {
+  UPD_KIND_NSDIFF = 0,       /* models/Diffusion_model/NsDiff/denoise.py:23-51                 */
+  UPD_KIND_TMDM = 1          /* models/Diffusion_model/TMDM/tmdm_model.py:23-64                */
+};
+
+/* Sampler implementations (same results within fp32 round-off). */
+enum {
+  UPD_IMPL_TCGEN05 = 0,      /* tcgen05/TMEM tensor-core kernel (default, the product path)    */
+  UPD_IMPL_SIMT = 1          /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
+};
+
+const char* upd_error_string(int code);
+/* cudaError_t of the last failing runtime call made by this library on the calling thread. */
+int upd_last_cuda_error(void);
+/* Library ABI version (bumped when a signature or the packed-weights layout changes). */
+int upd_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Weights.  Host-side, plain fp32 row-major arrays exactly as they sit in the reference
+ * state dict (keys `model.diffussion_model.*`):
+ *   lin{1,2,3}_w [128, in] (in = 3F NsDiff / 2F TMDM for lin1, 128 for lin2/3), lin*_b [128],
+ *   embed{1,2,3} [TE, 128] (TE = T for NsDiff, T+1 for TMDM), lin4_w [F,128], lin4_b [F],
+ *   sigma_w [F,128] / sigma_b [F] (NsDiff only; NULL for TMDM),
+ *   sched [n_sched, T]: NsDiff n_sched = 10 rows in the order p_sample_loop receives them
+ *     (nsdiff_utils.py:271): alphas, one_minus_alphas_bar_sqrt, alphas_cumprod,
+ *     alphas_cumprod_sum, alphas_cumprod_prev, alphas_cumprod_sum_prev, betas_tilde, betas_bar,
+ *     betas_tilde_m_1, betas_bar_m_1 -- copied from the reference-built fp32 tables, never
+ *     recomputed; TMDM n_sched = 2: alphas, one_minus_alphas_bar_sqrt (tmdm_diffusion_utils.py:107).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct UpdDenoiserWeights {
+  int kind;            /* UPD_KIND_*            */
+  int F;               /* dataset_nf, 1..4      */
+  int T;               /* diffusion_steps, 2..64 */
+  const float* lin1_w; const float* lin1_b; const float* embed1;
+  const float* lin2_w; const float* lin2_b; const float* embed2;
+  const float* lin3_w; const float* lin3_b; const float* embed3;
+  const float* lin4_w; const float* lin4_b;
+  const float* sigma_w; const float* sigma_b;
+  const float* sched;
+} UpdDenoiserWeights;
+
+/* Bytes of the packed blob for (kind, F, T); 0 if unsupported. */
+size_t upd_denoiser_pack_bytes(int kind, int F, int T);
+/* Pack host weights into `out_host` (capacity >= upd_denoiser_pack_bytes).  The caller uploads
+ * the blob once per model load (replaces nothing in the reference: this is the B200 layout of
+ * what utils/utils.py:660-689 load_diffusion_model materialises as nn.Parameters). */
+int upd_denoiser_pack(const UpdDenoiserWeights* w, void* out_host, size_t capacity);
+
+/* ------------------------------------------------------------------------------------------
+ * upd_nsdiff_sample -- replaces p_sample_loop + the K//S chunk loop of evaluation_step
+ *   (models/Diffusion_model/NsDiff/nsdiff_utils.py:271-284, :111-158, :209-239;
+ *    NsDiff_model.py:227-257 / :461-487) for a batch of n_win windows of B rows each.
+ *
+ *   packed_dev   blob from upd_denoiser_pack (kind NSDIFF), on the device
+ *   y0_hat_dev   [n_win*B, O, F] condition mean f(x); NULL = zeros (variants without f(x),
+ *                NsDiff_model.py:446).  It is also the prior mean y_T_mean (:231 / :464).
+ *   gx_dev       [n_win*B, O, F] condition variance g(x) (EPS already added where the
+ *                reference adds it, NsDiff_model.py:450)
+ *   K            samples to draw per row (= (n_z_samples // parallel_sample) * parallel_sample)
+ *   S            parallel_sample: only fixes the layout of injected noise and the Philox-free
+ *                reference ordering; results do not depend on it in Philox mode
+ *   seed, window_base   Philox4x32-10 key and the global index of the first window of this
+ *                batch: noise is keyed by (seed, global window, row, sample, position, feature,
+ *                draw) so a sweep gives identical samples however it is split over launches/GPUs
+ *   noise_dev    validation mode: NULL, or injected N(0,1) draws laid out as the reference
+ *                consumes them, [n_win, K/S, T, B*S, O, F] (draw 0 = y_T, draw i = step t=T-i)
+ *   out_dev      [n_win*B, K, O, F]  (the reference's cache element [B,O,F,K] is a permuted
+ *                view of exactly this memory, NsDiff_model.py:259-262)
+ *   impl         UPD_IMPL_*
+ * Limits: F in 1..4, T in 2..64, O*F*4 bytes 16-byte aligned not required.
+ * ------------------------------------------------------------------------------------------ */
+int upd_nsdiff_sample(const void* packed_dev, const float* y0_hat_dev, const float* gx_dev,
+                      int n_win, int B, int K, int S, int O, int F, int T,
+                      uint64_t seed, uint64_t window_base, const float* noise_dev,
+                      float* out_dev, int impl, void* stream);
+
+/* upd_tmdm_sample -- replaces TMDM p_sample_loop + chunk loop
+ *   (models/Diffusion_model/TMDM/tmdm_diffusion_utils.py:57-119, tmdm_adapter.py:132-151).
+ *   y0_hat_dev [n_win*B, Lr, F] with Lr = label_len + pred_len rows per trajectory; unit-variance
+ *   prior around it; out_dev [n_win*B, K, Lr, F] (caller slices the last pred_len positions).
+ *   noise_dev layout [n_win, K/S, T, B*S, Lr, F]. */
+int upd_tmdm_sample(const void* packed_dev, const float* y0_hat_dev,
+                    int n_win, int B, int K, int S, int Lr, int F, int T,
+                    uint64_t seed, uint64_t window_base, const float* noise_dev,
+                    float* out_dev, int impl, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * upd_mpv_reduce -- replaces summarize_pred_future_list / summarize_slbp_sensitivity /
+ *   summarize_slbp_sampling_for_fig6 (diffusion_model_uncertainy.py:286-303, :529-541, :701-713):
+ *   biased variance over the K trajectories (Welford, warp-shuffle merge), then means.
+ *
+ *   traj_dev     [n_win*B, K, O, F] as written by the samplers
+ *   scale_dev    NULL, or [2,F] = (scaler_mean, scaler_std): trajectories are mapped to raw units
+ *                x*std+mean before the statistics (_feature_inverse_transform, :267-283)
+ *   var_dev      NULL or [n_win*B, O, F] per-position predictive variance
+ *   mean_dev     NULL or [n_win*B, O, F] per-position predictive mean (prediction-error path, :542-549)
+ *   mpv_dev      [n_win]   mean of var over (B,O,F)       -> `ews` of uncertainty_ews
+ *   pmean_dev    [n_win]   mean of all samples            -> `pred_mean`
+ *   mpv_f_dev    [n_win,F] mean of var over (B,O) per feature -> SLBP MPV picks [pred_dim]
+ *   scratch_dev  >= upd_mpv_scratch_bytes(n_win, B, O, F) bytes
+ * ------------------------------------------------------------------------------------------ */
+size_t upd_mpv_scratch_bytes(int n_win, int B, int O, int F);
+int upd_mpv_reduce(const float* traj_dev, const float* scale_dev, int n_win, int B, int K, int O, int F,
+                   float* var_dev, float* mean_dev, float* mpv_dev, float* pmean_dev, float* mpv_f_dev,
+                   void* scratch_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * upd_sigma_estimation -- replaces SigmaEstimation.forward, i.e. cond_pred_model_g, the whole
+ *   "gx" uncertainty path (models/Diffusion_model/NsDiff/g_backbone.py:49-72, sigma.py:34-71).
+ *   x_dev [rows, L, F] scaled windows; weights as in the state dict `cond_pred_model_g.mlp.*`
+ *   (row-major fp32, device): w0 [H, L-R], b0 [H], ln1_w/ln1_b [F,H], w3 [H,H], b3 [H],
+ *   ln2_w/ln2_b [F,H], w6 [O,H], b6 [O].  add_eps is added to the result (1e-7 where the
+ *   reference adds EPS, else 0).  gx_dev [rows, O, F].  Limits: F in 1..4, O <= H.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct UpdSigmaWeights {
+  const float* w0; const float* b0; const float* ln1_w; const float* ln1_b;
+  const float* w3; const float* b3; const float* ln2_w; const float* ln2_b;
+  const float* w6; const float* b6;
+} UpdSigmaWeights;
+int upd_sigma_estimation(const UpdSigmaWeights* w_dev_ptrs, const float* x_dev, int rows, int L, int R,
+                         int F, int H, int O, float add_eps, float* gx_dev, void* stream);
+
+/* Known-answer self test of the tcgen05 descriptors this library relies on: D[128,N] = A[128,K] * B[N,K]^T
+ * with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K=128; mode 1: tf32 hi/lo
+ * 3-pass, K=8*k8).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */
+int upd_selftest_umma(const float* a_dev, const float* b_dev, float* d_dev, int K, int mode, int flags,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UPD_B200_H */

@@ -1,0 +1,318 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the reference-made
+golden fixtures and against the CPU oracle on seeded inputs.
+
+Tolerances (stated per north star): trajectories rel 1e-3 per value (+ an absolute floor of
+1e-4 x rms for values near zero), MPV rel 1e-4.  Observed errors are ~1e-6 x rms; the tighter
+`TIGHT` bounds below are what the kernels are actually held to.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, load_wo_fx_checkpoint
+from oracle import mpv_oracle, nsdiff_oracle, sigma_oracle, tmdm_oracle
+
+pytestmark = pytest.mark.gpu
+
+TIGHT_RMS = 2e-5      # max |d| / rms(ref)
+MPV_RTOL = 1e-5
+
+
+def _k():
+    from updgm_b200 import kernels, schedules
+    return kernels, schedules
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _assert_traj(out, ref, what):
+    out, ref = out.double().cpu(), ref.double().cpu()
+    assert torch.isfinite(out).all(), what
+    rms = ref.pow(2).mean().sqrt()
+    d = (out - ref).abs()
+    assert (d <= 1e-3 * ref.abs() + 1e-4 * rms).all(), "{}: beyond the stated tolerance, max|d|/rms={:.3e}".format(
+        what, float(d.max() / rms))
+    assert float(d.max() / rms) <= TIGHT_RMS, "{}: max|d|/rms={:.3e}".format(what, float(d.max() / rms))
+
+
+def _pack_ns(sd, F, T=20, schedule="linear"):
+    kernels, schedules = _k()
+    tab = schedules.nsdiff_tables(schedule, T, 1e-4, 0.02)
+    return kernels.pack_denoiser(sd, kernels.KIND_NSDIFF, F, T, schedules.stack_rows(tab, schedules.NSDIFF_ROWS), _dev())
+
+
+IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05")]
+
+
+# ---------------------------------------------------------------- tcgen05 descriptor known-answer
+@pytest.mark.parametrize("mode,K", [(0, 128), (1, 8), (1, 16)])
+def test_umma_selftest(mode, K):
+    kernels, _ = _k()
+    g = torch.Generator().manual_seed(5 + K)
+    a = torch.randn(128, K, generator=g)
+    b = torch.randn(128, K, generator=g)
+    # distinct structure per row/column so a transposed or permuted operand cannot pass by accident
+    a += torch.arange(128).float().view(-1, 1) * 0.01
+    b += torch.arange(K).float().view(1, -1) * 0.02
+    ref = a.double() @ b.double().t()
+    d = kernels.selftest_umma(a.to(_dev()), b.to(_dev()), mode=mode, flags=0).cpu().double()
+    scale = (a.double().abs() @ b.double().abs().t())
+    err = ((d - ref).abs() / scale).max().item()
+    assert err < 4e-6, "tcgen05 3-pass contraction off: {:.3e}".format(err)
+
+
+# ---------------------------------------------------------------- sampler vs reference fixtures
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", ["psample_loop_wo_fx.npz", "psample_loop_wo_fx_fx.npz"])
+def test_nsdiff_loop_golden_wo_fx(impl, name):
+    kernels, _ = _k()
+    _, sd = load_wo_fx_checkpoint()
+    g = load_golden(name)
+    packed = _pack_ns(sd, 2)
+    R, O, F = g["gx"].shape
+    dev = _dev()
+    y0 = g["y_0_hat"].to(dev)
+    out = kernels.nsdiff_sample(packed, y0 if name.endswith("_fx.npz") else None, g["gx"].to(dev), n_win=1, B=R, K=1,
+                                S=1, O=O, F=F, T=20, noise=g["noise"].to(dev).contiguous(), impl=impl)
+    _assert_traj(out.reshape(R, O, F), g["seq"][-1], name)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_nsdiff_loop_golden_random_F1(impl):
+    kernels, _ = _k()
+    g = load_golden("psample_loop_randF1.npz")
+    packed = _pack_ns(g["sd"], 1)
+    R, O, F = g["gx"].shape
+    dev = _dev()
+    out = kernels.nsdiff_sample(packed, g["y_0_hat"].to(dev), g["gx"].to(dev), 1, R, 1, 1, O, F, 20,
+                                noise=g["noise"].to(dev).contiguous(), impl=impl)
+    _assert_traj(out.reshape(R, O, F), g["seq"][-1], "randF1")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_evaluation_step_golden_chunked_noise_layout(impl):
+    """K=8 in chunks of S=4: noise tensor in the reference's own consumption order."""
+    kernels, _ = _k()
+    net_param, sd = load_wo_fx_checkpoint()
+    g = load_golden("evalstep_wo_fx_k8s4.npz")
+    dev = _dev()
+    packed = _pack_ns(sd, 2)
+    gx = (g["gx"] + 1e-7).to(dev)                     # NsDiff_model.py:450
+    out = kernels.nsdiff_sample(packed, None, gx, 1, 1, 8, 4, 200, 2, 20, noise=g["noise"].to(dev).contiguous(), impl=impl)
+    outs = out.reshape(1, 8, 200, 2).permute(0, 2, 3, 1)
+    _assert_traj(outs, g["outs"], "evalstep")
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_tmdm_loop_golden(impl):
+    kernels, schedules = _k()
+    g = load_golden("tmdm_loop_randF1.npz")
+    tab = schedules.tmdm_tables("linear", 20, 1e-4, 0.02)
+    dev = _dev()
+    packed = kernels.pack_denoiser(g["sd"], kernels.KIND_TMDM, 1, 20, schedules.stack_rows(tab, schedules.TMDM_ROWS), dev)
+    R, Lr, F = g["y_0_hat"].shape
+    out = kernels.tmdm_sample(packed, g["y_0_hat"].to(dev), 1, R, 1, 1, Lr, F, 20, noise=g["noise"].to(dev).contiguous(),
+                              impl=impl)
+    _assert_traj(out.reshape(R, Lr, F), g["seq"][-1], "tmdm")
+
+
+# ---------------------------------------------------------------- sampler vs oracle, seeded, multi-window
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("F", [1, 2, 3, 4])
+def test_nsdiff_vs_oracle_multiwindow(impl, F):
+    """n_win=3 windows x B=2 rows x K=6 (S=3) x O=37 (ragged tile tail), every feature count."""
+    kernels, schedules = _k()
+    torch.manual_seed(100 + F)
+    T, n_win, B, K, S, O = 20, 3, 2, 6, 3, 37
+    sd = _random_ns_weights(F, T)
+    sched = nsdiff_oracle.nsdiff_schedule("linear", T, 1e-4, 0.02)
+    y0 = torch.randn(n_win * B, O, F) * 0.5
+    gx = torch.rand(n_win * B, O, F) * 0.3 + 0.02
+    noise = torch.randn(n_win, K // S, T, B * S, O, F)
+    ref = torch.empty(n_win * B, K, O, F)
+    for w in range(n_win):
+        for c in range(K // S):
+            it = iter(noise[w, c])
+            y0t = nsdiff_oracle.tile_rows(y0[w * B:(w + 1) * B], S)
+            gxt = nsdiff_oracle.tile_rows(gx[w * B:(w + 1) * B], S)
+            seq = nsdiff_oracle.p_sample_loop(sd, sched, y0t, gxt, y0t, T, lambda like: next(it))
+            ref[w * B:(w + 1) * B, c * S:(c + 1) * S] = seq[-1].reshape(B, S, O, F)
+    dev = _dev()
+    packed = _pack_ns(sd, F, T)
+    out = kernels.nsdiff_sample(packed, y0.to(dev), gx.to(dev), n_win, B, K, S, O, F, T, noise=noise.to(dev), impl=impl)
+    _assert_traj(out, ref, "F=%d" % F)
+
+
+def _random_ns_weights(F, T):
+    P = nsdiff_oracle.DENOISER_PREFIX
+    sd = {}
+    dims = {"lin1": 3 * F, "lin2": 128, "lin3": 128}
+    for name, k in dims.items():
+        sd[P + name + ".lin.weight"] = (torch.rand(128, k) * 2 - 1) / k ** 0.5
+        sd[P + name + ".lin.bias"] = (torch.rand(128) * 2 - 1) / k ** 0.5
+        sd[P + name + ".embed.weight"] = torch.rand(T, 128)
+    for name in ("lin4", "sigma_lin"):
+        sd[P + name + ".weight"] = (torch.rand(F, 128) * 2 - 1) / 128 ** 0.5
+        sd[P + name + ".bias"] = (torch.rand(F) * 2 - 1) / 128 ** 0.5
+    return sd
+
+
+def test_tc_matches_simt_bitwise_structure_large():
+    """Full-size tile coverage: 5 windows x K=100 x O=200 (100k rows) -- both implementations agree."""
+    kernels, _ = _k()
+    _, sd = load_wo_fx_checkpoint()
+    dev = _dev()
+    packed = _pack_ns(sd, 2)
+    torch.manual_seed(3)
+    gx = (torch.rand(5, 200, 2) * 0.06 + 0.01).to(dev)
+    a = kernels.nsdiff_sample(packed, None, gx, 5, 1, 100, 100, 200, 2, 20, seed=11, window_base=7, impl=0)
+    b = kernels.nsdiff_sample(packed, None, gx, 5, 1, 100, 100, 200, 2, 20, seed=11, window_base=7, impl=1)
+    _assert_traj(a, b, "tc vs simt")
+
+
+# ---------------------------------------------------------------- Philox mode properties
+@pytest.mark.parametrize("impl", IMPLS)
+def test_philox_split_invariance_and_seed(impl):
+    """Same (seed, global window) -> identical samples however the sweep is cut into launches."""
+    kernels, _ = _k()
+    _, sd = load_wo_fx_checkpoint()
+    dev = _dev()
+    packed = _pack_ns(sd, 2)
+    torch.manual_seed(4)
+    gx = (torch.rand(4, 50, 2) * 0.06 + 0.01).to(dev)
+    full = kernels.nsdiff_sample(packed, None, gx, 4, 1, 16, 4, 50, 2, 20, seed=99, window_base=10, impl=impl)
+    lo = kernels.nsdiff_sample(packed, None, gx[:1].contiguous(), 1, 1, 16, 16, 50, 2, 20, seed=99, window_base=10, impl=impl)
+    hi = kernels.nsdiff_sample(packed, None, gx[1:].contiguous(), 3, 1, 16, 8, 50, 2, 20, seed=99, window_base=11, impl=impl)
+    assert torch.equal(full[:1], lo) and torch.equal(full[1:], hi)
+    other = kernels.nsdiff_sample(packed, None, gx, 4, 1, 16, 4, 50, 2, 20, seed=100, window_base=10, impl=impl)
+    assert not torch.equal(full, other)
+
+
+def test_philox_statistics_match_reference_distribution():
+    """MPV from in-kernel Philox noise agrees with the oracle driven by torch noise (K=2000)."""
+    kernels, _ = _k()
+    net_param, sd = load_wo_fx_checkpoint()
+    g = load_golden("evalstep_wo_fx_k8s4.npz")
+    dev = _dev()
+    packed = _pack_ns(sd, 2)
+    gx1 = g["gx"][:, :40] + 1e-7                                  # [1,40,2]
+    K = 2000
+    out = kernels.nsdiff_sample(packed, None, gx1.to(dev).contiguous(), 1, 1, K, K, 40, 2, 20, seed=2024)
+    torch.manual_seed(0)
+    sched = nsdiff_oracle.nsdiff_schedule()
+    gxt = nsdiff_oracle.tile_rows(gx1, K)
+    ref = nsdiff_oracle.p_sample_loop(sd, sched, torch.zeros_like(gxt), gxt, torch.zeros_like(gxt), 20, torch.randn_like)[-1]
+    v_gpu = out.reshape(K, 40, 2).var(dim=0, unbiased=False).mean().item()
+    v_ref = ref.var(dim=0, unbiased=False).mean().item()
+    m_gpu = out.mean().item()
+    assert abs(v_gpu - v_ref) / v_ref < 0.03, (v_gpu, v_ref)       # ~ 1/sqrt(K*40*2/corr) sampling error
+    assert abs(m_gpu) < 0.02
+
+
+# ---------------------------------------------------------------- g(x)
+def test_sigma_estimation_golden():
+    kernels, _ = _k()
+    net_param, sd = load_wo_fx_checkpoint()
+    dev = _dev()
+    ws = [sd["cond_pred_model_g.mlp.%s" % k].to(dev).contiguous() for k in
+          ("0.weight", "0.bias", "2.weight", "2.bias", "3.weight", "3.bias", "5.weight", "5.bias", "6.weight", "6.bias")]
+    g = load_golden("sigma_estimation_wo_fx.npz")
+    gx = kernels.sigma_estimation(ws, g["x"].to(dev), 100, 200).cpu()
+    np.testing.assert_allclose(gx.numpy(), g["gx"].numpy(), rtol=2e-5, atol=1e-7)
+    g2 = load_golden("evalstep_wo_fx_k8s4.npz")
+    gx2 = kernels.sigma_estimation(ws, g2["window_scaled"].to(dev), 100, 200, add_eps=1e-7).cpu()
+    np.testing.assert_allclose(gx2.numpy(), (g2["gx"] + 1e-7).numpy(), rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("rows,Lw,R,F,O", [(1, 100, 50, 1, 100), (7, 100, 50, 1, 100), (5, 60, 20, 3, 33), (9, 200, 100, 4, 200)])
+def test_sigma_estimation_vs_oracle(rows, Lw, R, F, O):
+    kernels, _ = _k()
+    torch.manual_seed(rows * 7 + F)
+    H = 512
+    n_in = Lw - R
+    P = "cond_pred_model_g."
+    sd = {P + "mlp.0.weight": torch.randn(H, n_in) / n_in ** 0.5, P + "mlp.0.bias": torch.randn(H) * 0.1,
+          P + "mlp.2.weight": torch.rand(F, H) + 0.5, P + "mlp.2.bias": torch.randn(F, H) * 0.1,
+          P + "mlp.3.weight": torch.randn(H, H) / H ** 0.5, P + "mlp.3.bias": torch.randn(H) * 0.1,
+          P + "mlp.5.weight": torch.rand(F, H) + 0.5, P + "mlp.5.bias": torch.randn(F, H) * 0.1,
+          P + "mlp.6.weight": torch.randn(O, H) / H ** 0.5, P + "mlp.6.bias": torch.randn(O) * 0.1}
+    x = torch.randn(rows, Lw, F).cumsum(dim=1) * 0.2
+    ref = sigma_oracle.sigma_estimation(sd, x, R, O)
+    dev = _dev()
+    ws = [sd[P + "mlp.%s" % k].to(dev).contiguous() for k in
+          ("0.weight", "0.bias", "2.weight", "2.bias", "3.weight", "3.bias", "5.weight", "5.bias", "6.weight", "6.bias")]
+    gx = kernels.sigma_estimation(ws, x.to(dev), R, O).cpu()
+    np.testing.assert_allclose(gx.numpy(), ref.numpy(), rtol=5e-5, atol=1e-6)
+
+
+# ---------------------------------------------------------------- MPV reduction
+def test_mpv_reduce_golden():
+    kernels, _ = _k()
+    g = load_golden("evalstep_wo_fx_k8s4.npz")
+    dev = _dev()
+    traj = g["outs"].permute(0, 3, 1, 2).contiguous().to(dev)        # [B=1,K,O,F]
+    r = kernels.mpv_reduce(traj, 1, 1, want_var=True, want_mean=True)
+    assert r["mpv"].item() == pytest.approx(float(g["net_ews_nomodel"]), rel=MPV_RTOL)
+    assert r["pred_mean"].item() == pytest.approx(float(g["net_pred_mean_nomodel"]), rel=1e-4, abs=1e-7)
+    assert r["mpv_f"][0, 0].item() == pytest.approx(float(g["slbp_mpv_dim0"]), rel=MPV_RTOL)
+    assert r["mpv_f"][0, 1].item() == pytest.approx(float(g["fig6_mpv_dim1"]), rel=MPV_RTOL)
+    scale = torch.stack([g["scaler_mean"], g["scaler_std"]]).to(dev).contiguous()
+    r2 = kernels.mpv_reduce(traj, 1, 1, scale=scale)
+    assert r2["mpv"].item() == pytest.approx(float(g["net_ews"]), rel=MPV_RTOL)
+    assert r2["pred_mean"].item() == pytest.approx(float(g["net_pred_mean"]), rel=MPV_RTOL)
+    tgt = ((g["target_raw"] - g["scaler_mean"]) / g["scaler_std"]).to(dev)
+    err = (r["mean"].reshape(200, 2) - tgt).abs().mean(dim=0)[0].item()
+    assert err == pytest.approx(float(g["slbp_err_dim0"]), rel=1e-5)
+
+
+@pytest.mark.parametrize("n_win,B,K,O,F", [(1, 1, 1, 1, 1), (3, 2, 7, 5, 3), (4, 3, 100, 100, 1), (2, 1, 100, 200, 2),
+                                           (5, 4, 33, 37, 2), (2, 2, 9, 3, 4)])
+def test_mpv_reduce_vs_oracle_ragged(n_win, B, K, O, F):
+    kernels, _ = _k()
+    torch.manual_seed(n_win * 100 + K)
+    traj = torch.randn(n_win * B, K, O, F) * torch.rand(n_win * B, 1, O, F) + torch.randn(n_win * B, 1, O, F) * 3
+    dev = _dev()
+    mean = torch.randn(F)
+    std = torch.rand(F) + 0.5
+    for scale in (None, torch.stack([mean, std])):
+        r = kernels.mpv_reduce(traj.to(dev), n_win, B, scale=None if scale is None else scale.to(dev).contiguous(), want_var=True)
+        for w in range(n_win):
+            elem = traj[w * B:(w + 1) * B].permute(0, 2, 3, 1).numpy()          # [B,O,F,K]
+            pm, mpv = mpv_oracle.network_mpv(elem, *( (None, None) if scale is None else (mean.numpy(), std.numpy())))
+            assert r["mpv"][w].item() == pytest.approx(mpv, rel=MPV_RTOL, abs=1e-9)
+            assert r["pred_mean"][w].item() == pytest.approx(pm, rel=1e-4, abs=1e-5)
+            if scale is None:
+                for f in range(F):
+                    want = np.asarray(elem, np.float64).var(axis=-1)[:, :, f].mean()
+                    assert r["mpv_f"][w, f].item() == pytest.approx(want, rel=MPV_RTOL, abs=1e-9)
+
+
+def test_mpv_linearity_property_full_size():
+    """BASELINE config-1 window size (K=100, O=200, F=2) x 64 windows: var(a*x+b) = a^2 var(x)."""
+    kernels, _ = _k()
+    dev = _dev()
+    torch.manual_seed(8)
+    traj = torch.randn(64, 100, 200, 2, device=dev)
+    r1 = kernels.mpv_reduce(traj, 64, 1)
+    r2 = kernels.mpv_reduce(traj * 3.0 + 5.0, 64, 1)
+    torch.testing.assert_close(r2["mpv"], r1["mpv"] * 9.0, rtol=2e-5, atol=0)
+    torch.testing.assert_close(r2["pred_mean"], r1["pred_mean"] * 3.0 + 5.0, rtol=2e-5, atol=1e-5)
+    ref = traj.double().var(dim=1, unbiased=False).mean(dim=(1, 2)).float()
+    torch.testing.assert_close(r1["mpv"], ref, rtol=MPV_RTOL, atol=0)
+
+
+# ---------------------------------------------------------------- error behaviour of the C ABI
+def test_c_abi_rejects_bad_arguments():
+    kernels, _ = _k()
+    _, sd = load_wo_fx_checkpoint()
+    dev = _dev()
+    packed = _pack_ns(sd, 2)
+    gx = torch.rand(1, 10, 2, device=dev)
+    with pytest.raises(RuntimeError, match="bad argument"):
+        kernels.nsdiff_sample(packed, None, gx, 1, 1, 0, 1, 10, 2, 20)
+    with pytest.raises(RuntimeError, match="unsupported"):
+        kernels.nsdiff_sample(packed, None, gx, 1, 1, 1, 1, 10, 5, 20)
+    with pytest.raises(RuntimeError, match="bad argument"):
+        kernels.nsdiff_sample(packed, None, gx, 1, 1, 6, 4, 10, 2, 20, noise=torch.zeros(4, device=dev))

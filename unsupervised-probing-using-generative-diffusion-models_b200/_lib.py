@@ -1,0 +1,101 @@
+"""ctypes binding of include/upd_b200.h.  There is no CPU fallback: if the library is missing or a
+call fails this module raises."""
+import ctypes
+import os
+
+import torch
+
+from . import _build
+
+_LIB = None
+
+SYMBOLS = (
+    "upd_error_string", "upd_last_cuda_error", "upd_abi_version", "upd_denoiser_pack_bytes", "upd_denoiser_pack",
+    "upd_nsdiff_sample", "upd_tmdm_sample", "upd_mpv_scratch_bytes", "upd_mpv_reduce", "upd_sigma_estimation",
+    "upd_selftest_umma",
+)
+
+KIND_NSDIFF, KIND_TMDM = 0, 1
+IMPL_TCGEN05, IMPL_SIMT = 0, 1
+_fp = ctypes.POINTER(ctypes.c_float)
+
+
+class UpdDenoiserWeights(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int), ("F", ctypes.c_int), ("T", ctypes.c_int)] + [
+        (n, ctypes.c_void_p) for n in ("lin1_w", "lin1_b", "embed1", "lin2_w", "lin2_b", "embed2", "lin3_w", "lin3_b",
+                                       "embed3", "lin4_w", "lin4_b", "sigma_w", "sigma_b", "sched")]
+
+
+class UpdSigmaWeights(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("w0", "b0", "ln1_w", "ln1_b", "w3", "b3", "ln2_w", "ln2_b", "w6", "b6")]
+
+
+def lib():
+    """Load (once) the in-tree shared library; raise loudly when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "CUDA library {} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). This package has no CPU fallback.".format(path))
+    L = ctypes.CDLL(path)
+    L.upd_error_string.restype = ctypes.c_char_p
+    L.upd_error_string.argtypes = [ctypes.c_int]
+    L.upd_last_cuda_error.restype = ctypes.c_int
+    L.upd_abi_version.restype = ctypes.c_int
+    L.upd_denoiser_pack_bytes.restype = ctypes.c_size_t
+    L.upd_denoiser_pack_bytes.argtypes = [ctypes.c_int] * 3
+    L.upd_denoiser_pack.restype = ctypes.c_int
+    L.upd_denoiser_pack.argtypes = [ctypes.POINTER(UpdDenoiserWeights), ctypes.c_void_p, ctypes.c_size_t]
+    vp, i, u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+    L.upd_nsdiff_sample.restype = ctypes.c_int
+    L.upd_nsdiff_sample.argtypes = [vp, vp, vp, i, i, i, i, i, i, i, u64, u64, vp, vp, i, vp]
+    L.upd_tmdm_sample.restype = ctypes.c_int
+    L.upd_tmdm_sample.argtypes = [vp, vp, i, i, i, i, i, i, i, u64, u64, vp, vp, i, vp]
+    L.upd_mpv_scratch_bytes.restype = ctypes.c_size_t
+    L.upd_mpv_scratch_bytes.argtypes = [i, i, i, i]
+    L.upd_mpv_reduce.restype = ctypes.c_int
+    L.upd_mpv_reduce.argtypes = [vp, vp, i, i, i, i, i, vp, vp, vp, vp, vp, vp, vp]
+    L.upd_sigma_estimation.restype = ctypes.c_int
+    L.upd_sigma_estimation.argtypes = [ctypes.POINTER(UpdSigmaWeights), vp, i, i, i, i, i, i, ctypes.c_float, vp, vp]
+    L.upd_selftest_umma.restype = ctypes.c_int
+    L.upd_selftest_umma.argtypes = [vp, vp, vp, i, i, i, vp]
+    _LIB = L
+    return L
+
+
+def check(code, what):
+    if code != 0:
+        L = lib()
+        msg = L.upd_error_string(code).decode()
+        if code == 3:
+            msg += " (cudaError {})".format(L.upd_last_cuda_error())
+        raise RuntimeError("{} failed: {}".format(what, msg))
+
+
+def ptr(t):
+    """Device/host pointer of a contiguous fp32 tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError("tensor must be contiguous")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def dev_f32(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(device):
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("this package runs on CUDA (sm_100a) only; got device {!r} (no CPU fallback)".format(str(device)))
+    if not torch.cuda.is_available():
+        raise RuntimeError("CUDA is not available (no CPU fallback)")
+    return device

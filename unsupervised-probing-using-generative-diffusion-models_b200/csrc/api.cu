@@ -1,0 +1,239 @@
+// extern "C" entry points (include/upd_b200.h): argument validation, host-side weight packing,
+// kernel launches on the caller's stream.  No global state, no allocation.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "upd_b200.h"
+#include "sampler_params.cuh"
+#include "upd_common.cuh"
+
+cudaError_t upd_launch_mpv(const float* traj, const float* scale, int n_win, int B, int K, int O, int F,
+                           float* var_out, float* mean_out, float* mpv, float* pmean, float* mpv_f,
+                           cudaStream_t stream);
+cudaError_t upd_launch_sigma(const UpdSigmaWeights& w, const float* x, int rows, int Lw, int R, int F, int H,
+                             int O, float add_eps, float* gx, cudaStream_t stream);
+cudaError_t upd_launch_selftest_umma(const float* a, const float* b, float* d, int K, int mode, int flags,
+                                     cudaStream_t stream);
+
+namespace {
+
+thread_local int g_last_cuda_error = 0;
+
+int cuda_fail(cudaError_t e) {
+  g_last_cuda_error = (int)e;
+  return UPD_ERR_CUDA;
+}
+
+// Device checks shared by every launch: sm_100 family, SM count for persistent grids.
+int device_info(int* sms) {
+  int dev = 0, major = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  if (major != 10) return UPD_ERR_NO_DEVICE;
+  e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  return UPD_OK;
+}
+
+bool dims_ok(int kind, int F, int T) {
+  return (kind == UPD_KIND_NSDIFF || kind == UPD_KIND_TMDM) && F >= 1 && F <= UPD_MAX_F && T >= 2 && T <= UPD_MAX_T;
+}
+
+float tf32_round(float x) {  // round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return x;
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+// Power-of-two scale that puts max|W| near 2^10: keeps the fp16 lo parts out of the subnormal
+// range without risking overflow.  Exactly undone in the epilogue.
+float pick_wscale(const float* w, int n) {
+  float m = 0.f;
+  for (int i = 0; i < n; ++i) m = fmaxf(m, fabsf(w[i]));
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e = (int)floorf(log2f(1024.f / m));
+  if (e > 24) e = 24;
+  if (e < -24) e = -24;
+  return ldexpf(1.f, e);
+}
+
+void pack_umma_f16(const float* w /*[128][128] row-major n,k*/, float wscale, unsigned char* hi, unsigned char* lo) {
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < 128; ++k) {
+      float v = w[n * 128 + k] * wscale;
+      __half h = __float2half_rn(v);
+      __half l = __float2half_rn(v - __half2float(h));
+      size_t off = (size_t)(k / 8) * 2048 + (size_t)n * 16 + (size_t)(k % 8) * 2;
+      memcpy(hi + off, &h, 2);
+      memcpy(lo + off, &l, 2);
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* upd_error_string(int code) {
+  switch (code) {
+    case UPD_OK: return "ok";
+    case UPD_ERR_BAD_ARG: return "bad argument";
+    case UPD_ERR_UNSUPPORTED: return "unsupported shape";
+    case UPD_ERR_CUDA: return "CUDA runtime error";
+    case UPD_ERR_NO_DEVICE: return "no sm_100 device";
+    default: return "unknown error";
+  }
+}
+
+int upd_last_cuda_error(void) { return g_last_cuda_error; }
+int upd_abi_version(void) { return UPD_ABI_VERSION; }
+
+size_t upd_denoiser_pack_bytes(int kind, int F, int T) {
+  if (!dims_ok(kind, F, T)) return 0;
+  return upd_make_layout(kind, F, T).total_bytes;
+}
+
+int upd_denoiser_pack(const UpdDenoiserWeights* w, void* out_host, size_t capacity) {
+  if (!w || !out_host) return UPD_ERR_BAD_ARG;
+  if (!dims_ok(w->kind, w->F, w->T)) return UPD_ERR_UNSUPPORTED;
+  const bool ns = (w->kind == UPD_KIND_NSDIFF);
+  if (!w->lin1_w || !w->lin1_b || !w->embed1 || !w->lin2_w || !w->lin2_b || !w->embed2 || !w->lin3_w ||
+      !w->lin3_b || !w->embed3 || !w->lin4_w || !w->lin4_b || !w->sched || (ns && (!w->sigma_w || !w->sigma_b)))
+    return UPD_ERR_BAD_ARG;
+  const UpdPackLayout L = upd_make_layout(w->kind, w->F, w->T);
+  if (capacity < L.total_bytes) return UPD_ERR_BAD_ARG;
+  unsigned char* o = (unsigned char*)out_host;
+  memset(o, 0, L.total_bytes);
+  auto fp = [&](uint32_t off) { return (float*)(o + off); };
+  const int F = w->F, T = w->T, IN = L.in_dim;
+
+  const float s2 = pick_wscale(w->lin2_w, 128 * 128), s3 = pick_wscale(w->lin3_w, 128 * 128);
+  pack_umma_f16(w->lin2_w, s2, o + L.u2hi, o + L.u2lo);
+  pack_umma_f16(w->lin3_w, s3, o + L.u3hi, o + L.u3lo);
+  // lin1 as tf32 hi/lo with the bias as column IN (the A tile carries a constant 1 there)
+  for (int n = 0; n < 128; ++n)
+    for (int k = 0; k < L.K1; ++k) {
+      float v = (k < IN) ? w->lin1_w[n * IN + k] : (k == IN ? w->lin1_b[n] : 0.f);
+      float h = tf32_round(v), l = tf32_round(v - h);
+      size_t off = (size_t)(k / 4) * 2048 + (size_t)n * 16 + (size_t)(k % 4) * 4;
+      memcpy(o + L.u1hi + off, &h, 4);
+      memcpy(o + L.u1lo + off, &l, 4);
+    }
+  memcpy(fp(L.b2), w->lin2_b, 128 * 4);
+  memcpy(fp(L.b3), w->lin3_b, 128 * 4);
+  memcpy(fp(L.e1), w->embed1, (size_t)L.TE * 128 * 4);
+  memcpy(fp(L.e2), w->embed2, (size_t)L.TE * 128 * 4);
+  memcpy(fp(L.e3), w->embed3, (size_t)L.TE * 128 * 4);
+  memcpy(fp(L.w4), w->lin4_w, (size_t)F * 128 * 4);
+  memcpy(fp(L.b4), w->lin4_b, (size_t)F * 4);
+  if (ns) {
+    memcpy(fp(L.ws), w->sigma_w, (size_t)F * 128 * 4);
+    memcpy(fp(L.bs), w->sigma_b, (size_t)F * 4);
+  }
+  fp(L.scales)[0] = 1.f / s2;
+  fp(L.scales)[1] = 1.f / s3;
+  memcpy(fp(L.sched), w->sched, (size_t)L.n_sched * T * 4);
+  // fp32 k-major transposes for the FFMA kernel
+  for (int k = 0; k < IN; ++k)
+    for (int n = 0; n < 128; ++n) fp(L.w1t)[k * 128 + n] = w->lin1_w[n * IN + k];
+  memcpy(fp(L.b1), w->lin1_b, 128 * 4);
+  for (int k = 0; k < 128; ++k)
+    for (int n = 0; n < 128; ++n) {
+      fp(L.w2t)[k * 128 + n] = w->lin2_w[n * 128 + k];
+      fp(L.w3t)[k * 128 + n] = w->lin3_w[n * 128 + k];
+    }
+  return UPD_OK;
+}
+
+static int sample_common(int kind, const void* packed, const float* y0_hat, const float* gx, int n_win, int B,
+                         int K, int S, int O, int F, int T, uint64_t seed, uint64_t window_base,
+                         const float* noise, float* out, int impl, void* stream) {
+  if (!packed || !out || n_win <= 0 || B <= 0 || K <= 0 || S <= 0 || O <= 0) return UPD_ERR_BAD_ARG;
+  if (kind == UPD_KIND_NSDIFF && !gx) return UPD_ERR_BAD_ARG;
+  if (kind == UPD_KIND_TMDM && !y0_hat) return UPD_ERR_BAD_ARG;
+  if (!dims_ok(kind, F, T)) return UPD_ERR_UNSUPPORTED;
+  if (noise && (K % S) != 0) return UPD_ERR_BAD_ARG;
+  if (impl != UPD_IMPL_TCGEN05 && impl != UPD_IMPL_SIMT) return UPD_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0) return UPD_ERR_BAD_ARG;
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc != UPD_OK) return rc;
+  UpdSamplerParams p;
+  p.packed = packed; p.y0_hat = y0_hat; p.gx = gx; p.noise = noise; p.out = out;
+  p.n_win = n_win; p.B = B; p.K = K; p.S = S; p.O = O; p.T = T;
+  p.n_rows = (long long)n_win * B * K * O;
+  p.seed = seed; p.window_base = window_base;
+  cudaError_t e = (impl == UPD_IMPL_SIMT) ? upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream)
+                                          : upd_launch_sampler_tc(p, kind, F, sms, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
+}
+
+int upd_nsdiff_sample(const void* packed_dev, const float* y0_hat_dev, const float* gx_dev, int n_win, int B, int K,
+                      int S, int O, int F, int T, uint64_t seed, uint64_t window_base, const float* noise_dev,
+                      float* out_dev, int impl, void* stream) {
+  return sample_common(UPD_KIND_NSDIFF, packed_dev, y0_hat_dev, gx_dev, n_win, B, K, S, O, F, T, seed, window_base,
+                       noise_dev, out_dev, impl, stream);
+}
+
+int upd_tmdm_sample(const void* packed_dev, const float* y0_hat_dev, int n_win, int B, int K, int S, int Lr, int F,
+                    int T, uint64_t seed, uint64_t window_base, const float* noise_dev, float* out_dev, int impl,
+                    void* stream) {
+  return sample_common(UPD_KIND_TMDM, packed_dev, y0_hat_dev, nullptr, n_win, B, K, S, Lr, F, T, seed, window_base,
+                       noise_dev, out_dev, impl, stream);
+}
+
+size_t upd_mpv_scratch_bytes(int n_win, int B, int O, int F) {
+  if (n_win <= 0 || B <= 0 || O <= 0 || F <= 0) return 0;
+  return 2 * sizeof(float) * (size_t)n_win * B * O * F + 256;
+}
+
+int upd_mpv_reduce(const float* traj_dev, const float* scale_dev, int n_win, int B, int K, int O, int F,
+                   float* var_dev, float* mean_dev, float* mpv_dev, float* pmean_dev, float* mpv_f_dev,
+                   void* scratch_dev, void* stream) {
+  if (!traj_dev || n_win <= 0 || B <= 0 || K <= 0 || O <= 0) return UPD_ERR_BAD_ARG;
+  if (F < 1 || F > UPD_MAX_F) return UPD_ERR_UNSUPPORTED;
+  if ((!var_dev || !mean_dev) && !scratch_dev) return UPD_ERR_BAD_ARG;
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc != UPD_OK) return rc;
+  size_t n = (size_t)n_win * B * O * F;
+  float* sc = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch_dev) + 127) & ~(uintptr_t)127);
+  float* var = var_dev ? var_dev : sc;
+  float* mean = mean_dev ? mean_dev : sc + ((n + 31) & ~(size_t)31);
+  cudaError_t e = upd_launch_mpv(traj_dev, scale_dev, n_win, B, K, O, F, var, mean, mpv_dev, pmean_dev, mpv_f_dev,
+                                 (cudaStream_t)stream);
+  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
+}
+
+int upd_sigma_estimation(const UpdSigmaWeights* w, const float* x_dev, int rows, int L, int R, int F, int H, int O,
+                         float add_eps, float* gx_dev, void* stream) {
+  if (!w || !x_dev || !gx_dev || rows <= 0 || L <= 0 || R < 1 || R >= L || H <= 0 || O <= 0) return UPD_ERR_BAD_ARG;
+  if (!w->w0 || !w->b0 || !w->ln1_w || !w->ln1_b || !w->w3 || !w->b3 || !w->ln2_w || !w->ln2_b || !w->w6 || !w->b6)
+    return UPD_ERR_BAD_ARG;
+  if (F < 1 || F > UPD_MAX_F || O > H) return UPD_ERR_UNSUPPORTED;
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc != UPD_OK) return rc;
+  cudaError_t e = upd_launch_sigma(*w, x_dev, rows, L, R, F, H, O, add_eps, gx_dev, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
+}
+
+int upd_selftest_umma(const float* a_dev, const float* b_dev, float* d_dev, int K, int mode, int flags, void* stream) {
+  if (!a_dev || !b_dev || !d_dev) return UPD_ERR_BAD_ARG;
+  if (mode == 0 ? (K != 128) : (K < 8 || K > 32 || K % 8)) return UPD_ERR_UNSUPPORTED;
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc != UPD_OK) return rc;
+  cudaError_t e = upd_launch_selftest_umma(a_dev, b_dev, d_dev, K, mode, flags, (cudaStream_t)stream);
+  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
+}
+
+}  // extern "C"
