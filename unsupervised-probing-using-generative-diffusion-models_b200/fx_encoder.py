@@ -1,0 +1,216 @@
+"""f(x): the Non-stationary-Transformer condition encoder, run once per window row.
+
+PARITY UNPINNED.  The reference builds this model (models/Diffusion_model/NsDiff/mu_backbone.py:53-183,
+TMDM/tmdm_ns_transformer.py:40-174) from blocks of the un-vendored dependency torch-timeseries==0.1.10
+(``DataEmbedding``, ``Encoder/EncoderLayer``, ``Decoder/DecoderLayer``, ``DSAttention/AttentionLayer``),
+which is neither in the reference tree nor installable here, and no shipped checkpoint contains
+``cond_pred_model.*`` weights.  Everything the reference itself spells out (series stationarisation,
+tau/delta Projector, decoder input, de-normalisation, VAE mean path) follows those files line by line;
+the library blocks follow the published Non-stationary Transformer (Liu et al., NeurIPS 2022) design the
+dependency packages: de-stationary attention softmax(scale * (Q K^T * tau + delta)) V, post-norm
+encoder/decoder layers with 1x1-conv feed-forward, circular-conv token embedding + sinusoidal positions.
+Parameter names follow that lineage so such checkpoints would load by name.
+
+This encoder is off the roofline-critical path (once per window vs K*T denoiser evaluations per window):
+it runs as PyTorch library ops (cuBLAS GEMMs, fused SDPA) on the same stream, as SURVEY section 8(f)
+row 1 ("next") schedules its hand-written replacement after the sampler.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class Projector(nn.Module):
+    """mu_backbone.py:12-41: MLP producing the de-stationary factors tau (scalar) / delta (per step)."""
+
+    def __init__(self, enc_in, seq_len, hidden_dims, hidden_layers, output_dim, kernel_size=3):
+        super().__init__()
+        self.series_conv = nn.Conv1d(seq_len, 1, kernel_size=kernel_size, padding=1, padding_mode="circular", bias=False)
+        layers = [nn.Linear(2 * enc_in, hidden_dims[0]), nn.ReLU()]
+        for i in range(hidden_layers - 1):
+            layers += [nn.Linear(hidden_dims[i], hidden_dims[i + 1]), nn.ReLU()]
+        layers += [nn.Linear(hidden_dims[-1], output_dim, bias=False)]
+        self.backbone = nn.Sequential(*layers)
+
+    def forward(self, x, stats):
+        b = x.shape[0]
+        x = self.series_conv(x)                    # B x 1 x E
+        x = torch.cat([x, stats], dim=1).view(b, -1)
+        return self.backbone(x)
+
+
+class TokenEmbedding(nn.Module):
+    def __init__(self, c_in, d_model):
+        super().__init__()
+        self.tokenConv = nn.Conv1d(c_in, d_model, kernel_size=3, padding=1, padding_mode="circular", bias=False)
+
+    def forward(self, x):
+        return self.tokenConv(x.permute(0, 2, 1)).transpose(1, 2)
+
+
+class PositionalEmbedding(nn.Module):
+    def __init__(self, d_model, max_len=5000):
+        super().__init__()
+        pe = torch.zeros(max_len, d_model)
+        pos = torch.arange(0, max_len).float().unsqueeze(1)
+        div = (torch.arange(0, d_model, 2).float() * -(math.log(10000.0) / d_model)).exp()
+        pe[:, 0::2] = torch.sin(pos * div)
+        pe[:, 1::2] = torch.cos(pos * div)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+    def forward(self, x):
+        return self.pe[:, : x.size(1)]
+
+
+class DataEmbedding(nn.Module):
+    """Value (circular conv) + positional embedding; the hot path never supplies time marks (x_mark=None)."""
+
+    def __init__(self, c_in, d_model):
+        super().__init__()
+        self.value_embedding = TokenEmbedding(c_in, d_model)
+        self.position_embedding = PositionalEmbedding(d_model)
+
+    def forward(self, x, x_mark=None):
+        return self.value_embedding(x) + self.position_embedding(x)
+
+
+class AttentionLayer(nn.Module):
+    """Projections + de-stationary attention: softmax(scale * (Q K^T * tau + delta)) V."""
+
+    def __init__(self, d_model, n_heads, causal):
+        super().__init__()
+        self.n_heads, self.causal = n_heads, causal
+        dk = d_model // n_heads
+        self.query_projection = nn.Linear(d_model, dk * n_heads)
+        self.key_projection = nn.Linear(d_model, dk * n_heads)
+        self.value_projection = nn.Linear(d_model, dk * n_heads)
+        self.out_projection = nn.Linear(dk * n_heads, d_model)
+
+    def forward(self, queries, keys, values, tau=None, delta=None):
+        B, Lq, _ = queries.shape
+        S = keys.shape[1]
+        H = self.n_heads
+        q = self.query_projection(queries).view(B, Lq, H, -1).transpose(1, 2)
+        k = self.key_projection(keys).view(B, S, H, -1).transpose(1, 2)
+        v = self.value_projection(values).view(B, S, H, -1).transpose(1, 2)
+        scale = 1.0 / math.sqrt(q.shape[-1])
+        if tau is not None:
+            q = q * tau.view(B, 1, 1, 1)
+        mask = None
+        if delta is not None:
+            mask = (scale * delta).view(B, 1, 1, S).expand(B, H, Lq, S)
+        if self.causal:
+            tri = torch.ones(Lq, S, dtype=torch.bool, device=q.device).triu(1)
+            cm = torch.zeros(Lq, S, dtype=q.dtype, device=q.device).masked_fill(tri, float("-inf"))
+            mask = cm if mask is None else mask + cm
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, scale=scale)
+        return self.out_projection(out.transpose(1, 2).reshape(B, Lq, -1))
+
+
+def _act(name):
+    return F.relu if name == "relu" else F.gelu
+
+
+class EncoderLayer(nn.Module):
+    def __init__(self, d_model, n_heads, d_ff, activation):
+        super().__init__()
+        self.attention = AttentionLayer(d_model, n_heads, causal=False)
+        self.conv1 = nn.Conv1d(d_model, d_ff, 1)
+        self.conv2 = nn.Conv1d(d_ff, d_model, 1)
+        self.norm1, self.norm2 = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        self.activation = _act(activation)
+
+    def forward(self, x, tau, delta):
+        x = self.norm1(x + self.attention(x, x, x, tau, delta))
+        y = self.conv2(self.activation(self.conv1(x.transpose(-1, 1)))).transpose(-1, 1)
+        return self.norm2(x + y)
+
+
+class Encoder(nn.Module):
+    def __init__(self, layers, d_model):
+        super().__init__()
+        self.attn_layers = nn.ModuleList(layers)
+        self.norm = nn.LayerNorm(d_model)
+
+    def forward(self, x, tau, delta):
+        for layer in self.attn_layers:
+            x = layer(x, tau, delta)
+        return self.norm(x)
+
+
+class DecoderLayer(nn.Module):
+    def __init__(self, d_model, n_heads, d_ff, activation):
+        super().__init__()
+        self.self_attention = AttentionLayer(d_model, n_heads, causal=True)
+        self.cross_attention = AttentionLayer(d_model, n_heads, causal=False)
+        self.conv1 = nn.Conv1d(d_model, d_ff, 1)
+        self.conv2 = nn.Conv1d(d_ff, d_model, 1)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(d_model), nn.LayerNorm(d_model), nn.LayerNorm(d_model)
+        self.activation = _act(activation)
+
+    def forward(self, x, cross, tau, delta):
+        x = self.norm1(x + self.self_attention(x, x, x, tau, None))
+        x = self.norm2(x + self.cross_attention(x, cross, cross, tau, delta))
+        y = self.conv2(self.activation(self.conv1(x.transpose(-1, 1)))).transpose(-1, 1)
+        return self.norm3(x + y)
+
+
+class Decoder(nn.Module):
+    def __init__(self, layers, d_model, c_out):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+        self.norm = nn.LayerNorm(d_model)
+        self.projection = nn.Linear(d_model, c_out, bias=True)
+
+    def forward(self, x, cross, tau, delta):
+        for layer in self.layers:
+            x = layer(x, cross, tau, delta)
+        return self.projection(self.norm(x))
+
+
+class NsTransformer(nn.Module):
+    """ns_Transformer.Model.  ``vae=False``: NsDiff f(x) (mu_backbone.py:53-183) returning
+    (pred [B,O,F], dec_out); ``vae=True``: TMDM condition model (tmdm_ns_transformer.py:40-174), eval
+    path (z = posterior mean), returning (pred, dec_out [B,label+O,F], None, None)."""
+
+    def __init__(self, configs, vae=False):
+        super().__init__()
+        self.pred_len, self.seq_len, self.label_len = configs.pred_len, configs.seq_len, configs.label_len
+        self.vae = vae
+        nf = configs.dataset_nf
+        d = configs.d_model
+        self.enc_embedding = DataEmbedding(nf, d)
+        self.dec_embedding = DataEmbedding(nf, d)
+        self.encoder = Encoder([EncoderLayer(d, configs.n_heads, configs.d_ff, configs.activation)
+                                for _ in range(configs.e_layers)], d)
+        self.decoder = Decoder([DecoderLayer(d, configs.n_heads, configs.d_ff, configs.activation)
+                                for _ in range(configs.d_layers)], d, nf)
+        self.tau_learner = Projector(nf, configs.seq_len, configs.p_hidden_dims, configs.p_hidden_layers, 1)
+        self.delta_learner = Projector(nf, configs.seq_len, configs.p_hidden_dims, configs.p_hidden_layers,
+                                       configs.seq_len)
+        if vae:
+            def mlp():
+                return nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, d))
+            self.z_mean, self.z_logvar, self.z_out = mlp(), mlp(), mlp()
+
+    def forward(self, x_enc, x_dec, *unused):
+        if self.vae and len(unused) >= 2:            # TMDM call signature (x_enc, x_mark_enc, x_dec, x_mark_dec)
+            x_dec = unused[0]
+        x_raw = x_enc
+        mean_enc = x_enc.mean(1, keepdim=True)
+        x_enc = x_enc - mean_enc
+        std_enc = torch.sqrt(torch.var(x_enc, dim=1, keepdim=True, unbiased=False) + 1e-5)
+        x_enc = x_enc / std_enc
+        x_dec_new = torch.cat([x_enc[:, -self.label_len:, :], torch.zeros_like(x_dec[:, -self.pred_len:, :])], dim=1)
+        tau = self.tau_learner(x_raw, std_enc).exp()          # B x 1
+        delta = self.delta_learner(x_raw, mean_enc)           # B x S
+        enc_out = self.encoder(self.enc_embedding(x_enc), tau, delta)
+        if self.vae:
+            enc_out = self.z_out(self.z_mean(enc_out))        # eval: z = posterior mean (:133-134)
+        dec_out = self.decoder(self.dec_embedding(x_dec_new), enc_out, tau, delta)
+        dec_out = dec_out * std_enc + mean_enc
+        if self.vae:
+            return dec_out[:, -self.pred_len:, :], dec_out, None, None
+        return dec_out[:, -self.pred_len:, :], dec_out

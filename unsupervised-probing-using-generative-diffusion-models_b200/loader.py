@@ -1,0 +1,56 @@
+"""Model factory and checkpoint loader with the reference's signatures
+(models/models.py:5-32, utils/utils.py:660-689).  Checkpoints are the reference's own files:
+``torch.save({'net_param': dict, 'state_dict': OrderedDict})``."""
+import torch
+
+from . import _lib
+
+NOT_YET = {
+    "DiffSTG": "DiffSTG (graph-conv U-Net sampler) is scheduled after the MLP-denoiser families (SURVEY 8a15)",
+    "DiffusionTS": "DiffusionTS (transformer x0-predictor with Langevin infill) is scheduled after the MLP-denoiser "
+                   "families (SURVEY 8a14)",
+    "NsDiff_spatial": "NsDiff_spatial is not referenced by any shipped configuration (SURVEY 8a11)",
+}
+
+
+def diffusion_models(task_model, net_param, **kwargs):
+    """models/models.py:5-32."""
+    if task_model == "NsDiff":
+        from .nsdiff import NsDiff_model
+        return NsDiff_model(net_param=net_param, train_model_select=kwargs["train_model_select"],
+                            pretrain_f_path=net_param["pretrain_f_path"] if net_param.get("pretrain_f_path") else None,
+                            pretrain_g_path=net_param["pretrain_g_path"] if net_param.get("pretrain_g_path") else None)
+    if task_model == "NsDiff_model_variants":
+        from .nsdiff import NsDiff_model_variants
+        return NsDiff_model_variants(net_param=net_param, train_model_select=kwargs["train_model_select"])
+    if task_model == "TMDM":
+        from .tmdm import TMDM_model
+        return TMDM_model(net_param=net_param)
+    if task_model in NOT_YET:
+        raise NotImplementedError(NOT_YET[task_model])
+    raise ValueError("the definition  don't exit\n\tyou can define it before using it")
+
+
+def load_diffusion_model(path, device, infer_para=None, dataparallel=True, **kwargs):
+    """utils/utils.py:660-689: full-pickle load, ``infer_para`` merged before construction (so it can
+    change n_z_samples / parallel_sample / diffusion_steps), ``module.`` prefixes stripped,
+    ``net_param['device']`` overwritten, strict state-dict load.  -> (model, loaded_net_param)."""
+    device = _lib.require_cuda(device)
+    with open(path, "rb") as f:
+        state = torch.load(f, map_location=lambda storage, loc: storage, weights_only=False)
+    loaded_net_param = state["net_param"]
+    if infer_para is not None:
+        loaded_net_param.update(infer_para)
+    loaded_state_dict = state["state_dict"]
+    if not torch.cuda.device_count() > 1 or not dataparallel:
+        loaded_state_dict = {k.replace("module.", ""): v for k, v in loaded_state_dict.items()}
+    else:
+        # the reference keeps the prefix when several GPUs are visible because it would wrap the model in
+        # DataParallel; this build runs one process per GPU and never wraps, so the prefix always goes
+        loaded_state_dict = {k.replace("module.", ""): v for k, v in loaded_state_dict.items()}
+    loaded_net_param["device"] = device
+    model = diffusion_models(task_model=loaded_net_param["task_model"], net_param=loaded_net_param,
+                             train_model_select=kwargs["train_model_select"]).to(device)
+    model.load_state_dict(loaded_state_dict, strict=True)
+    model = model.to(device)
+    return model, loaded_net_param
