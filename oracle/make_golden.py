@@ -46,7 +46,11 @@ def main():
 
     # ---- shipped checkpoint: copied as data (bench config[0] / smoke / loader tests use it) ----
     for rel in ("ews_results/NsDiff_machine/wo_fx/model_trained",
-                "ews_results/NsDiff_machine/wo_fx/model_trained.yaml"):
+                "ews_results/NsDiff_machine/wo_fx/model_trained.yaml",
+                # training YAMLs only (their checkpoints are absent from the reference tree): they define the
+                # architectures of BASELINE configs 2 and 3, instantiated with seeded random weights
+                "ews_results/model_compare/NsDiff/biomass/model_trained.yaml",
+                "ews_results/model_compare/TMDM/neuronal/model_trained.yaml"):
         dst = os.path.join(GOLD, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)
         shutil.copyfile(os.path.join(ref_harness.REFERENCE_ROOT, rel), dst)

@@ -14,6 +14,7 @@ import torch.nn as nn
 from . import kernels, schedules
 
 EPS = 10e-8  # NsDiff_model.py:37
+FX_ROWS_PER_CALL = 4096
 
 
 class ConditionalLinearParams(nn.Module):
@@ -124,7 +125,7 @@ class _NsDiffBase(nn.Module):
     def packed_weights(self):
         """Packed denoiser blob on the model's device; rebuilt if the parameters changed."""
         w = self.model.diffussion_model.lin1.lin.weight
-        key = (w.device, w._version, self.model.diffussion_model.lin3.lin.weight._version)
+        key = (w.device,) + tuple(p._version for p in self.model.diffussion_model.parameters())
         if self._packed is None or self._packed_key != key:
             sd = {"model." + k: v for k, v in self.model.state_dict().items()}
             rows = schedules.stack_rows(self.model.tables, schedules.NSDIFF_ROWS)
@@ -143,10 +144,13 @@ class _NsDiffBase(nn.Module):
         batch_x = batch_x.to(dev, torch.float32).contiguous()
         y0 = None
         if getattr(self, "cond_pred_model", None) is not None:
-            dec_inp = torch.cat([batch_x[:, -self.label_len:, :],
-                                 torch.zeros(batch_x.size(0), self.pred_len, self.dataset_nf, device=dev)], dim=1)
-            y0, _ = self.cond_pred_model(batch_x, dec_inp)
-            y0 = y0.contiguous()
+            parts = []
+            for r0 in range(0, batch_x.size(0), FX_ROWS_PER_CALL):      # bounds the encoder's activation memory
+                xb = batch_x[r0:r0 + FX_ROWS_PER_CALL]
+                dec_inp = torch.cat([xb[:, -self.label_len:, :],
+                                     torch.zeros(xb.size(0), self.pred_len, self.dataset_nf, device=dev)], dim=1)
+                parts.append(self.cond_pred_model(xb, dec_inp)[0])
+            y0 = torch.cat(parts).contiguous()
         if getattr(self, "cond_pred_model_g", None) is not None:
             gx = self.cond_pred_model_g(batch_x, add_eps=EPS if self.variant_adds_eps else 0.0)
         else:

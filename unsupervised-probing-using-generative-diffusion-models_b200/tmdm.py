@@ -96,7 +96,7 @@ class TMDM_model(nn.Module):
 
     def packed_weights(self):
         w = self.model.diffussion_model.lin1.lin.weight
-        key = (w.device, w._version, self.model.diffussion_model.lin3.lin.weight._version)
+        key = (w.device,) + tuple(p._version for p in self.model.diffussion_model.parameters())
         if self._packed is None or self._packed_key != key:
             sd = {"model." + k: v for k, v in self.model.state_dict().items()}
             rows = schedules.stack_rows(self.model.tables, schedules.TMDM_ROWS)
