@@ -46,7 +46,8 @@ enum {
 /* Sampler implementations (same results within fp32 round-off). */
 enum {
   UPD_IMPL_TCGEN05 = 0,      /* tcgen05/TMEM tensor-core kernel (default, the product path)    */
-  UPD_IMPL_SIMT = 1          /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
+  UPD_IMPL_SIMT = 1,         /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
+  UPD_IMPL_TCGEN05_8W = 2    /* first-generation 8-warp tcgen05 kernel (kept for A/B timing)   */
 };
 
 const char* upd_error_string(int code);

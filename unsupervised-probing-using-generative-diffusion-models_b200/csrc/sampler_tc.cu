@@ -355,7 +355,14 @@ selftest_umma_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
   const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
   const uint32_t abuf = tmem_base + lane_sel, dbuf = abuf + 128u;
   // A row of this thread -> TMEM with the sampler's operand encodings
-  if (mode == 0) {
+  if (mode == 0 && (flags & 4)) {
+    for (int q = 0; q < 8; ++q) {          // 16-column groups: hi words [16q,16q+8), lo words [16q+8,16q+16)
+      uint32_t o[16];
+      for (int j = 0; j < 16; j += 2)
+        tc::split_f16x2(A[tid * K + 16 * q + j], A[tid * K + 16 * q + j + 1], o[j / 2], o[8 + j / 2]);
+      tc::tmem_st16(abuf + 16u * q, o);
+    }
+  } else if (mode == 0) {
     for (int c = 0; c < 4; ++c) {
       uint32_t o[32];
       for (int j = 0; j < 32; j += 2) {
@@ -391,7 +398,8 @@ selftest_umma_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
   const uint32_t lbo = (flags & 1) ? UMMA_SBO : UMMA_LBO, sbo = (flags & 1) ? UMMA_LBO : UMMA_SBO;
   if (tid == 0) {
     tc::fence_after_sync();
-    if (mode == 0) tc::issue_layer_f16x3(tmem_base + 128u, tmem_base, tc::smem_u32(bhi), tc::smem_u32(blo), lbo, sbo);
+    if (mode == 0 && (flags & 4)) tc::issue_layer_f16x3_g16(tmem_base + 128u, tmem_base, tc::smem_u32(bhi), tc::smem_u32(blo), lbo, sbo);
+    else if (mode == 0) tc::issue_layer_f16x3(tmem_base + 128u, tmem_base, tc::smem_u32(bhi), tc::smem_u32(blo), lbo, sbo);
     else tc::issue_layer_tf32x3(tmem_base + 128u, tmem_base, K, tc::smem_u32(bhi), tc::smem_u32(blo), lbo, sbo);
     tc::mma_commit(tc::smem_u32(&sync.mma_bar[0]));
   }

@@ -1,0 +1,387 @@
+// Fused persistent reverse-diffusion sampler on tcgen05 tensor cores, 16-warp version (the product path).
+//
+// Same algorithm and operand encodings as the 8-warp kernel it replaced, re-balanced for the pipe that
+// actually bounds this MLP -- MUFU (514 softplus = 1028 ex2/lg2 per denoiser row-step):
+//
+//   * one CTA per SM, 512 threads = 2 tiles x 8 warps.  A tile is 128 denoiser rows (row = TMEM lane).  Each
+//     TMEM lane quadrant is served by TWO warps that split the 128 hidden columns in halves, so four warps
+//     per scheduler are resident: while a tile waits for its MMAs (or at a barrier) the other tile still has
+//     two warps per scheduler to keep the MUFU pipe fed.  TMEM (512 columns = 2 tiles x 2 buffers x 128)
+//     is what limits the SM to two tiles; warps, not tiles, are what hide latency.
+//   * softplus is evaluated in base 2: L = lg2(1 + ex2(z')), z' = (acc*inv + b) * (e*log2e).  NsDiff
+//     L2-normalises every hidden layer, so the factor ln2 between softplus and L cancels; for TMDM (no
+//     normalisation) and for the heads it is folded into the scalar applied to the next accumulator.
+//     6 instructions per hidden element instead of 9.
+//   * hidden activations are re-encoded IN PLACE over the accumulator columns they came from, 16 columns
+//     at a time: K-slice j of the next A operand = fp16 hi in columns [16j,16j+8), lo in [16j+8,16j+16).
+//   * per-row reductions (sum of squares for F.normalize, head partial sums) are exchanged between the two
+//     column halves through shared memory, riding on the barrier that precedes each MMA issue anyway.
+//   * row state (y, y0_hat, gx), Philox noise, the posterior algebra and the A1 operand belong to the
+//     half-0 warp of each row.
+#include "sampler_params.cuh"
+#include "tc_helpers.cuh"
+#include "upd_common.cuh"
+
+namespace {
+
+constexpr int TC2_THREADS = 512;
+constexpr uint32_t UMMA_LBO = 2048;   // K-adjacent core matrices (layout in upd_common.cuh)
+constexpr uint32_t UMMA_SBO = 128;    // N-adjacent core matrices
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct __align__(8) Tc2Sync {
+  unsigned long long wbar;
+  unsigned long long mma_bar[2];
+  uint32_t tmem_base;
+  uint32_t pad;
+};
+
+// lg2(1 + 2^z): softplus(z*ln2)/ln2.  Two MUFU ops; z is clamped where the caller cannot bound it.
+__device__ __forceinline__ float lg2_1p_ex2(float z) {
+  float u, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(z));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + u));
+  return l;
+}
+
+// One 16-column group of an accumulator -> activations -> fp16 hi/lo A operand, in place.
+// FIRST: layer 1 (bias rides in the GEMM).  CLAMP: guard ex2 overflow where inputs are unbounded.
+template <bool FIRST, bool CLAMP>
+__device__ __forceinline__ float epilogue_group(const uint32_t (&r)[16], uint32_t (&o)[16], const float* __restrict__ e,
+                                                const float* __restrict__ b, float inv) {
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    float4 e4 = *reinterpret_cast<const float4*>(e + j);
+    float4 b4 = FIRST ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b + j);
+    float z0 = FIRST ? __uint_as_float(r[j]) * e4.x : (__uint_as_float(r[j]) * inv + b4.x) * e4.x;
+    float z1 = FIRST ? __uint_as_float(r[j + 1]) * e4.y : (__uint_as_float(r[j + 1]) * inv + b4.y) * e4.y;
+    float z2 = FIRST ? __uint_as_float(r[j + 2]) * e4.z : (__uint_as_float(r[j + 2]) * inv + b4.z) * e4.z;
+    float z3 = FIRST ? __uint_as_float(r[j + 3]) * e4.w : (__uint_as_float(r[j + 3]) * inv + b4.w) * e4.w;
+    if (CLAMP) { z0 = fminf(z0, 126.f); z1 = fminf(z1, 126.f); z2 = fminf(z2, 126.f); z3 = fminf(z3, 126.f); }
+    float h0 = lg2_1p_ex2(z0), h1 = lg2_1p_ex2(z1), h2 = lg2_1p_ex2(z2), h3 = lg2_1p_ex2(z3);
+    ss = fmaf(h0, h0, ss); ss = fmaf(h1, h1, ss); ss = fmaf(h2, h2, ss); ss = fmaf(h3, h3, ss);
+    tc::split_f16x2(h0, h1, o[j / 2], o[8 + j / 2]);
+    tc::split_f16x2(h2, h3, o[j / 2 + 1], o[8 + j / 2 + 1]);
+  }
+  return ss;
+}
+
+// This warp's 64 columns of one hidden layer: 4 groups, TMEM loads software-pipelined one group ahead.
+template <bool FIRST, bool CLAMP>
+__device__ __forceinline__ float epilogue_half(uint32_t buf, const float* __restrict__ e, const float* __restrict__ b,
+                                               float inv) {
+  float ss = 0.f;
+  uint32_t r[16], rn[16], o[16];
+  tc::tmem_ld16(buf, r);
+  tc::wait_ld();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    if (q < 3) tc::tmem_ld16(buf + 16u * (q + 1), rn);
+    ss += epilogue_group<FIRST, CLAMP>(r, o, e + 16 * q, b + 16 * q, inv);
+    tc::tmem_st16(buf + 16u * q, o);
+    if (q < 3) {
+      tc::wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = rn[i];
+    }
+  }
+  return ss;
+}
+
+template <int KIND, int F>
+__global__ void __launch_bounds__(TC2_THREADS, 1)
+sampler_tc2_kernel(const UpdSamplerParams p) {
+  constexpr bool NS = (KIND == 0);
+  constexpr int IN = NS ? 3 * F : 2 * F;
+  constexpr int K1 = ((IN + 1 + 7) / 8) * 8;
+  const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
+  extern __shared__ __align__(128) unsigned char smem[];
+  auto sf = [&](uint32_t off) { return reinterpret_cast<float*>(smem + off); };
+  constexpr uint32_t STEP_BYTES = NS ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
+  const uint32_t steps_off = upd_align128(L.tc_image_bytes);
+  const uint32_t xch_off = upd_align128(steps_off + STEP_BYTES * p.T);
+  // exchange area per tile: ssx[3 layers][2 halves][128 rows], headx[2F][128 rows]
+  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 2 * UPD_MAX_F * 128;
+  const uint32_t sync_off = upd_align128(xch_off + 2 * XCH_TILE_FLOATS * 4);
+  Tc2Sync* sync = reinterpret_cast<Tc2Sync*>(smem + sync_off);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    tc::mbar_init(tc::smem_u32(&sync->wbar), 1);
+    tc::mbar_init(tc::smem_u32(&sync->mma_bar[0]), 1);
+    tc::mbar_init(tc::smem_u32(&sync->mma_bar[1]), 1);
+    tc::fence_mbar_init();
+  }
+  if (warp == 0) tc::tmem_alloc<512>(tc::smem_u32(&sync->tmem_base));
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem_base = sync->tmem_base;
+  if (tid == 0) {
+    const uint32_t bar = tc::smem_u32(&sync->wbar);
+    tc::mbar_expect_tx(bar, L.tc_image_bytes);
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(p.packed);
+    for (uint32_t off = 0; off < L.tc_image_bytes; off += 16384u) {
+      uint32_t n = L.tc_image_bytes - off < 16384u ? L.tc_image_bytes - off : 16384u;
+      tc::bulk_g2s(tc::smem_u32(smem + off), src + off, n, bar);
+    }
+  }
+  tc::mbar_wait(tc::smem_u32(&sync->wbar), 0);
+  // step-embedding tables to base 2 (e * log2e), per-step posterior scalars: once per CTA
+  for (int i = tid; i < L.TE * 128; i += TC2_THREADS) {
+    sf(L.e1)[i] *= LOG2E; sf(L.e2)[i] *= LOG2E; sf(L.e3)[i] *= LOG2E;
+  }
+  if (tid < p.T) {
+    if (NS) reinterpret_cast<UpdNsStep*>(smem + steps_off)[tid] = upd_ns_step(sf(L.sched), p.T, tid);
+    else reinterpret_cast<UpdTmStep*>(smem + steps_off)[tid] = upd_tm_step(sf(L.sched), p.T, tid);
+  }
+  __syncthreads();
+
+  const int tile_id = warp >> 3, half = (warp >> 2) & 1, quad = warp & 3;
+  const int trow = quad * 32 + lane;                        // row within the tile = TMEM lane
+  const bool owner = (half == 0);
+  const bool issuer = owner && quad == 0 && lane == 0;
+  const uint32_t col0 = (uint32_t)tile_id * 256u;
+  const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
+  const uint32_t buf0 = tmem_base + lane_sel + col0, buf1 = buf0 + 128u;        // whole-row views (owner A1 write)
+  const uint32_t my0 = buf0 + 64u * half, my1 = buf1 + 64u * half;              // this warp's column half
+  const uint32_t mma0 = tmem_base + col0, mma1 = mma0 + 128u;
+  const uint32_t bar = tc::smem_u32(&sync->mma_bar[tile_id]);
+  const uint32_t img = tc::smem_u32(smem);
+  float* ssx = sf(xch_off) + tile_id * XCH_TILE_FLOATS;     // [3][2][128]
+  float* headx = ssx + 3 * 2 * 128;                         // [2F][128]
+  const int full_bar = 1 + tile_id, head_bar = 3 + tile_id;
+  const float inv_ws2 = sf(L.scales)[0] * (NS ? 1.0f : LN2), inv_ws3 = sf(L.scales)[1] * (NS ? 1.0f : LN2);
+  const float* e1 = sf(L.e1) + 64 * half;
+  const float* e2 = sf(L.e2) + 64 * half;
+  const float* e3 = sf(L.e3) + 64 * half;
+  const float* b2 = sf(L.b2) + 64 * half;
+  const float* b3 = sf(L.b3) + 64 * half;
+  const float* w4 = sf(L.w4) + 64 * half;
+  const float* wsg = sf(L.ws) + 64 * half;
+  uint32_t phase = 0;
+
+  const long long n_tiles = (p.n_rows + 127) / 128;
+  for (long long tile = (long long)blockIdx.x * 2 + tile_id; tile < n_tiles; tile += (long long)gridDim.x * 2) {
+    const long long row = tile * 128 + trow;
+    const bool live = row < p.n_rows;
+    UpdRowIndex ix = upd_row_index(p, live ? row : p.n_rows - 1);
+    float y[F], y0h[F], gxv[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) { y[f] = 0.f; y0h[f] = 0.f; gxv[f] = 1.f; }
+    if (owner) {
+      const long long cidx = (ix.r0 * p.O + ix.o) * F;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        y0h[f] = p.y0_hat ? p.y0_hat[cidx + f] : 0.f;
+        gxv[f] = NS ? p.gx[cidx + f] : 1.f;
+        float z = upd_draw(p, ix, f, F, 0);
+        y[f] = NS ? sqrtf(gxv[f]) * z + y0h[f] : z + y0h[f];       // nsdiff_utils.py:274 / tmdm_diffusion_utils.py:110
+      }
+    }
+    for (int t = p.T - 1; t >= 0; --t) {
+      // ---------------- layer 1: A1 = [y | y0_hat | gx | 1 | 0] as tf32 hi/lo (owner warps) ----------------
+      if (owner) {
+        float in[K1];
+#pragma unroll
+        for (int i = 0; i < K1; ++i) in[i] = 0.f;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          in[f] = y[f];
+          in[F + f] = y0h[f];
+          if (NS) in[2 * F + f] = gxv[f];
+        }
+        in[IN] = 1.0f;
+        if (K1 == 8) {
+          uint32_t a[16];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float hi = tc::to_tf32(in[i]);
+            a[i] = __float_as_uint(hi);
+            a[8 + i] = __float_as_uint(tc::to_tf32(in[i] - hi));
+          }
+          tc::tmem_st16(buf0, a);
+        } else {
+          uint32_t a[32];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float v = in[i % K1];
+            float hi = tc::to_tf32(v);
+            a[i] = __float_as_uint(hi);
+            a[16 + i] = __float_as_uint(tc::to_tf32(v - hi));
+          }
+          tc::tmem_st32(buf0, a);
+        }
+        tc::wait_st();
+      }
+      tc::fence_before_sync();
+      tc::named_bar_sync(full_bar, 256);
+      if (issuer) {
+        tc::fence_after_sync();
+        tc::issue_layer_tf32x3(mma1, mma0, K1, img + L.u1hi, img + L.u1lo, UMMA_LBO, UMMA_SBO);
+        tc::mma_commit(bar);
+      }
+      tc::mbar_wait(bar, phase); phase ^= 1u;
+      tc::fence_after_sync();
+
+      // ---------------- layer 1 epilogue -> A2 (in place, buf1); layer 2 ----------------
+      float ss = epilogue_half<true, true>(my1, e1 + t * 128, nullptr, 1.f);
+      if (NS) ssx[(0 * 2 + half) * 128 + trow] = ss;
+      tc::wait_st();
+      tc::fence_before_sync();
+      tc::named_bar_sync(full_bar, 256);
+      if (issuer) {
+        tc::fence_after_sync();
+        tc::issue_layer_f16x3_g16(mma0, mma1, img + L.u2hi, img + L.u2lo, UMMA_LBO, UMMA_SBO);
+        tc::mma_commit(bar);
+      }
+      float inv = inv_ws2;
+      if (NS) inv = inv_ws2 / fmaxf(sqrtf(ssx[0 * 128 + trow] + ssx[1 * 128 + trow]), 1e-12f);   // F.normalize, folded past the GEMM
+      tc::mbar_wait(bar, phase); phase ^= 1u;
+      tc::fence_after_sync();
+
+      // ---------------- layer 2 epilogue -> A3 (in place, buf0); layer 3 ----------------
+      ss = epilogue_half<false, !NS>(my0, e2 + t * 128, b2, inv);
+      if (NS) ssx[(1 * 2 + half) * 128 + trow] = ss;
+      tc::wait_st();
+      tc::fence_before_sync();
+      tc::named_bar_sync(full_bar, 256);
+      if (issuer) {
+        tc::fence_after_sync();
+        tc::issue_layer_f16x3_g16(mma1, mma0, img + L.u3hi, img + L.u3lo, UMMA_LBO, UMMA_SBO);
+        tc::mma_commit(bar);
+      }
+      inv = inv_ws3;
+      if (NS) inv = inv_ws3 / fmaxf(sqrtf(ssx[2 * 128 + trow] + ssx[3 * 128 + trow]), 1e-12f);
+      tc::mbar_wait(bar, phase); phase ^= 1u;
+      tc::fence_after_sync();
+
+      // ---------------- layer 3 epilogue + heads (denoise.py:50 / tmdm_model.py:63) ----------------
+      float pe[F], ps[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) { pe[f] = 0.f; ps[f] = 0.f; }
+      const float* e3t = e3 + t * 128;
+      if (NS) {
+        // pass 1: L3 kept in TMEM as fp32 (in place), partial sum of squares
+        ss = 0.f;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(my1 + 16u * q, r);
+          tc::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float h = lg2_1p_ex2((__uint_as_float(r[j]) * inv + b3[16 * q + j]) * e3t[16 * q + j]);
+            ss = fmaf(h, h, ss);
+            r[j] = __float_as_uint(h);
+          }
+          tc::tmem_st16(my1 + 16u * q, r);
+        }
+        ssx[(2 * 2 + half) * 128 + trow] = ss;
+        tc::wait_st();
+        tc::named_bar_sync(full_bar, 256);
+        // pass 2: t = L3/||L3|| * log2e;  eps ~ sum w4*t,  sigma ~ sum ws*lg2(1+2^t)   (ln2 applied at the end)
+        const float inv3 = LOG2E / fmaxf(sqrtf(ssx[4 * 128 + trow] + ssx[5 * 128 + trow]), 1e-12f);
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(my1 + 16u * q, r);
+          tc::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float tt = __uint_as_float(r[j]) * inv3;
+            float sp = lg2_1p_ex2(tt);
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+              pe[f] = fmaf(w4[f * 128 + 16 * q + j], tt, pe[f]);
+              ps[f] = fmaf(wsg[f * 128 + 16 * q + j], sp, ps[f]);
+            }
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(my1 + 16u * q, r);
+          tc::wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float h = lg2_1p_ex2(fminf((__uint_as_float(r[j]) * inv + b3[16 * q + j]) * e3t[16 * q + j], 126.f));
+#pragma unroll
+            for (int f = 0; f < F; ++f) pe[f] = fmaf(w4[f * 128 + 16 * q + j], h, pe[f]);
+          }
+        }
+      }
+      if (!owner) {
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          headx[f * 128 + trow] = pe[f];
+          if (NS) headx[(F + f) * 128 + trow] = ps[f];
+        }
+        __threadfence_block();
+        tc::named_bar_arrive(head_bar, 256);
+      } else {
+        tc::named_bar_sync(head_bar, 256);
+        // ---------------- posterior update (owner warps) ----------------
+        const bool last = (t == 0);
+        if (NS) {
+          const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float eps = (pe[f] + headx[f * 128 + trow]) * LN2 + sf(L.b4)[f];
+            float sig = upd_softplus_accurate((ps[f] + headx[(F + f) * 128 + trow]) * LN2 + sf(L.bs)[f]);
+            float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
+            y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, z, last);
+          }
+        } else {
+          const UpdTmStep st = reinterpret_cast<const UpdTmStep*>(smem + steps_off)[t];
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float eps = (pe[f] + headx[f * 128 + trow]) * LN2 + sf(L.b4)[f];
+            float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
+            y[f] = upd_tm_update(st, y[f], y0h[f], eps, z, last);
+          }
+        }
+      }
+    }
+    if (owner && live) {
+#pragma unroll
+      for (int f = 0; f < F; ++f) p.out[row * F + f] = y[f];
+    }
+  }
+
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
+}
+
+template <int KIND, int F>
+cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
+  const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
+  constexpr uint32_t STEP_BYTES = (KIND == 0) ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
+  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 2 * UPD_MAX_F * 128;
+  size_t smem = upd_align128(upd_align128(upd_align128(L.tc_image_bytes) + STEP_BYTES * p.T) + 2 * XCH_TILE_FLOATS * 4) +
+                sizeof(Tc2Sync) + 128;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  auto kern = sampler_tc2_kernel<KIND, F>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  long long n_tiles = (p.n_rows + 127) / 128;
+  long long ctas = (n_tiles + 1) / 2;
+  int grid = (int)(ctas < sms ? ctas : sms);
+  if (grid < 1) grid = 1;
+  kern<<<grid, TC2_THREADS, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t upd_launch_sampler_tc2(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream) {
+#define UPD_CASE(KK, FF) if (kind == KK && F == FF) return launch<KK, FF>(p, sms, stream);
+  UPD_CASE(0, 1) UPD_CASE(0, 2) UPD_CASE(0, 3) UPD_CASE(0, 4)
+  UPD_CASE(1, 1) UPD_CASE(1, 2) UPD_CASE(1, 3) UPD_CASE(1, 4)
+#undef UPD_CASE
+  return cudaErrorInvalidValue;
+}

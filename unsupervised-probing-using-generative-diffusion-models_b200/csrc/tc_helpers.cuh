@@ -62,6 +62,11 @@ __device__ __forceinline__ void named_bar_sync(int id, int n) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
 }
 
+// Producer side of a named barrier: signal without waiting (consumers use named_bar_sync with the same count).
+__device__ __forceinline__ void named_bar_arrive(int id, int n) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, SWIZZLE_NONE ("interleave"): core matrix = 8 rows x 16 B
 // stored contiguously (128 B); LBO = byte distance between core matrices adjacent in K,
@@ -115,6 +120,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -160,6 +173,21 @@ __device__ __forceinline__ void issue_layer_f16x3(uint32_t d_tmem, uint32_t a_tm
   for (int j = 0; j < 8; ++j) {
     uint32_t a_hi = a_tmem + 32u * (j >> 1) + 8u * (j & 1);
     uint32_t a_lo = a_hi + 16u;
+    uint64_t b_hi = smem_desc(bhi_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
+    uint64_t b_lo = smem_desc(blo_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
+    mma_f16_ts(d_tmem, a_lo, b_hi, IDESC_F16_M128_N128, j > 0);
+    mma_f16_ts(d_tmem, a_hi, b_lo, IDESC_F16_M128_N128, true);
+    mma_f16_ts(d_tmem, a_hi, b_hi, IDESC_F16_M128_N128, true);
+  }
+}
+// Same contraction with the 16-column in-place A layout of the 16-warp sampler: K-slice j = fp16 hi words in
+// columns [16j,16j+8), lo words in [16j+8,16j+16).
+__device__ __forceinline__ void issue_layer_f16x3_g16(uint32_t d_tmem, uint32_t a_tmem, uint32_t bhi_smem,
+                                                      uint32_t blo_smem, uint32_t lbo, uint32_t sbo) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    uint32_t a_hi = a_tmem + 16u * j;
+    uint32_t a_lo = a_hi + 8u;
     uint64_t b_hi = smem_desc(bhi_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
     uint64_t b_lo = smem_desc(blo_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
     mma_f16_ts(d_tmem, a_lo, b_hi, IDESC_F16_M128_N128, j > 0);
