@@ -299,7 +299,7 @@ def run_own_arm(args, rank, world, local_rank):
                      "note": "algorithmic FLOPs = 2*33408 MAC per denoiser row-step (SURVEY 8a7); the MLP is MUFU-bound "
                              "(514 softplus per row-step), see DESIGN.md"},
     }
-    if world == 1:
+    if world == 1 and not os.environ.get("UPD_BENCH_SKIP_CPU"):   # (set only when the run is wrapped in ncu)
         threads = os.cpu_count() or 1
         rows = 100
         rate, sec = cpu_reference_rate(cfg, rows=rows, n_steps=2, n_warm=1, threads=threads)

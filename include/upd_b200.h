@@ -46,8 +46,7 @@ enum {
 /* Sampler implementations (same results within fp32 round-off). */
 enum {
   UPD_IMPL_TCGEN05 = 0,      /* tcgen05/TMEM tensor-core kernel (default, the product path)    */
-  UPD_IMPL_SIMT = 1,         /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
-  UPD_IMPL_TCGEN05_8W = 2    /* first-generation 8-warp tcgen05 kernel (kept for A/B timing)   */
+  UPD_IMPL_SIMT = 1          /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
 };
 
 const char* upd_error_string(int code);
@@ -163,7 +162,7 @@ int upd_sigma_estimation(const UpdSigmaWeights* w_dev_ptrs, const float* x_dev, 
 
 /* Known-answer self test of the tcgen05 descriptors this library relies on: D[128,N] = A[128,K] * B[N,K]^T
  * with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K=128; mode 1: tf32 hi/lo
- * 3-pass, K=8*k8).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */
+ * 3-pass, K=8*k8); flags bit 0 swaps the descriptor's LBO/SBO (negative control: must give a wrong D).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */
 int upd_selftest_umma(const float* a_dev, const float* b_dev, float* d_dev, int K, int mode, int flags,
                       void* stream);
 

@@ -43,12 +43,12 @@ def _pack_ns(sd, F, T=20, schedule="linear"):
     return kernels.pack_denoiser(sd, kernels.KIND_NSDIFF, F, T, schedules.stack_rows(tab, schedules.NSDIFF_ROWS), _dev())
 
 
-IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param(2, id="tcgen05_8w")]
+IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05")]
 
 
 # ---------------------------------------------------------------- tcgen05 descriptor known-answer
-@pytest.mark.parametrize("mode,K,flags", [(0, 128, 0), (0, 128, 4), (1, 8, 0), (1, 16, 0)])
-def test_umma_selftest(mode, K, flags):
+@pytest.mark.parametrize("mode,K", [(0, 128), (1, 8), (1, 16)])
+def test_umma_selftest(mode, K):
     kernels, _ = _k()
     g = torch.Generator().manual_seed(5 + K)
     a = torch.randn(128, K, generator=g)
@@ -57,7 +57,7 @@ def test_umma_selftest(mode, K, flags):
     a += torch.arange(128).float().view(-1, 1) * 0.01
     b += torch.arange(K).float().view(1, -1) * 0.02
     ref = a.double() @ b.double().t()
-    d = kernels.selftest_umma(a.to(_dev()), b.to(_dev()), mode=mode, flags=flags).cpu().double()
+    d = kernels.selftest_umma(a.to(_dev()), b.to(_dev()), mode=mode, flags=0).cpu().double()
     scale = (a.double().abs() @ b.double().abs().t())
     err = ((d - ref).abs() / scale).max().item()
     assert err < 4e-6, "tcgen05 3-pass contraction off: {:.3e}".format(err)

@@ -16,7 +16,7 @@ SYMBOLS = (
 )
 
 KIND_NSDIFF, KIND_TMDM = 0, 1
-IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_8W = 0, 1, 2
+IMPL_TCGEN05, IMPL_SIMT = 0, 1
 _fp = ctypes.POINTER(ctypes.c_float)
 
 

@@ -1,31 +1,38 @@
-// Fused persistent reverse-diffusion sampler on tcgen05 tensor cores (UPD_IMPL_TCGEN05).
+// Fused persistent reverse-diffusion sampler on tcgen05 tensor cores (UPD_IMPL_TCGEN05, the product path).
 //
-// One CTA per SM, 256 threads = two independent warpgroups.  A warpgroup owns a tile of 128
-// denoiser rows (row = one (window,row,sample,position), thread = row = TMEM lane) and carries it
-// through all T reverse steps without leaving the SM:
+// One launch carries every (window,row,sample,position) of a sweep through all T reverse steps without leaving
+// the SM: weights resident in shared memory (bulk-copied once per CTA), activations ping-ponging between two
+// TMEM buffers, three chained GEMMs per step on tcgen05 (A from TMEM, B from shared memory, fp16/tf32 hi-lo
+// split with three passes = fp32-grade accuracy), NsDiff / TMDM posterior algebra and Philox noise in registers.
+// It is organised around the pipe that actually bounds this MLP -- MUFU (514 softplus = 1028 ex2/lg2 per
+// denoiser row-step) -- not the tensor pipe:
 //
-//   weights  : lin2/lin3 as fp16 hi/lo (x wscale) and lin1|bias as tf32 hi/lo, in UMMA K-major
-//              core-matrix layout, plus the fp32 tables, bulk-copied (TMA 1-D) into shared memory
-//              once per CTA and resident for the whole launch.
-//   per step : A1 = [y | y0_hat | gx | 1] (tf32 hi/lo) -> TMEM;  D1 = A1 * W1'      (3 tf32 MMAs / K-slice)
-//              epilogue: e[t] * D -> softplus -> sum of squares -> fp16 hi/lo, written IN PLACE
-//                        over the accumulator columns it was read from (A operand of the next layer)
-//              D2 = A2 * W2', D3 = A3 * W3'   (A from TMEM, B from smem, 24 fp16 MMAs each = hi*hi+lo*hi+hi*lo)
-//              the L2 normalisation of layer l is applied as a scalar on the accumulator of layer l+1
-//              heads (eps, sigma) as fp32 FMAs on the thread's own row; NsDiff/TMDM posterior algebra;
-//              Philox (or injected) Gaussian noise.
-//   TMEM     : 512 columns = 2 tiles x 2 ping-pong buffers x 128 columns.
-// While one warpgroup waits for its MMAs the other one runs its softplus epilogue, so the MUFU pipe
-// (the real bound of this MLP: 514 softplus per row-step) and the tensor pipe overlap.
+//   * one CTA per SM, 512 threads = 2 tiles x 8 warps.  A tile is 128 denoiser rows (row = TMEM lane).  Each
+//     TMEM lane quadrant is served by TWO warps that split the 128 hidden columns in halves, so four warps
+//     per scheduler are resident: while a tile waits for its MMAs (or at a barrier) the other tile still has
+//     two warps per scheduler to keep the MUFU pipe fed.  TMEM (512 columns = 2 tiles x 2 buffers x 128)
+//     is what limits the SM to two tiles; warps, not tiles, are what hide latency.
+//   * softplus is evaluated in base 2: L = lg2(1 + ex2(z')), z' = (acc*inv + b) * (e*log2e).  NsDiff
+//     L2-normalises every hidden layer, so the factor ln2 between softplus and L cancels; for TMDM (no
+//     normalisation) and for the heads it is folded into the scalar applied to the next accumulator.
+//     6 instructions per hidden element instead of 9.
+//   * hidden activations are re-encoded IN PLACE over the accumulator columns they came from, 16 columns
+//     at a time: K-slice j of the next A operand = fp16 hi in columns [16j,16j+8), lo in [16j+8,16j+16).
+//   * per-row reductions (sum of squares for F.normalize, head partial sums) are exchanged between the two
+//     column halves through shared memory, riding on the barrier that precedes each MMA issue anyway.
+//   * row state (y, y0_hat, gx), Philox noise, the posterior algebra and the A1 operand belong to the
+//     half-0 warp of each row.
 #include "sampler_params.cuh"
 #include "tc_helpers.cuh"
 #include "upd_common.cuh"
 
 namespace {
 
-constexpr int TC_THREADS = 256;
-constexpr uint32_t UMMA_LBO = 2048;   // K-adjacent core matrices (see upd_common.cuh layout)
+constexpr int TC_THREADS = 512;
+constexpr uint32_t UMMA_LBO = 2048;   // K-adjacent core matrices (layout in upd_common.cuh)
 constexpr uint32_t UMMA_SBO = 128;    // N-adjacent core matrices
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
 
 struct __align__(8) TcSync {
   unsigned long long wbar;
@@ -34,32 +41,55 @@ struct __align__(8) TcSync {
   uint32_t pad;
 };
 
-// e[t] * acc (+bias, *inv) -> softplus -> ss; result re-encoded in place as the next A operand.
-template <bool FIRST>
-__device__ __forceinline__ float epilogue_to_a(uint32_t buf, const float* __restrict__ e, const float* __restrict__ b,
+// lg2(1 + 2^z): softplus(z*ln2)/ln2.  Two MUFU ops; z is clamped where the caller cannot bound it.
+__device__ __forceinline__ float lg2_1p_ex2(float z) {
+  float u, l;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(z));
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + u));
+  return l;
+}
+
+// One 16-column group of an accumulator -> activations -> fp16 hi/lo A operand, in place.
+// FIRST: layer 1 (bias rides in the GEMM).  CLAMP: guard ex2 overflow where inputs are unbounded.
+template <bool FIRST, bool CLAMP>
+__device__ __forceinline__ float epilogue_group(const uint32_t (&r)[16], uint32_t (&o)[16], const float* __restrict__ e,
+                                                const float* __restrict__ b, float inv) {
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    float4 e4 = *reinterpret_cast<const float4*>(e + j);
+    float4 b4 = FIRST ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b + j);
+    float z0 = FIRST ? __uint_as_float(r[j]) * e4.x : (__uint_as_float(r[j]) * inv + b4.x) * e4.x;
+    float z1 = FIRST ? __uint_as_float(r[j + 1]) * e4.y : (__uint_as_float(r[j + 1]) * inv + b4.y) * e4.y;
+    float z2 = FIRST ? __uint_as_float(r[j + 2]) * e4.z : (__uint_as_float(r[j + 2]) * inv + b4.z) * e4.z;
+    float z3 = FIRST ? __uint_as_float(r[j + 3]) * e4.w : (__uint_as_float(r[j + 3]) * inv + b4.w) * e4.w;
+    if (CLAMP) { z0 = fminf(z0, 126.f); z1 = fminf(z1, 126.f); z2 = fminf(z2, 126.f); z3 = fminf(z3, 126.f); }
+    float h0 = lg2_1p_ex2(z0), h1 = lg2_1p_ex2(z1), h2 = lg2_1p_ex2(z2), h3 = lg2_1p_ex2(z3);
+    ss = fmaf(h0, h0, ss); ss = fmaf(h1, h1, ss); ss = fmaf(h2, h2, ss); ss = fmaf(h3, h3, ss);
+    tc::split_f16x2(h0, h1, o[j / 2], o[8 + j / 2]);
+    tc::split_f16x2(h2, h3, o[j / 2 + 1], o[8 + j / 2 + 1]);
+  }
+  return ss;
+}
+
+// This warp's 64 columns of one hidden layer: 4 groups, TMEM loads software-pipelined one group ahead.
+template <bool FIRST, bool CLAMP>
+__device__ __forceinline__ float epilogue_half(uint32_t buf, const float* __restrict__ e, const float* __restrict__ b,
                                                float inv) {
   float ss = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 4; ++c) {
-    uint32_t r[32], o[32];
-    tc::tmem_ld32(buf + 32u * c, r);
-    tc::wait_ld();
+  uint32_t r[16], rn[16], o[16];
+  tc::tmem_ld16(buf, r);
+  tc::wait_ld();
 #pragma unroll
-    for (int j = 0; j < 32; j += 4) {
-      float4 e4 = *reinterpret_cast<const float4*>(e + 32 * c + j);
-      float4 b4 = FIRST ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b + 32 * c + j);
-      float a0 = __uint_as_float(r[j]), a1 = __uint_as_float(r[j + 1]), a2 = __uint_as_float(r[j + 2]),
-            a3 = __uint_as_float(r[j + 3]);
-      float z0 = FIRST ? a0 * e4.x : (a0 * inv + b4.x) * e4.x;
-      float z1 = FIRST ? a1 * e4.y : (a1 * inv + b4.y) * e4.y;
-      float z2 = FIRST ? a2 * e4.z : (a2 * inv + b4.z) * e4.z;
-      float z3 = FIRST ? a3 * e4.w : (a3 * inv + b4.w) * e4.w;
-      float h0 = upd_softplus(z0), h1 = upd_softplus(z1), h2 = upd_softplus(z2), h3 = upd_softplus(z3);
-      ss = fmaf(h0, h0, ss); ss = fmaf(h1, h1, ss); ss = fmaf(h2, h2, ss); ss = fmaf(h3, h3, ss);
-      tc::split_f16x2(h0, h1, o[j / 2], o[16 + j / 2]);
-      tc::split_f16x2(h2, h3, o[j / 2 + 1], o[16 + j / 2 + 1]);
+  for (int q = 0; q < 4; ++q) {
+    if (q < 3) tc::tmem_ld16(buf + 16u * (q + 1), rn);
+    ss += epilogue_group<FIRST, CLAMP>(r, o, e + 16 * q, b + 16 * q, inv);
+    tc::tmem_st16(buf + 16u * q, o);
+    if (q < 3) {
+      tc::wait_ld();
+#pragma unroll
+      for (int i = 0; i < 16; ++i) r[i] = rn[i];
     }
-    tc::tmem_st32(buf + 32u * c, o);
   }
   return ss;
 }
@@ -72,13 +102,16 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   constexpr int K1 = ((IN + 1 + 7) / 8) * 8;
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
   extern __shared__ __align__(128) unsigned char smem[];
-  auto sf = [&](uint32_t off) { return reinterpret_cast<const float*>(smem + off); };
-  const uint32_t steps_off = upd_align128(L.tc_image_bytes);
+  auto sf = [&](uint32_t off) { return reinterpret_cast<float*>(smem + off); };
   constexpr uint32_t STEP_BYTES = NS ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
-  const uint32_t sync_off = upd_align128(steps_off + STEP_BYTES * p.T);
+  const uint32_t steps_off = upd_align128(L.tc_image_bytes);
+  const uint32_t xch_off = upd_align128(steps_off + STEP_BYTES * p.T);
+  // exchange area per tile: ssx[3 layers][2 halves][128 rows], headx[2F][128 rows]
+  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 2 * UPD_MAX_F * 128;
+  const uint32_t sync_off = upd_align128(xch_off + 2 * XCH_TILE_FLOATS * 4);
   TcSync* sync = reinterpret_cast<TcSync*>(smem + sync_off);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     tc::mbar_init(tc::smem_u32(&sync->wbar), 1);
     tc::mbar_init(tc::smem_u32(&sync->mma_bar[0]), 1);
@@ -100,42 +133,61 @@ sampler_tc_kernel(const UpdSamplerParams p) {
     }
   }
   tc::mbar_wait(tc::smem_u32(&sync->wbar), 0);
-  // per-step posterior scalars, computed once per CTA
+  // step-embedding tables to base 2 (e * log2e), per-step posterior scalars: once per CTA
+  for (int i = tid; i < L.TE * 128; i += TC_THREADS) {
+    sf(L.e1)[i] *= LOG2E; sf(L.e2)[i] *= LOG2E; sf(L.e3)[i] *= LOG2E;
+  }
   if (tid < p.T) {
     if (NS) reinterpret_cast<UpdNsStep*>(smem + steps_off)[tid] = upd_ns_step(sf(L.sched), p.T, tid);
     else reinterpret_cast<UpdTmStep*>(smem + steps_off)[tid] = upd_tm_step(sf(L.sched), p.T, tid);
   }
   __syncthreads();
 
-  const int wg = tid >> 7, wtid = tid & 127, quad = (tid >> 5) & 3;
-  const uint32_t col0 = (uint32_t)wg * 256u;
+  const int tile_id = warp >> 3, half = (warp >> 2) & 1, quad = warp & 3;
+  const int trow = quad * 32 + lane;                        // row within the tile = TMEM lane
+  const bool owner = (half == 0);
+  const bool issuer = owner && quad == 0 && lane == 0;
+  const uint32_t col0 = (uint32_t)tile_id * 256u;
   const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-  const uint32_t buf0 = tmem_base + lane_sel + col0, buf1 = buf0 + 128u;          // this warp's lanes
-  const uint32_t mma0 = tmem_base + col0, mma1 = mma0 + 128u;                      // lane 0 (MMA operands)
-  const uint32_t bar = tc::smem_u32(&sync->mma_bar[wg]);
+  const uint32_t buf0 = tmem_base + lane_sel + col0, buf1 = buf0 + 128u;        // whole-row views (owner A1 write)
+  const uint32_t my0 = buf0 + 64u * half, my1 = buf1 + 64u * half;              // this warp's column half
+  const uint32_t mma0 = tmem_base + col0, mma1 = mma0 + 128u;
+  const uint32_t bar = tc::smem_u32(&sync->mma_bar[tile_id]);
   const uint32_t img = tc::smem_u32(smem);
-  const float inv_ws2 = sf(L.scales)[0], inv_ws3 = sf(L.scales)[1];
+  float* ssx = sf(xch_off) + tile_id * XCH_TILE_FLOATS;     // [3][2][128]
+  float* headx = ssx + 3 * 2 * 128;                         // [2F][128]
+  const int full_bar = 1 + tile_id, head_bar = 3 + tile_id;
+  const float inv_ws2 = sf(L.scales)[0] * (NS ? 1.0f : LN2), inv_ws3 = sf(L.scales)[1] * (NS ? 1.0f : LN2);
+  const float* e1 = sf(L.e1) + 64 * half;
+  const float* e2 = sf(L.e2) + 64 * half;
+  const float* e3 = sf(L.e3) + 64 * half;
+  const float* b2 = sf(L.b2) + 64 * half;
+  const float* b3 = sf(L.b3) + 64 * half;
+  const float* w4 = sf(L.w4) + 64 * half;
+  const float* wsg = sf(L.ws) + 64 * half;
   uint32_t phase = 0;
 
   const long long n_tiles = (p.n_rows + 127) / 128;
-  for (long long tile = (long long)blockIdx.x * 2 + wg; tile < n_tiles; tile += (long long)gridDim.x * 2) {
-    const long long row = tile * 128 + wtid;
+  for (long long tile = (long long)blockIdx.x * 2 + tile_id; tile < n_tiles; tile += (long long)gridDim.x * 2) {
+    const long long row = tile * 128 + trow;
     const bool live = row < p.n_rows;
-    const UpdRowIndex ix = upd_row_index(p, live ? row : p.n_rows - 1);
+    UpdRowIndex ix = upd_row_index(p, live ? row : p.n_rows - 1);
     float y[F], y0h[F], gxv[F];
-    {
+#pragma unroll
+    for (int f = 0; f < F; ++f) { y[f] = 0.f; y0h[f] = 0.f; gxv[f] = 1.f; }
+    if (owner) {
       const long long cidx = (ix.r0 * p.O + ix.o) * F;
 #pragma unroll
       for (int f = 0; f < F; ++f) {
         y0h[f] = p.y0_hat ? p.y0_hat[cidx + f] : 0.f;
         gxv[f] = NS ? p.gx[cidx + f] : 1.f;
         float z = upd_draw(p, ix, f, F, 0);
-        y[f] = NS ? sqrtf(gxv[f]) * z + y0h[f] : z + y0h[f];     // nsdiff_utils.py:274 / tmdm_diffusion_utils.py:110
+        y[f] = NS ? sqrtf(gxv[f]) * z + y0h[f] : z + y0h[f];       // nsdiff_utils.py:274 / tmdm_diffusion_utils.py:110
       }
     }
     for (int t = p.T - 1; t >= 0; --t) {
-      // ---------------- layer 1: A1 = [y | y0_hat | gx | 1 | 0] as tf32 hi/lo ----------------
-      {
+      // ---------------- layer 1: A1 = [y | y0_hat | gx | 1 | 0] as tf32 hi/lo (owner warps) ----------------
+      if (owner) {
         float in[K1];
 #pragma unroll
         for (int i = 0; i < K1; ++i) in[i] = 0.f;
@@ -166,11 +218,11 @@ sampler_tc_kernel(const UpdSamplerParams p) {
           }
           tc::tmem_st32(buf0, a);
         }
+        tc::wait_st();
       }
-      tc::wait_st();
       tc::fence_before_sync();
-      tc::named_bar_sync(1 + wg, 128);
-      if (wtid == 0) {
+      tc::named_bar_sync(full_bar, 256);
+      if (issuer) {
         tc::fence_after_sync();
         tc::issue_layer_tf32x3(mma1, mma0, K1, img + L.u1hi, img + L.u1lo, UMMA_LBO, UMMA_SBO);
         tc::mma_commit(bar);
@@ -179,117 +231,126 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       tc::fence_after_sync();
 
       // ---------------- layer 1 epilogue -> A2 (in place, buf1); layer 2 ----------------
-      float ss = epilogue_to_a<true>(buf1, sf(L.e1) + t * 128, nullptr, 1.f);
+      float ss = epilogue_half<true, true>(my1, e1 + t * 128, nullptr, 1.f);
+      if (NS) ssx[(0 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
       tc::fence_before_sync();
-      tc::named_bar_sync(1 + wg, 128);
-      if (wtid == 0) {
+      tc::named_bar_sync(full_bar, 256);
+      if (issuer) {
         tc::fence_after_sync();
-        tc::issue_layer_f16x3(mma0, mma1, img + L.u2hi, img + L.u2lo, UMMA_LBO, UMMA_SBO);
+        tc::issue_layer_f16x3_g16(mma0, mma1, img + L.u2hi, img + L.u2lo, UMMA_LBO, UMMA_SBO);
         tc::mma_commit(bar);
       }
-      float inv = NS ? inv_ws2 / fmaxf(sqrtf(ss), 1e-12f) : inv_ws2;      // F.normalize folded past the GEMM
+      float inv = inv_ws2;
+      if (NS) inv = inv_ws2 / fmaxf(sqrtf(ssx[0 * 128 + trow] + ssx[1 * 128 + trow]), 1e-12f);   // F.normalize, folded past the GEMM
       tc::mbar_wait(bar, phase); phase ^= 1u;
       tc::fence_after_sync();
 
       // ---------------- layer 2 epilogue -> A3 (in place, buf0); layer 3 ----------------
-      ss = epilogue_to_a<false>(buf0, sf(L.e2) + t * 128, sf(L.b2), inv);
+      ss = epilogue_half<false, !NS>(my0, e2 + t * 128, b2, inv);
+      if (NS) ssx[(1 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
       tc::fence_before_sync();
-      tc::named_bar_sync(1 + wg, 128);
-      if (wtid == 0) {
+      tc::named_bar_sync(full_bar, 256);
+      if (issuer) {
         tc::fence_after_sync();
-        tc::issue_layer_f16x3(mma1, mma0, img + L.u3hi, img + L.u3lo, UMMA_LBO, UMMA_SBO);
+        tc::issue_layer_f16x3_g16(mma1, mma0, img + L.u3hi, img + L.u3lo, UMMA_LBO, UMMA_SBO);
         tc::mma_commit(bar);
       }
-      inv = NS ? inv_ws3 / fmaxf(sqrtf(ss), 1e-12f) : inv_ws3;
+      inv = inv_ws3;
+      if (NS) inv = inv_ws3 / fmaxf(sqrtf(ssx[2 * 128 + trow] + ssx[3 * 128 + trow]), 1e-12f);
       tc::mbar_wait(bar, phase); phase ^= 1u;
       tc::fence_after_sync();
 
       // ---------------- layer 3 epilogue + heads (denoise.py:50 / tmdm_model.py:63) ----------------
-      float eps[F], sig[F];
+      float pe[F], ps[F];
 #pragma unroll
-      for (int f = 0; f < F; ++f) { eps[f] = 0.f; sig[f] = 0.f; }
-      const float* e3 = sf(L.e3) + t * 128;
-      const float* b3 = sf(L.b3);
-      const float* w4 = sf(L.w4);
-      const float* wsg = sf(L.ws);
+      for (int f = 0; f < F; ++f) { pe[f] = 0.f; ps[f] = 0.f; }
+      const float* e3t = e3 + t * 128;
       if (NS) {
-        // pass 1: h3 = softplus(.) kept in TMEM as fp32 (in place), sum of squares
+        // pass 1: L3 kept in TMEM as fp32 (in place), partial sum of squares
         ss = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tc::tmem_ld32(buf1 + 32u * c, r);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(my1 + 16u * q, r);
           tc::wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float h = upd_softplus((__uint_as_float(r[j]) * inv + b3[32 * c + j]) * e3[32 * c + j]);
+          for (int j = 0; j < 16; ++j) {
+            float h = lg2_1p_ex2((__uint_as_float(r[j]) * inv + b3[16 * q + j]) * e3t[16 * q + j]);
             ss = fmaf(h, h, ss);
             r[j] = __float_as_uint(h);
           }
-          tc::tmem_st32(buf1 + 32u * c, r);
+          tc::tmem_st16(my1 + 16u * q, r);
         }
+        ssx[(2 * 2 + half) * 128 + trow] = ss;
         tc::wait_st();
-        const float inv3 = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
-        // pass 2: normalised h -> eps head, softplus(h) -> sigma head
+        tc::named_bar_sync(full_bar, 256);
+        // pass 2: t = L3/||L3|| * log2e;  eps ~ sum w4*t,  sigma ~ sum ws*lg2(1+2^t)   (ln2 applied at the end)
+        const float inv3 = LOG2E / fmaxf(sqrtf(ssx[4 * 128 + trow] + ssx[5 * 128 + trow]), 1e-12f);
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tc::tmem_ld32(buf1 + 32u * c, r);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(my1 + 16u * q, r);
           tc::wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float hn = __uint_as_float(r[j]) * inv3;
-            float sp = upd_softplus(hn);
+          for (int j = 0; j < 16; ++j) {
+            float tt = __uint_as_float(r[j]) * inv3;
+            float sp = lg2_1p_ex2(tt);
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-              eps[f] = fmaf(w4[f * 128 + 32 * c + j], hn, eps[f]);
-              sig[f] = fmaf(wsg[f * 128 + 32 * c + j], sp, sig[f]);
+              pe[f] = fmaf(w4[f * 128 + 16 * q + j], tt, pe[f]);
+              ps[f] = fmaf(wsg[f * 128 + 16 * q + j], sp, ps[f]);
             }
           }
         }
-#pragma unroll
-        for (int f = 0; f < F; ++f) {
-          eps[f] += sf(L.b4)[f];
-          sig[f] = upd_softplus_accurate(sig[f] + sf(L.bs)[f]);
-        }
       } else {
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          uint32_t r[32];
-          tc::tmem_ld32(buf1 + 32u * c, r);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t r[16];
+          tc::tmem_ld16(my1 + 16u * q, r);
           tc::wait_ld();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float h = upd_softplus((__uint_as_float(r[j]) * inv + b3[32 * c + j]) * e3[32 * c + j]);
+          for (int j = 0; j < 16; ++j) {
+            float h = lg2_1p_ex2(fminf((__uint_as_float(r[j]) * inv + b3[16 * q + j]) * e3t[16 * q + j], 126.f));
 #pragma unroll
-            for (int f = 0; f < F; ++f) eps[f] = fmaf(w4[f * 128 + 32 * c + j], h, eps[f]);
+            for (int f = 0; f < F; ++f) pe[f] = fmaf(w4[f * 128 + 16 * q + j], h, pe[f]);
           }
         }
-#pragma unroll
-        for (int f = 0; f < F; ++f) eps[f] += sf(L.b4)[f];
       }
-
-      // ---------------- posterior update ----------------
-      const bool last = (t == 0);
-      if (NS) {
-        const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
+      if (!owner) {
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
-          y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps[f], sig[f], z, last);
+          headx[f * 128 + trow] = pe[f];
+          if (NS) headx[(F + f) * 128 + trow] = ps[f];
         }
+        __threadfence_block();
+        tc::named_bar_arrive(head_bar, 256);
       } else {
-        const UpdTmStep st = reinterpret_cast<const UpdTmStep*>(smem + steps_off)[t];
+        tc::named_bar_sync(head_bar, 256);
+        // ---------------- posterior update (owner warps) ----------------
+        const bool last = (t == 0);
+        if (NS) {
+          const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-          float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
-          y[f] = upd_tm_update(st, y[f], y0h[f], eps[f], z, last);
+          for (int f = 0; f < F; ++f) {
+            float eps = (pe[f] + headx[f * 128 + trow]) * LN2 + sf(L.b4)[f];
+            float sig = upd_softplus_accurate((ps[f] + headx[(F + f) * 128 + trow]) * LN2 + sf(L.bs)[f]);
+            float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
+            y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, z, last);
+          }
+        } else {
+          const UpdTmStep st = reinterpret_cast<const UpdTmStep*>(smem + steps_off)[t];
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float eps = (pe[f] + headx[f * 128 + trow]) * LN2 + sf(L.b4)[f];
+            float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
+            y[f] = upd_tm_update(st, y[f], y0h[f], eps, z, last);
+          }
         }
       }
     }
-    if (live) {
+    if (owner && live) {
 #pragma unroll
       for (int f = 0; f < F; ++f) p.out[row * F + f] = y[f];
     }
@@ -304,7 +365,9 @@ template <int KIND, int F>
 cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
   constexpr uint32_t STEP_BYTES = (KIND == 0) ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
-  size_t smem = upd_align128(upd_align128(L.tc_image_bytes) + STEP_BYTES * p.T) + sizeof(TcSync) + 128;
+  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 2 * UPD_MAX_F * 128;
+  size_t smem = upd_align128(upd_align128(upd_align128(L.tc_image_bytes) + STEP_BYTES * p.T) + 2 * XCH_TILE_FLOATS * 4) +
+                sizeof(TcSync) + 128;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   auto kern = sampler_tc_kernel<KIND, F>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -317,105 +380,6 @@ cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
-// ------------------------------------------------------------------------------------------------
-// Known-answer kernel for the descriptor / operand encodings above: D = A * B^T, one CTA.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 1)
-selftest_umma_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ D, int K, int mode,
-                     int flags) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ TcSync sync;
-  unsigned char* bhi = smem;
-  unsigned char* blo = smem + 32768;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  if (tid == 0) { tc::mbar_init(tc::smem_u32(&sync.mma_bar[0]), 1); tc::fence_mbar_init(); }
-  if (warp == 0) tc::tmem_alloc<256>(tc::smem_u32(&sync.tmem_base));
-  // B -> shared, UMMA K-major no-swizzle core-matrix layout (same element map as the host packer)
-  for (int idx = tid; idx < 128 * K; idx += 128) {
-    int n = idx / K, k = idx % K;
-    float v = Bm[n * K + k];
-    if (mode == 0) {
-      __half h = __float2half_rn(v);
-      __half l = __float2half_rn(v - __half2float(h));
-      size_t off = (size_t)(k / 8) * 2048 + (size_t)n * 16 + (size_t)(k % 8) * 2;
-      *reinterpret_cast<__half*>(bhi + off) = h;
-      *reinterpret_cast<__half*>(blo + off) = l;
-    } else {
-      float h = tc::to_tf32(v), l = tc::to_tf32(v - h);
-      size_t off = (size_t)(k / 4) * 2048 + (size_t)n * 16 + (size_t)(k % 4) * 4;
-      *reinterpret_cast<float*>(bhi + off) = h;
-      *reinterpret_cast<float*>(blo + off) = l;
-    }
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem_base = sync.tmem_base;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-  const uint32_t abuf = tmem_base + lane_sel, dbuf = abuf + 128u;
-  // A row of this thread -> TMEM with the sampler's operand encodings
-  if (mode == 0 && (flags & 4)) {
-    for (int q = 0; q < 8; ++q) {          // 16-column groups: hi words [16q,16q+8), lo words [16q+8,16q+16)
-      uint32_t o[16];
-      for (int j = 0; j < 16; j += 2)
-        tc::split_f16x2(A[tid * K + 16 * q + j], A[tid * K + 16 * q + j + 1], o[j / 2], o[8 + j / 2]);
-      tc::tmem_st16(abuf + 16u * q, o);
-    }
-  } else if (mode == 0) {
-    for (int c = 0; c < 4; ++c) {
-      uint32_t o[32];
-      for (int j = 0; j < 32; j += 2) {
-        float a0 = A[tid * K + 32 * c + j], a1 = A[tid * K + 32 * c + j + 1];
-        if (flags & 2) { float tmp = a0; a0 = a1; a1 = tmp; }
-        tc::split_f16x2(a0, a1, o[j / 2], o[16 + j / 2]);
-      }
-      tc::tmem_st32(abuf + 32u * c, o);
-    }
-  } else {
-    uint32_t a[32];
-    for (int i = 0; i < 32; ++i) a[i] = 0u;
-    // hi in columns [0,K), lo in [K,2K); K <= 16 fits one x32 store, K = 24/32 needs two
-    for (int half = 0; half < (K > 16 ? 2 : 1); ++half) {
-      for (int i = 0; i < 32; ++i) {
-        int col = 32 * half + i;
-        float v = 0.f;
-        bool is_lo = col >= K;
-        int k = is_lo ? col - K : col;
-        if (k < K) {
-          float x = A[tid * K + k];
-          float hi = tc::to_tf32(x);
-          v = is_lo ? tc::to_tf32(x - hi) : hi;
-        }
-        a[i] = __float_as_uint(v);
-      }
-      tc::tmem_st32(abuf + 32u * half, a);
-    }
-  }
-  tc::wait_st();
-  tc::fence_before_sync();
-  __syncthreads();
-  const uint32_t lbo = (flags & 1) ? UMMA_SBO : UMMA_LBO, sbo = (flags & 1) ? UMMA_LBO : UMMA_SBO;
-  if (tid == 0) {
-    tc::fence_after_sync();
-    if (mode == 0 && (flags & 4)) tc::issue_layer_f16x3_g16(tmem_base + 128u, tmem_base, tc::smem_u32(bhi), tc::smem_u32(blo), lbo, sbo);
-    else if (mode == 0) tc::issue_layer_f16x3(tmem_base + 128u, tmem_base, tc::smem_u32(bhi), tc::smem_u32(blo), lbo, sbo);
-    else tc::issue_layer_tf32x3(tmem_base + 128u, tmem_base, K, tc::smem_u32(bhi), tc::smem_u32(blo), lbo, sbo);
-    tc::mma_commit(tc::smem_u32(&sync.mma_bar[0]));
-  }
-  tc::mbar_wait(tc::smem_u32(&sync.mma_bar[0]), 0);
-  tc::fence_after_sync();
-  for (int c = 0; c < 4; ++c) {
-    uint32_t r[32];
-    tc::tmem_ld32(dbuf + 32u * c, r);
-    tc::wait_ld();
-    for (int j = 0; j < 32; ++j) D[tid * 128 + 32 * c + j] = __uint_as_float(r[j]);
-  }
-  tc::fence_before_sync();
-  __syncthreads();
-  if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
-}
-
 }  // namespace
 
 cudaError_t upd_launch_sampler_tc(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream) {
@@ -424,12 +388,4 @@ cudaError_t upd_launch_sampler_tc(const UpdSamplerParams& p, int kind, int F, in
   UPD_CASE(1, 1) UPD_CASE(1, 2) UPD_CASE(1, 3) UPD_CASE(1, 4)
 #undef UPD_CASE
   return cudaErrorInvalidValue;
-}
-
-cudaError_t upd_launch_selftest_umma(const float* a, const float* b, float* d, int K, int mode, int flags,
-                                     cudaStream_t stream) {
-  cudaError_t e = cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  if (e != cudaSuccess) return e;
-  selftest_umma_kernel<<<1, 128, 65536, stream>>>(a, b, d, K, mode, flags);
-  return cudaGetLastError();
 }

@@ -164,23 +164,9 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(u);
 }
 
-// Issue one 128x128xK contraction as three passes (hi*hi + lo*hi + hi*lo) of K/KS slices.
-//   f16: slice = 16 elements = 8 TMEM columns of A, two 2048-byte-apart core-matrix columns of B.
-// A chunk layout (32 elements per 32 columns): hi words in columns [32c,32c+16), lo in [32c+16,32c+32).
-__device__ __forceinline__ void issue_layer_f16x3(uint32_t d_tmem, uint32_t a_tmem, uint32_t bhi_smem, uint32_t blo_smem,
-                                                  uint32_t lbo, uint32_t sbo) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    uint32_t a_hi = a_tmem + 32u * (j >> 1) + 8u * (j & 1);
-    uint32_t a_lo = a_hi + 16u;
-    uint64_t b_hi = smem_desc(bhi_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
-    uint64_t b_lo = smem_desc(blo_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
-    mma_f16_ts(d_tmem, a_lo, b_hi, IDESC_F16_M128_N128, j > 0);
-    mma_f16_ts(d_tmem, a_hi, b_lo, IDESC_F16_M128_N128, true);
-    mma_f16_ts(d_tmem, a_hi, b_hi, IDESC_F16_M128_N128, true);
-  }
-}
-// Same contraction with the 16-column in-place A layout of the 16-warp sampler: K-slice j = fp16 hi words in
+// Issue one 128x128x128 contraction as three passes (hi*hi + lo*hi + hi*lo) of eight K-slices.
+// fp16: slice = 16 elements = 8 TMEM columns of A and two 2048-byte-apart core-matrix columns of B.
+// A layout (in place over the previous accumulator, 16 columns at a time): K-slice j = fp16 hi words in
 // columns [16j,16j+8), lo words in [16j+8,16j+16).
 __device__ __forceinline__ void issue_layer_f16x3_g16(uint32_t d_tmem, uint32_t a_tmem, uint32_t bhi_smem,
                                                       uint32_t blo_smem, uint32_t lbo, uint32_t sbo) {

@@ -22,6 +22,73 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _tf32_hi(x):
+    """Upper 19 bits of an fp32 tensor: exactly representable in TF32, so x - hi is exact in fp32."""
+    return (x.contiguous().view(torch.int32) & -8192).view(torch.float32)
+
+
+class _SplitWeight:
+    """hi/lo TF32 split of a weight matrix, cached until the parameter changes."""
+
+    def __init__(self):
+        self.key, self.hi, self.lo = None, None, None
+
+    def get(self, w):
+        key = (w.data_ptr(), w._version, w.device)
+        if key != self.key:
+            w2 = w.detach().reshape(w.shape[0], -1)
+            self.hi = _tf32_hi(w2)
+            self.lo = w2 - self.hi
+            self.key = key
+        return self.hi, self.lo
+
+
+def split_linear(x, weight, bias, cache):
+    """y = x W^T + b with fp32-grade accuracy on the TF32 tensor cores: three library GEMMs
+    (hi*hi + lo*hi + hi*lo, fp32 accumulate), the same error-compensated split the fused sampler uses.
+    Plain fp32 SIMT GEMMs made this encoder 43 % of a sweep's GPU time (profiles/r01_bench_launches_summary.txt).
+    On the CPU (model construction, tests of the host logic) it is an ordinary F.linear."""
+    if not x.is_cuda:
+        return F.linear(x, weight.reshape(weight.shape[0], -1), bias)
+    w_hi, w_lo = cache.get(weight)
+    x2 = x.reshape(-1, x.shape[-1])
+    x_hi = _tf32_hi(x2)
+    x_lo = x2 - x_hi
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        y = torch.mm(x_lo, w_hi.t())
+        y.addmm_(x_hi, w_lo.t())
+        y.addmm_(x_hi, w_hi.t())
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    if bias is not None:
+        y += bias
+    return y.view(*x.shape[:-1], weight.shape[0])
+
+
+class SLinear(nn.Linear):
+    """nn.Linear (same parameters / state-dict keys) evaluated with split_linear."""
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        self._split = _SplitWeight()
+
+    def forward(self, x):
+        return split_linear(x, self.weight, self.bias, self._split)
+
+
+class PointwiseConv(nn.Conv1d):
+    """nn.Conv1d(kernel_size=1) parameters (weight [out,in,1]) applied along the last axis of [B,L,C]."""
+
+    def __init__(self, c_in, c_out):
+        super().__init__(c_in, c_out, 1)
+        self._split = _SplitWeight()
+
+    def forward(self, x):
+        return split_linear(x, self.weight, self.bias, self._split)
+
+
 class Projector(nn.Module):
     """mu_backbone.py:12-41: MLP producing the de-stationary factors tau (scalar) / delta (per step)."""
 
@@ -36,8 +103,13 @@ class Projector(nn.Module):
 
     def forward(self, x, stats):
         b = x.shape[0]
-        x = self.series_conv(x)                    # B x 1 x E
-        x = torch.cat([x, stats], dim=1).view(b, -1)
+        # circular Conv1d(seq_len -> 1, k=3) over the feature axis as three shifted fp32 contractions
+        # (same reason as TokenEmbedding: no implicit TF32 convolution in the condition path)
+        w = self.series_conv.weight                 # [1, S, 3]
+        conv = 0
+        for k, shift in enumerate((1, 0, -1)):
+            conv = conv + torch.einsum("bse,s->be", torch.roll(x, shifts=shift, dims=2), w[0, :, k])
+        x = torch.cat([conv.unsqueeze(1), stats], dim=1).reshape(b, -1)
         return self.backbone(x)
 
 
@@ -47,7 +119,13 @@ class TokenEmbedding(nn.Module):
         self.tokenConv = nn.Conv1d(c_in, d_model, kernel_size=3, padding=1, padding_mode="circular", bias=False)
 
     def forward(self, x):
-        return self.tokenConv(x.permute(0, 2, 1)).transpose(1, 2)
+        # circular Conv1d(k=3, no bias) written as three shifted contractions in plain fp32 (c_in is 1..4):
+        # keeps cuDNN's default TF32 convolution path out of the condition mean
+        w = self.tokenConv.weight                                    # [d_model, c_in, 3]
+        out = 0
+        for k, shift in enumerate((1, 0, -1)):
+            out = out + torch.einsum("blc,dc->bld", torch.roll(x, shifts=shift, dims=1), w[:, :, k])
+        return out
 
 
 class PositionalEmbedding(nn.Module):
@@ -83,10 +161,10 @@ class AttentionLayer(nn.Module):
         super().__init__()
         self.n_heads, self.causal = n_heads, causal
         dk = d_model // n_heads
-        self.query_projection = nn.Linear(d_model, dk * n_heads)
-        self.key_projection = nn.Linear(d_model, dk * n_heads)
-        self.value_projection = nn.Linear(d_model, dk * n_heads)
-        self.out_projection = nn.Linear(dk * n_heads, d_model)
+        self.query_projection = SLinear(d_model, dk * n_heads)
+        self.key_projection = SLinear(d_model, dk * n_heads)
+        self.value_projection = SLinear(d_model, dk * n_heads)
+        self.out_projection = SLinear(dk * n_heads, d_model)
 
     def forward(self, queries, keys, values, tau=None, delta=None):
         B, Lq, _ = queries.shape
@@ -117,14 +195,14 @@ class EncoderLayer(nn.Module):
     def __init__(self, d_model, n_heads, d_ff, activation):
         super().__init__()
         self.attention = AttentionLayer(d_model, n_heads, causal=False)
-        self.conv1 = nn.Conv1d(d_model, d_ff, 1)
-        self.conv2 = nn.Conv1d(d_ff, d_model, 1)
+        self.conv1 = PointwiseConv(d_model, d_ff)
+        self.conv2 = PointwiseConv(d_ff, d_model)
         self.norm1, self.norm2 = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
         self.activation = _act(activation)
 
     def forward(self, x, tau, delta):
         x = self.norm1(x + self.attention(x, x, x, tau, delta))
-        y = self.conv2(self.activation(self.conv1(x.transpose(-1, 1)))).transpose(-1, 1)
+        y = self.conv2(self.activation(self.conv1(x)))
         return self.norm2(x + y)
 
 
@@ -145,15 +223,15 @@ class DecoderLayer(nn.Module):
         super().__init__()
         self.self_attention = AttentionLayer(d_model, n_heads, causal=True)
         self.cross_attention = AttentionLayer(d_model, n_heads, causal=False)
-        self.conv1 = nn.Conv1d(d_model, d_ff, 1)
-        self.conv2 = nn.Conv1d(d_ff, d_model, 1)
+        self.conv1 = PointwiseConv(d_model, d_ff)
+        self.conv2 = PointwiseConv(d_ff, d_model)
         self.norm1, self.norm2, self.norm3 = nn.LayerNorm(d_model), nn.LayerNorm(d_model), nn.LayerNorm(d_model)
         self.activation = _act(activation)
 
     def forward(self, x, cross, tau, delta):
         x = self.norm1(x + self.self_attention(x, x, x, tau, None))
         x = self.norm2(x + self.cross_attention(x, cross, cross, tau, delta))
-        y = self.conv2(self.activation(self.conv1(x.transpose(-1, 1)))).transpose(-1, 1)
+        y = self.conv2(self.activation(self.conv1(x)))
         return self.norm3(x + y)
 
 
@@ -162,7 +240,7 @@ class Decoder(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList(layers)
         self.norm = nn.LayerNorm(d_model)
-        self.projection = nn.Linear(d_model, c_out, bias=True)
+        self.projection = SLinear(d_model, c_out, bias=True)
 
     def forward(self, x, cross, tau, delta):
         for layer in self.layers:
