@@ -43,7 +43,14 @@ class _SplitWeight:
         return self.hi, self.lo
 
 
-def split_linear(x, weight, bias, cache):
+def split_operand(x):
+    """(x2d, hi, lo) of an activation tensor, computed once and shared by every GEMM that consumes it."""
+    x2 = x.reshape(-1, x.shape[-1])
+    hi = _tf32_hi(x2)
+    return x2, hi, x2 - hi
+
+
+def split_linear(x, weight, bias, cache, pre=None):
     """y = x W^T + b with fp32-grade accuracy on the TF32 tensor cores: three library GEMMs
     (hi*hi + lo*hi + hi*lo, fp32 accumulate), the same error-compensated split the fused sampler uses.
     Plain fp32 SIMT GEMMs made this encoder 43 % of a sweep's GPU time (profiles/r01_bench_launches_summary.txt).
@@ -51,19 +58,16 @@ def split_linear(x, weight, bias, cache):
     if not x.is_cuda:
         return F.linear(x, weight.reshape(weight.shape[0], -1), bias)
     w_hi, w_lo = cache.get(weight)
-    x2 = x.reshape(-1, x.shape[-1])
-    x_hi = _tf32_hi(x2)
-    x_lo = x2 - x_hi
+    _, x_hi, x_lo = split_operand(x) if pre is None else pre
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
-        y = torch.mm(x_lo, w_hi.t())
+        # small terms first; the bias rides in the first GEMM's epilogue instead of a separate pass
+        y = torch.mm(x_lo, w_hi.t()) if bias is None else torch.addmm(bias, x_lo, w_hi.t())
         y.addmm_(x_hi, w_lo.t())
         y.addmm_(x_hi, w_hi.t())
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    if bias is not None:
-        y += bias
     return y.view(*x.shape[:-1], weight.shape[0])
 
 
@@ -74,8 +78,8 @@ class SLinear(nn.Linear):
         super().__init__(*a, **k)
         self._split = _SplitWeight()
 
-    def forward(self, x):
-        return split_linear(x, self.weight, self.bias, self._split)
+    def forward(self, x, pre=None):
+        return split_linear(x, self.weight, self.bias, self._split, pre)
 
 
 class PointwiseConv(nn.Conv1d):
@@ -170,9 +174,11 @@ class AttentionLayer(nn.Module):
         B, Lq, _ = queries.shape
         S = keys.shape[1]
         H = self.n_heads
-        q = self.query_projection(queries).view(B, Lq, H, -1).transpose(1, 2)
-        k = self.key_projection(keys).view(B, S, H, -1).transpose(1, 2)
-        v = self.value_projection(values).view(B, S, H, -1).transpose(1, 2)
+        pre_q = split_operand(queries) if queries.is_cuda else None
+        pre_kv = pre_q if keys is queries else (split_operand(keys) if keys.is_cuda else None)
+        q = self.query_projection(queries, pre_q).view(B, Lq, H, -1).transpose(1, 2)
+        k = self.key_projection(keys, pre_kv).view(B, S, H, -1).transpose(1, 2)
+        v = self.value_projection(values, pre_kv).view(B, S, H, -1).transpose(1, 2)
         scale = 1.0 / math.sqrt(q.shape[-1])
         if tau is not None:
             q = q * tau.view(B, 1, 1, 1)
