@@ -3,6 +3,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "upd_b200.h"
@@ -169,6 +170,9 @@ static int sample_common(int kind, const void* packed, const float* y0_hat, cons
   p.n_win = n_win; p.B = B; p.K = K; p.S = S; p.O = O; p.T = T;
   p.n_rows = (long long)n_win * B * K * O;
   p.seed = seed; p.window_base = window_base;
+#ifdef UPD_TRACE
+  { const char* e = getenv("UPD_TRACE_PTR"); p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr; }
+#endif
   cudaError_t e = (impl == UPD_IMPL_SIMT) ? upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream)
                                           : upd_launch_sampler_tc(p, kind, F, sms, (cudaStream_t)stream);
   if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;

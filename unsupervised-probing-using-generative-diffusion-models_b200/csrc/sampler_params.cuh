@@ -11,6 +11,9 @@ struct UpdSamplerParams {
   long long n_rows;        // n_win*B*K*O denoiser rows
   int n_win, B, K, S, O, T;
   unsigned long long seed, window_base;
+#ifdef UPD_TRACE
+  long long* trace;        // debug builds only (scratch/): [16 warps][T][16] clock64 stamps of CTA 0, first tile
+#endif
 };
 
 // A denoiser row is one (r0 = w*B + b, sample k, position o); rows are numbered in output order

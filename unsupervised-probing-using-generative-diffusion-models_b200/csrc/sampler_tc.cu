@@ -18,10 +18,14 @@
 //     6 instructions per hidden element instead of 9.
 //   * hidden activations are re-encoded IN PLACE over the accumulator columns they came from, 16 columns
 //     at a time: K-slice j of the next A operand = fp16 hi in columns [16j,16j+8), lo in [16j+8,16j+16).
+//   * the two tiles take the MUFU-heavy phases in strict turns (named-barrier hand-off, mufu_turn_*): one tile's
+//     softplus epilogue runs at the full MUFU rate while the other's MMAs, head FMAs and posterior are in flight.
 //   * per-row reductions (sum of squares for F.normalize, head partial sums) are exchanged between the two
 //     column halves through shared memory, riding on the barrier that precedes each MMA issue anyway.
-//   * row state (y, y0_hat, gx), Philox noise, the posterior algebra and the A1 operand belong to the
-//     half-0 warp of each row.
+//   * the sigma head's softplus acts on the L2-normalised hidden vector (components in [0,1]) and is a
+//     polynomial on the FMA pipe: 386 instead of 514 MUFU softplus per row-step.
+//   * row state (y, y0_hat, gx), the posterior algebra and the A1 operand belong to the half-0 warp of each
+//     row; the half-1 warp draws the Philox noise for it while it would otherwise idle.
 #include "sampler_params.cuh"
 #include "tc_helpers.cuh"
 #include "upd_common.cuh"
@@ -31,6 +35,7 @@ namespace {
 constexpr int TC_THREADS = 512;
 constexpr uint32_t UMMA_LBO = 2048;   // K-adjacent core matrices (layout in upd_common.cuh)
 constexpr uint32_t UMMA_SBO = 128;    // N-adjacent core matrices
+constexpr int PP_BAR0 = 13;           // named barriers 13/14: MUFU turn of tile 0 / tile 1 (see mufu_turn_*)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
@@ -48,6 +53,28 @@ __device__ __forceinline__ float lg2_1p_ex2(float z) {
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + u));
   return l;
 }
+
+// softplus(x) for x in [0,1] without MUFU: x/2 + P(x^2), P = degree-4 near-minimax fit of log(2 cosh(sqrt(u)/2))
+// on u in [0,1] (|error| < 4e-9 before fp32 rounding, 1e-7 after).  The sigma head applies softplus to the
+// L2-normalised, non-negative hidden vector, whose components always lie in [0,1]; evaluating those 128 of the
+// 514 softplus per row-step on the FMA pipe removes a quarter of the kernel's MUFU work.
+__device__ __forceinline__ float softplus_unit(float x) {
+  const float u = x * x;
+  float p = -2.16761418414535e-05f;
+  p = fmaf(p, u, 0.0003433137317188084f);
+  p = fmaf(p, u, -0.005206969100981951f);
+  p = fmaf(p, u, 0.12499982863664627f);
+  p = fmaf(p, u, 0.6931471824645996f);
+  return fmaf(0.5f, x, p);
+}
+
+// MUFU hand-off between the two tiles of a CTA.  Left alone the tiles fall into lock-step (measured with clock64
+// stamps: both in their softplus epilogue at once, each at half MUFU rate, then both waiting on interleaved MMAs
+// with the MUFU pipe idle: 24.8k cycles per step).  A tile therefore takes the MUFU-heavy phases (the three
+// softplus epilogues of a step) in turns: wait for the partner to finish its phase, run, hand over.  While one
+// tile computes softplus the other has its MMAs, head FMAs and posterior algebra in flight.
+__device__ __forceinline__ void mufu_turn_begin(int tile_id) { tc::named_bar_sync(PP_BAR0 + tile_id, TC_THREADS); }
+__device__ __forceinline__ void mufu_turn_end(int tile_id) { tc::named_bar_arrive(PP_BAR0 + (tile_id ^ 1), TC_THREADS); }
 
 // One 16-column group of an accumulator -> activations -> fp16 hi/lo A operand, in place.
 // FIRST: layer 1 (bias rides in the GEMM).  CLAMP: guard ex2 overflow where inputs are unbounded.
@@ -94,6 +121,12 @@ __device__ __forceinline__ float epilogue_half(uint32_t buf, const float* __rest
   return ss;
 }
 
+#ifdef UPD_TRACE
+#define UPD_STAMP(k) do { if (tracing && lane == 0) p.trace[(warp * p.T + (p.T - 1 - t)) * 16 + (k)] = clock64(); } while (0)
+#else
+#define UPD_STAMP(k) do { } while (0)
+#endif
+
 template <int KIND, int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 sampler_tc_kernel(const UpdSamplerParams p) {
@@ -107,7 +140,7 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   const uint32_t steps_off = upd_align128(L.tc_image_bytes);
   const uint32_t xch_off = upd_align128(steps_off + STEP_BYTES * p.T);
   // exchange area per tile: ssx[3 layers][2 halves][128 rows], headx[2F][128 rows]
-  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 2 * UPD_MAX_F * 128;
+  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 3 * UPD_MAX_F * 128;
   const uint32_t sync_off = upd_align128(xch_off + 2 * XCH_TILE_FLOATS * 4);
   TcSync* sync = reinterpret_cast<TcSync*>(smem + sync_off);
 
@@ -155,8 +188,10 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   const uint32_t bar = tc::smem_u32(&sync->mma_bar[tile_id]);
   const uint32_t img = tc::smem_u32(smem);
   float* ssx = sf(xch_off) + tile_id * XCH_TILE_FLOATS;     // [3][2][128]
-  float* headx = ssx + 3 * 2 * 128;                         // [2F][128]
-  const int full_bar = 1 + tile_id, head_bar = 3 + tile_id;
+  float* headx = ssx + 3 * 2 * 128;                         // [2F][128] head partial sums, then [F][128] noise
+  // named barriers: 1,2 = all 256 threads of a tile (precede every MMA issue); 5..12 = the two warps that share
+  // a TMEM lane quadrant (64 threads), for the half<->half exchanges that need no tile-wide rendezvous
+  const int full_bar = 1 + tile_id, pair_bar = 5 + tile_id * 4 + quad;
   const float inv_ws2 = sf(L.scales)[0] * (NS ? 1.0f : LN2), inv_ws3 = sf(L.scales)[1] * (NS ? 1.0f : LN2);
   const float* e1 = sf(L.e1) + 64 * half;
   const float* e2 = sf(L.e2) + 64 * half;
@@ -168,7 +203,16 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   uint32_t phase = 0;
 
   const long long n_tiles = (p.n_rows + 127) / 128;
-  for (long long tile = (long long)blockIdx.x * 2 + tile_id; tile < n_tiles; tile += (long long)gridDim.x * 2) {
+#ifdef UPD_TRACE
+  bool tracing = false;
+#endif
+  // Every tile slot of every CTA runs the same number of iterations (slots past the end compute on a clamped
+  // row and store nothing): the MUFU hand-off below is a strict alternation and must never wait for a
+  // partner that has already left.
+  const long long n_iters = (n_tiles + 2LL * gridDim.x - 1) / (2LL * gridDim.x);
+  if (tile_id == 1) tc::named_bar_arrive(PP_BAR0, TC_THREADS);          // tile 0 takes the first turn
+  for (long long it = 0; it < n_iters; ++it) {
+    const long long tile = (it * gridDim.x + blockIdx.x) * 2 + tile_id;
     const long long row = tile * 128 + trow;
     const bool live = row < p.n_rows;
     UpdRowIndex ix = upd_row_index(p, live ? row : p.n_rows - 1);
@@ -185,7 +229,11 @@ sampler_tc_kernel(const UpdSamplerParams p) {
         y[f] = NS ? sqrtf(gxv[f]) * z + y0h[f] : z + y0h[f];       // nsdiff_utils.py:274 / tmdm_diffusion_utils.py:110
       }
     }
+#ifdef UPD_TRACE
+    tracing = (p.trace != nullptr) && blockIdx.x == 0 && it == 1;
+#endif
     for (int t = p.T - 1; t >= 0; --t) {
+      UPD_STAMP(0);
       // ---------------- layer 1: A1 = [y | y0_hat | gx | 1 | 0] as tf32 hi/lo (owner warps) ----------------
       if (owner) {
         float in[K1];
@@ -222,6 +270,7 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       }
       tc::fence_before_sync();
       tc::named_bar_sync(full_bar, 256);
+      UPD_STAMP(1);
       if (issuer) {
         tc::fence_after_sync();
         tc::issue_layer_tf32x3(mma1, mma0, K1, img + L.u1hi, img + L.u1lo, UMMA_LBO, UMMA_SBO);
@@ -229,13 +278,18 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       }
       tc::mbar_wait(bar, phase); phase ^= 1u;
       tc::fence_after_sync();
+      UPD_STAMP(2);
 
       // ---------------- layer 1 epilogue -> A2 (in place, buf1); layer 2 ----------------
+      mufu_turn_begin(tile_id);
       float ss = epilogue_half<true, true>(my1, e1 + t * 128, nullptr, 1.f);
+      mufu_turn_end(tile_id);
       if (NS) ssx[(0 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
+      UPD_STAMP(3);
       tc::fence_before_sync();
       tc::named_bar_sync(full_bar, 256);
+      UPD_STAMP(4);
       if (issuer) {
         tc::fence_after_sync();
         tc::issue_layer_f16x3_g16(mma0, mma1, img + L.u2hi, img + L.u2lo, UMMA_LBO, UMMA_SBO);
@@ -245,13 +299,18 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       if (NS) inv = inv_ws2 / fmaxf(sqrtf(ssx[0 * 128 + trow] + ssx[1 * 128 + trow]), 1e-12f);   // F.normalize, folded past the GEMM
       tc::mbar_wait(bar, phase); phase ^= 1u;
       tc::fence_after_sync();
+      UPD_STAMP(5);
 
       // ---------------- layer 2 epilogue -> A3 (in place, buf0); layer 3 ----------------
+      mufu_turn_begin(tile_id);
       ss = epilogue_half<false, !NS>(my0, e2 + t * 128, b2, inv);
+      mufu_turn_end(tile_id);
       if (NS) ssx[(1 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
+      UPD_STAMP(6);
       tc::fence_before_sync();
       tc::named_bar_sync(full_bar, 256);
+      UPD_STAMP(7);
       if (issuer) {
         tc::fence_after_sync();
         tc::issue_layer_f16x3_g16(mma1, mma0, img + L.u3hi, img + L.u3lo, UMMA_LBO, UMMA_SBO);
@@ -261,12 +320,14 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       if (NS) inv = inv_ws3 / fmaxf(sqrtf(ssx[2 * 128 + trow] + ssx[3 * 128 + trow]), 1e-12f);
       tc::mbar_wait(bar, phase); phase ^= 1u;
       tc::fence_after_sync();
+      UPD_STAMP(8);
 
       // ---------------- layer 3 epilogue + heads (denoise.py:50 / tmdm_model.py:63) ----------------
       float pe[F], ps[F];
 #pragma unroll
       for (int f = 0; f < F; ++f) { pe[f] = 0.f; ps[f] = 0.f; }
       const float* e3t = e3 + t * 128;
+      mufu_turn_begin(tile_id);
       if (NS) {
         // pass 1: L3 kept in TMEM as fp32 (in place), partial sum of squares
         ss = 0.f;
@@ -284,10 +345,13 @@ sampler_tc_kernel(const UpdSamplerParams p) {
           tc::tmem_st16(my1 + 16u * q, r);
         }
         ssx[(2 * 2 + half) * 128 + trow] = ss;
+        mufu_turn_end(tile_id);
         tc::wait_st();
-        tc::named_bar_sync(full_bar, 256);
-        // pass 2: t = L3/||L3|| * log2e;  eps ~ sum w4*t,  sigma ~ sum ws*lg2(1+2^t)   (ln2 applied at the end)
-        const float inv3 = LOG2E / fmaxf(sqrtf(ssx[4 * 128 + trow] + ssx[5 * 128 + trow]), 1e-12f);
+        UPD_STAMP(9);
+        tc::named_bar_sync(pair_bar, 64);
+        UPD_STAMP(10);
+        // pass 2: hn = L3/||L3|| (= h/||h||, components in [0,1]);  eps = sum w4*hn,  sigma ~ sum ws*softplus(hn)
+        const float inv3 = 1.0f / fmaxf(sqrtf(ssx[4 * 128 + trow] + ssx[5 * 128 + trow]), 1e-12f);
 #pragma unroll 1
         for (int q = 0; q < 4; ++q) {
           uint32_t r[16];
@@ -295,11 +359,11 @@ sampler_tc_kernel(const UpdSamplerParams p) {
           tc::wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float tt = __uint_as_float(r[j]) * inv3;
-            float sp = lg2_1p_ex2(tt);
+            float hn = __uint_as_float(r[j]) * inv3;
+            float sp = softplus_unit(hn);
 #pragma unroll
             for (int f = 0; f < F; ++f) {
-              pe[f] = fmaf(w4[f * 128 + 16 * q + j], tt, pe[f]);
+              pe[f] = fmaf(w4[f * 128 + 16 * q + j], hn, pe[f]);
               ps[f] = fmaf(wsg[f * 128 + 16 * q + j], sp, ps[f]);
             }
           }
@@ -317,38 +381,41 @@ sampler_tc_kernel(const UpdSamplerParams p) {
             for (int f = 0; f < F; ++f) pe[f] = fmaf(w4[f * 128 + 16 * q + j], h, pe[f]);
           }
         }
+        mufu_turn_end(tile_id);
       }
+      const bool last = (t == 0);
+      UPD_STAMP(11);
       if (!owner) {
+        // the idle half hands over its partial sums and draws this step's noise for the owner
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           headx[f * 128 + trow] = pe[f];
           if (NS) headx[(F + f) * 128 + trow] = ps[f];
+          headx[(2 * F + f) * 128 + trow] = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
         }
         __threadfence_block();
-        tc::named_bar_arrive(head_bar, 256);
+        tc::named_bar_arrive(pair_bar, 64);
       } else {
-        tc::named_bar_sync(head_bar, 256);
+        tc::named_bar_sync(pair_bar, 64);
         // ---------------- posterior update (owner warps) ----------------
-        const bool last = (t == 0);
         if (NS) {
           const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
 #pragma unroll
           for (int f = 0; f < F; ++f) {
-            float eps = (pe[f] + headx[f * 128 + trow]) * LN2 + sf(L.b4)[f];
-            float sig = upd_softplus_accurate((ps[f] + headx[(F + f) * 128 + trow]) * LN2 + sf(L.bs)[f]);
-            float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
-            y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, z, last);
+            float eps = (pe[f] + headx[f * 128 + trow]) + sf(L.b4)[f];
+            float sig = upd_softplus_accurate((ps[f] + headx[(F + f) * 128 + trow]) + sf(L.bs)[f]);
+            y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, headx[(2 * F + f) * 128 + trow], last);
           }
         } else {
           const UpdTmStep st = reinterpret_cast<const UpdTmStep*>(smem + steps_off)[t];
 #pragma unroll
           for (int f = 0; f < F; ++f) {
             float eps = (pe[f] + headx[f * 128 + trow]) * LN2 + sf(L.b4)[f];
-            float z = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
-            y[f] = upd_tm_update(st, y[f], y0h[f], eps, z, last);
+            y[f] = upd_tm_update(st, y[f], y0h[f], eps, headx[(2 * F + f) * 128 + trow], last);
           }
         }
       }
+      UPD_STAMP(12);
     }
     if (owner && live) {
 #pragma unroll
@@ -365,7 +432,7 @@ template <int KIND, int F>
 cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
   constexpr uint32_t STEP_BYTES = (KIND == 0) ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
-  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 2 * UPD_MAX_F * 128;
+  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 3 * UPD_MAX_F * 128;
   size_t smem = upd_align128(upd_align128(upd_align128(L.tc_image_bytes) + STEP_BYTES * p.T) + 2 * XCH_TILE_FLOATS * 4) +
                 sizeof(TcSync) + 128;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
