@@ -22,8 +22,10 @@
 //     softplus epilogue runs at the full MUFU rate while the other's MMAs, head FMAs and posterior are in flight.
 //   * per-row reductions (sum of squares for F.normalize, head partial sums) are exchanged between the two
 //     column halves through shared memory, riding on the barrier that precedes each MMA issue anyway.
-//   * the sigma head's softplus acts on the L2-normalised hidden vector (components in [0,1]) and is a
-//     polynomial on the FMA pipe: 386 instead of 514 MUFU softplus per row-step.
+//   * the sigma head's softplus acts on the L2-normalised hidden vector (components in [0,1]): it is a
+//     polynomial, and because a polynomial of hn = L/||L|| is a sum of power sums of L, both heads are
+//     accumulated inside the layer-3 epilogue and rescaled once ||L|| is known -- 386 instead of 514 MUFU
+//     softplus per row-step and no second pass over the row.
 //   * row state (y, y0_hat, gx), the posterior algebra and the A1 operand belong to the half-0 warp of each
 //     row; the half-1 warp draws the Philox noise for it while it would otherwise idle.
 #include "sampler_params.cuh"
@@ -35,6 +37,9 @@ namespace {
 constexpr int TC_THREADS = 512;
 constexpr uint32_t UMMA_LBO = 2048;   // K-adjacent core matrices (layout in upd_common.cuh)
 constexpr uint32_t UMMA_SBO = 128;    // N-adjacent core matrices
+#ifndef UPD_HANDOFF_GROUP
+#define UPD_HANDOFF_GROUP 4
+#endif
 constexpr int PP_BAR0 = 13;           // named barriers 13/14: MUFU turn of tile 0 / tile 1 (see mufu_turn_*)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -56,17 +61,10 @@ __device__ __forceinline__ float lg2_1p_ex2(float z) {
 
 // softplus(x) for x in [0,1] without MUFU: x/2 + P(x^2), P = degree-4 near-minimax fit of log(2 cosh(sqrt(u)/2))
 // on u in [0,1] (|error| < 4e-9 before fp32 rounding, 1e-7 after).  The sigma head applies softplus to the
-// L2-normalised, non-negative hidden vector, whose components always lie in [0,1]; evaluating those 128 of the
-// 514 softplus per row-step on the FMA pipe removes a quarter of the kernel's MUFU work.
-__device__ __forceinline__ float softplus_unit(float x) {
-  const float u = x * x;
-  float p = -2.16761418414535e-05f;
-  p = fmaf(p, u, 0.0003433137317188084f);
-  p = fmaf(p, u, -0.005206969100981951f);
-  p = fmaf(p, u, 0.12499982863664627f);
-  p = fmaf(p, u, 0.6931471824645996f);
-  return fmaf(0.5f, x, p);
-}
+// L2-normalised, non-negative hidden vector, whose components always lie in [0,1]; taking those 128 of the 514
+// softplus per row-step off the MUFU pipe removes a quarter of the kernel's transcendental work.
+constexpr float SPU_C0 = 0.6931471824645996f, SPU_C1 = 0.12499982863664627f, SPU_C2 = -0.005206969100981951f,
+                SPU_C3 = 0.0003433137317188084f, SPU_C4 = -2.16761418414535e-05f;
 
 // MUFU hand-off between the two tiles of a CTA.  Left alone the tiles fall into lock-step (measured with clock64
 // stamps: both in their softplus epilogue at once, each at half MUFU rate, then both waiting on interleaved MMAs
@@ -86,10 +84,12 @@ __device__ __forceinline__ float epilogue_group(const uint32_t (&r)[16], uint32_
   for (int j = 0; j < 16; j += 4) {
     float4 e4 = *reinterpret_cast<const float4*>(e + j);
     float4 b4 = FIRST ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b + j);
-    float z0 = FIRST ? __uint_as_float(r[j]) * e4.x : (__uint_as_float(r[j]) * inv + b4.x) * e4.x;
-    float z1 = FIRST ? __uint_as_float(r[j + 1]) * e4.y : (__uint_as_float(r[j + 1]) * inv + b4.y) * e4.y;
-    float z2 = FIRST ? __uint_as_float(r[j + 2]) * e4.z : (__uint_as_float(r[j + 2]) * inv + b4.z) * e4.z;
-    float z3 = FIRST ? __uint_as_float(r[j + 3]) * e4.w : (__uint_as_float(r[j + 3]) * inv + b4.w) * e4.w;
+    // (acc*inv + b) as one FMA: the pre-activation differs from the reference's two roundings by < 1 ulp, far
+    // below the reordering of the 128-term sums it comes from
+    float z0 = FIRST ? __uint_as_float(r[j]) * e4.x : fmaf(__uint_as_float(r[j]), inv, b4.x) * e4.x;
+    float z1 = FIRST ? __uint_as_float(r[j + 1]) * e4.y : fmaf(__uint_as_float(r[j + 1]), inv, b4.y) * e4.y;
+    float z2 = FIRST ? __uint_as_float(r[j + 2]) * e4.z : fmaf(__uint_as_float(r[j + 2]), inv, b4.z) * e4.z;
+    float z3 = FIRST ? __uint_as_float(r[j + 3]) * e4.w : fmaf(__uint_as_float(r[j + 3]), inv, b4.w) * e4.w;
     if (CLAMP) { z0 = fminf(z0, 126.f); z1 = fminf(z1, 126.f); z2 = fminf(z2, 126.f); z3 = fminf(z3, 126.f); }
     float h0 = lg2_1p_ex2(z0), h1 = lg2_1p_ex2(z1), h2 = lg2_1p_ex2(z2), h3 = lg2_1p_ex2(z3);
     ss = fmaf(h0, h0, ss); ss = fmaf(h1, h1, ss); ss = fmaf(h2, h2, ss); ss = fmaf(h3, h3, ss);
@@ -100,9 +100,11 @@ __device__ __forceinline__ float epilogue_group(const uint32_t (&r)[16], uint32_
 }
 
 // This warp's 64 columns of one hidden layer: 4 groups, TMEM loads software-pipelined one group ahead.
+constexpr int HANDOFF_GROUP = UPD_HANDOFF_GROUP;   // the MUFU turn is handed over after this many of the 4 groups
+
 template <bool FIRST, bool CLAMP>
 __device__ __forceinline__ float epilogue_half(uint32_t buf, const float* __restrict__ e, const float* __restrict__ b,
-                                               float inv) {
+                                               float inv, int tile_id) {
   float ss = 0.f;
   uint32_t r[16], rn[16], o[16];
   tc::tmem_ld16(buf, r);
@@ -112,6 +114,7 @@ __device__ __forceinline__ float epilogue_half(uint32_t buf, const float* __rest
     if (q < 3) tc::tmem_ld16(buf + 16u * (q + 1), rn);
     ss += epilogue_group<FIRST, CLAMP>(r, o, e + 16 * q, b + 16 * q, inv);
     tc::tmem_st16(buf + 16u * q, o);
+    if (q == HANDOFF_GROUP - 1) mufu_turn_end(tile_id);
     if (q < 3) {
       tc::wait_ld();
 #pragma unroll
@@ -139,8 +142,9 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   constexpr uint32_t STEP_BYTES = NS ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
   const uint32_t steps_off = upd_align128(L.tc_image_bytes);
   const uint32_t xch_off = upd_align128(steps_off + STEP_BYTES * p.T);
-  // exchange area per tile: ssx[3 layers][2 halves][128 rows], headx[2F][128 rows]
-  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 3 * UPD_MAX_F * 128;
+  // exchange area per tile: ssx[2 layers][2 halves][128 rows]; headx[1 + 7F][128 rows] = layer-3 sum of squares,
+  // F eps sums, F noise draws, 5F sigma-head sums handed from the half-1 warp to the row's owner
+  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0 && F > 1) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
   const uint32_t sync_off = upd_align128(xch_off + 2 * XCH_TILE_FLOATS * 4);
   TcSync* sync = reinterpret_cast<TcSync*>(smem + sync_off);
 
@@ -187,8 +191,8 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   const uint32_t mma0 = tmem_base + col0, mma1 = mma0 + 128u;
   const uint32_t bar = tc::smem_u32(&sync->mma_bar[tile_id]);
   const uint32_t img = tc::smem_u32(smem);
-  float* ssx = sf(xch_off) + tile_id * XCH_TILE_FLOATS;     // [3][2][128]
-  float* headx = ssx + 3 * 2 * 128;                         // [2F][128] head partial sums, then [F][128] noise
+  float* ssx = sf(xch_off) + tile_id * XCH_TILE_FLOATS;     // [2][2][128]
+  float* headx = ssx + ((NS && F > 1) ? 3 : 2) * 2 * 128;   // [1 + 7F][128] (single-pass heads) or [3F][128]
   // named barriers: 1,2 = all 256 threads of a tile (precede every MMA issue); 5..12 = the two warps that share
   // a TMEM lane quadrant (64 threads), for the half<->half exchanges that need no tile-wide rendezvous
   const int full_bar = 1 + tile_id, pair_bar = 5 + tile_id * 4 + quad;
@@ -201,6 +205,14 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   const float* w4 = sf(L.w4) + 64 * half;
   const float* wsg = sf(L.ws) + 64 * half;
   uint32_t phase = 0;
+  // c0 * sum_j ws[f][j]: the constant term of the sigma-head polynomial (see layer-3 epilogue)
+  float ws_sum[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) {
+    float a = 0.f;
+    if (NS) for (int j = 0; j < 128; ++j) a += sf(L.ws)[f * 128 + j];
+    ws_sum[f] = SPU_C0 * a;
+  }
 
   const long long n_tiles = (p.n_rows + 127) / 128;
 #ifdef UPD_TRACE
@@ -282,8 +294,8 @@ sampler_tc_kernel(const UpdSamplerParams p) {
 
       // ---------------- layer 1 epilogue -> A2 (in place, buf1); layer 2 ----------------
       mufu_turn_begin(tile_id);
-      float ss = epilogue_half<true, true>(my1, e1 + t * 128, nullptr, 1.f);
-      mufu_turn_end(tile_id);
+      UPD_STAMP(13);
+      float ss = epilogue_half<true, true>(my1, e1 + t * 128, nullptr, 1.f, tile_id);
       if (NS) ssx[(0 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
       UPD_STAMP(3);
@@ -303,8 +315,8 @@ sampler_tc_kernel(const UpdSamplerParams p) {
 
       // ---------------- layer 2 epilogue -> A3 (in place, buf0); layer 3 ----------------
       mufu_turn_begin(tile_id);
-      ss = epilogue_half<false, !NS>(my0, e2 + t * 128, b2, inv);
-      mufu_turn_end(tile_id);
+      UPD_STAMP(14);
+      ss = epilogue_half<false, !NS>(my0, e2 + t * 128, b2, inv, tile_id);
       if (NS) ssx[(1 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
       UPD_STAMP(6);
@@ -322,98 +334,181 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       tc::fence_after_sync();
       UPD_STAMP(8);
 
+      if constexpr (!(NS && F > 1)) {
       // ---------------- layer 3 epilogue + heads (denoise.py:50 / tmdm_model.py:63) ----------------
+      // NsDiff heads read hn = h/||h|| (= L/||L||): eps = lin4(hn), sigma = softplus(sigma_lin(softplus(hn))).
+      // ||L|| is only known once the whole row is done, so instead of a second pass over the row the layer-3
+      // epilogue accumulates everything the heads need as sums that are rescaled afterwards:
+      //   lin4(hn)                 = inv3 * sum_j w4_j L_j
+      //   sigma_lin(softplus(hn))  = sum_j ws_j (hn_j/2 + P(hn_j^2))          (hn_j in [0,1], P above)
+      //                            = inv3/2 * sum_j ws_j L_j + c0 * sum_j ws_j + sum_k c_k inv3^(2k) * sum_j ws_j L_j^(2k)
+      // i.e. the weighted power sums M_k = sum_j ws_j L_j^(2k), k = 1..4.  These FMAs ride in the MUFU-bound
+      // phase, where issue slots are free; no TMEM round trip of the row, no second pass.
+      float pe[F], pb[F], m1[F], m2[F], m3[F], m4[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) { pe[f] = 0.f; pb[f] = 0.f; m1[f] = 0.f; m2[f] = 0.f; m3[f] = 0.f; m4[f] = 0.f; }
+      const float* e3t = e3 + t * 128;
+      ss = 0.f;
+      mufu_turn_begin(tile_id);
+      UPD_STAMP(15);
+      {
+        uint32_t r[16], rn[16];
+        tc::tmem_ld16(my1, r);
+        tc::wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (q < 3) tc::tmem_ld16(my1 + 16u * (q + 1), rn);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int c = 16 * q + j;
+            float h = lg2_1p_ex2(fminf(fmaf(__uint_as_float(r[j]), inv, b3[c]) * e3t[c], 126.f));
+            if (NS) {
+              float u = h * h;
+              ss += u;
+              float u2 = u * u, u3 = u2 * u, u4 = u2 * u2;
+#pragma unroll
+              for (int f = 0; f < F; ++f) {
+                const float wv = wsg[f * 128 + c];
+                pe[f] = fmaf(w4[f * 128 + c], h, pe[f]);
+                pb[f] = fmaf(wv, h, pb[f]);
+                m1[f] = fmaf(wv, u, m1[f]);
+                m2[f] = fmaf(wv, u2, m2[f]);
+                m3[f] = fmaf(wv, u3, m3[f]);
+                m4[f] = fmaf(wv, u4, m4[f]);
+              }
+            } else {
+#pragma unroll
+              for (int f = 0; f < F; ++f) pe[f] = fmaf(w4[f * 128 + c], h, pe[f]);
+            }
+          }
+          if (q < 3) {
+            tc::wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r[i] = rn[i];
+          }
+        }
+      }
+      mufu_turn_end(tile_id);
+      UPD_STAMP(9);
+      const bool last = (t == 0);
+      if (!owner) {
+        // the half that owns no row state hands over its partial sums and draws this step's noise
+        headx[0 * 128 + trow] = ss;
+#pragma unroll
+        for (int f = 0; f < F; ++f) {
+          headx[(1 + f) * 128 + trow] = pe[f];
+          headx[(1 + F + f) * 128 + trow] = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
+          if (NS) {
+            headx[(1 + 2 * F + f) * 128 + trow] = pb[f];
+            headx[(1 + 3 * F + f) * 128 + trow] = m1[f];
+            headx[(1 + 4 * F + f) * 128 + trow] = m2[f];
+            headx[(1 + 5 * F + f) * 128 + trow] = m3[f];
+            headx[(1 + 6 * F + f) * 128 + trow] = m4[f];
+          }
+        }
+        __threadfence_block();
+        tc::named_bar_arrive(pair_bar, 64);
+      } else {
+        tc::named_bar_sync(pair_bar, 64);
+        UPD_STAMP(10);
+        // ---------------- posterior update (owner warps) ----------------
+        if (NS) {
+          const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
+          const float inv3 = 1.0f / fmaxf(sqrtf(ss + headx[trow]), 1e-12f);
+          const float i2 = inv3 * inv3, i4 = i2 * i2;
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float eps = (pe[f] + headx[(1 + f) * 128 + trow]) * inv3 + sf(L.b4)[f];
+            float lin = 0.5f * inv3 * (pb[f] + headx[(1 + 2 * F + f) * 128 + trow]);
+            float poly = fmaf(i2, SPU_C1 * (m1[f] + headx[(1 + 3 * F + f) * 128 + trow]), ws_sum[f]);
+            poly = fmaf(i4, SPU_C2 * (m2[f] + headx[(1 + 4 * F + f) * 128 + trow]), poly);
+            poly = fmaf(i4 * i2, SPU_C3 * (m3[f] + headx[(1 + 5 * F + f) * 128 + trow]), poly);
+            poly = fmaf(i4 * i4, SPU_C4 * (m4[f] + headx[(1 + 6 * F + f) * 128 + trow]), poly);
+            float sig = upd_softplus_accurate(lin + poly + sf(L.bs)[f]);
+            y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, headx[(1 + F + f) * 128 + trow], last);
+          }
+        } else {
+          const UpdTmStep st = reinterpret_cast<const UpdTmStep*>(smem + steps_off)[t];
+#pragma unroll
+          for (int f = 0; f < F; ++f) {
+            float eps = (pe[f] + headx[(1 + f) * 128 + trow]) * LN2 + sf(L.b4)[f];
+            y[f] = upd_tm_update(st, y[f], y0h[f], eps, headx[(1 + F + f) * 128 + trow], last);
+          }
+        }
+      }
+      } else {
+      // ---------------- layer 3 epilogue + heads, two passes (NsDiff, F > 1) ----------------
+      // With several features the head sums cost 6F FMAs per element, which would make the MUFU turn issue-bound;
+      // here pass 1 (in the MUFU turn) only produces L3 and its sum of squares, and pass 2 (outside the turn,
+      // overlapping the other tile's softplus) evaluates the heads on hn = L3/||L3|| re-read from TMEM.
       float pe[F], ps[F];
 #pragma unroll
       for (int f = 0; f < F; ++f) { pe[f] = 0.f; ps[f] = 0.f; }
       const float* e3t = e3 + t * 128;
       mufu_turn_begin(tile_id);
-      if (NS) {
-        // pass 1: L3 kept in TMEM as fp32 (in place), partial sum of squares
-        ss = 0.f;
+      UPD_STAMP(15);
+      ss = 0.f;
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          uint32_t r[16];
-          tc::tmem_ld16(my1 + 16u * q, r);
-          tc::wait_ld();
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[16];
+        tc::tmem_ld16(my1 + 16u * q, r);
+        tc::wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float h = lg2_1p_ex2((__uint_as_float(r[j]) * inv + b3[16 * q + j]) * e3t[16 * q + j]);
-            ss = fmaf(h, h, ss);
-            r[j] = __float_as_uint(h);
-          }
-          tc::tmem_st16(my1 + 16u * q, r);
+        for (int j = 0; j < 16; ++j) {
+          float h = lg2_1p_ex2(fminf(fmaf(__uint_as_float(r[j]), inv, b3[16 * q + j]) * e3t[16 * q + j], 126.f));
+          ss = fmaf(h, h, ss);
+          r[j] = __float_as_uint(h);
         }
-        ssx[(2 * 2 + half) * 128 + trow] = ss;
-        mufu_turn_end(tile_id);
-        tc::wait_st();
-        UPD_STAMP(9);
-        tc::named_bar_sync(pair_bar, 64);
-        UPD_STAMP(10);
-        // pass 2: hn = L3/||L3|| (= h/||h||, components in [0,1]);  eps = sum w4*hn,  sigma ~ sum ws*softplus(hn)
-        const float inv3 = 1.0f / fmaxf(sqrtf(ssx[4 * 128 + trow] + ssx[5 * 128 + trow]), 1e-12f);
+        tc::tmem_st16(my1 + 16u * q, r);
+      }
+      ssx[(2 * 2 + half) * 128 + trow] = ss;
+      mufu_turn_end(tile_id);
+      tc::wait_st();
+      UPD_STAMP(9);
+      tc::named_bar_sync(pair_bar, 64);
+      UPD_STAMP(10);
+      const float inv3 = 1.0f / fmaxf(sqrtf(ssx[4 * 128 + trow] + ssx[5 * 128 + trow]), 1e-12f);
 #pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          uint32_t r[16];
-          tc::tmem_ld16(my1 + 16u * q, r);
-          tc::wait_ld();
+      for (int q = 0; q < 4; ++q) {
+        uint32_t r[16];
+        tc::tmem_ld16(my1 + 16u * q, r);
+        tc::wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float hn = __uint_as_float(r[j]) * inv3;
-            float sp = softplus_unit(hn);
+        for (int j = 0; j < 16; ++j) {
+          const float hn = __uint_as_float(r[j]) * inv3, u = hn * hn;
+          float sp = fmaf(SPU_C4, u, SPU_C3);
+          sp = fmaf(sp, u, SPU_C2);
+          sp = fmaf(sp, u, SPU_C1);
+          sp = fmaf(sp, u, SPU_C0);
+          sp = fmaf(0.5f, hn, sp);
 #pragma unroll
-            for (int f = 0; f < F; ++f) {
-              pe[f] = fmaf(w4[f * 128 + 16 * q + j], hn, pe[f]);
-              ps[f] = fmaf(wsg[f * 128 + 16 * q + j], sp, ps[f]);
-            }
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
-          uint32_t r[16];
-          tc::tmem_ld16(my1 + 16u * q, r);
-          tc::wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float h = lg2_1p_ex2(fminf((__uint_as_float(r[j]) * inv + b3[16 * q + j]) * e3t[16 * q + j], 126.f));
-#pragma unroll
-            for (int f = 0; f < F; ++f) pe[f] = fmaf(w4[f * 128 + 16 * q + j], h, pe[f]);
+          for (int f = 0; f < F; ++f) {
+            pe[f] = fmaf(w4[f * 128 + 16 * q + j], hn, pe[f]);
+            ps[f] = fmaf(wsg[f * 128 + 16 * q + j], sp, ps[f]);
           }
         }
-        mufu_turn_end(tile_id);
       }
       const bool last = (t == 0);
       UPD_STAMP(11);
       if (!owner) {
-        // the idle half hands over its partial sums and draws this step's noise for the owner
 #pragma unroll
         for (int f = 0; f < F; ++f) {
           headx[f * 128 + trow] = pe[f];
-          if (NS) headx[(F + f) * 128 + trow] = ps[f];
+          headx[(F + f) * 128 + trow] = ps[f];
           headx[(2 * F + f) * 128 + trow] = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
         }
         __threadfence_block();
         tc::named_bar_arrive(pair_bar, 64);
       } else {
         tc::named_bar_sync(pair_bar, 64);
-        // ---------------- posterior update (owner warps) ----------------
-        if (NS) {
-          const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
+        const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
 #pragma unroll
-          for (int f = 0; f < F; ++f) {
-            float eps = (pe[f] + headx[f * 128 + trow]) + sf(L.b4)[f];
-            float sig = upd_softplus_accurate((ps[f] + headx[(F + f) * 128 + trow]) + sf(L.bs)[f]);
-            y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, headx[(2 * F + f) * 128 + trow], last);
-          }
-        } else {
-          const UpdTmStep st = reinterpret_cast<const UpdTmStep*>(smem + steps_off)[t];
-#pragma unroll
-          for (int f = 0; f < F; ++f) {
-            float eps = (pe[f] + headx[f * 128 + trow]) * LN2 + sf(L.b4)[f];
-            y[f] = upd_tm_update(st, y[f], y0h[f], eps, headx[(2 * F + f) * 128 + trow], last);
-          }
+        for (int f = 0; f < F; ++f) {
+          float eps = (pe[f] + headx[f * 128 + trow]) + sf(L.b4)[f];
+          float sig = upd_softplus_accurate((ps[f] + headx[(F + f) * 128 + trow]) + sf(L.bs)[f]);
+          y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, headx[(2 * F + f) * 128 + trow], last);
         }
+      }
       }
       UPD_STAMP(12);
     }
@@ -432,7 +527,7 @@ template <int KIND, int F>
 cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
   constexpr uint32_t STEP_BYTES = (KIND == 0) ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
-  constexpr uint32_t XCH_TILE_FLOATS = 3 * 2 * 128 + 3 * UPD_MAX_F * 128;
+  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0 && F > 1) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
   size_t smem = upd_align128(upd_align128(upd_align128(L.tc_image_bytes) + STEP_BYTES * p.T) + 2 * XCH_TILE_FLOATS * 4) +
                 sizeof(TcSync) + 128;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
