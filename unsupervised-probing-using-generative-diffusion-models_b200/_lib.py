@@ -35,7 +35,7 @@ def lib():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
+    path = os.environ.get("UPD_LIB_PATH", _build.LIB_PATH)     # override: debug / experimental builds of csrc/
     if not os.path.exists(path):
         raise RuntimeError(
             "CUDA library {} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
