@@ -160,6 +160,72 @@ typedef struct UpdSigmaWeights {
 int upd_sigma_estimation(const UpdSigmaWeights* w_dev_ptrs, const float* x_dev, int rows, int L, int R,
                          int F, int H, int O, float add_eps, float* gx_dev, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * DiffusionTS conditional sampler.  The x0-predicting transformer runs above this ABI
+ * (library GEMMs + these kernels); the entry points below are the per-step algebra of
+ * Diffusion_TS.fast_sample_infill (models/Diffusion_model/DiffusionTS/DiffusionTS.py:277-310) and the
+ * Fourier seasonal head.  n = number of fp32 elements; every pointer is device memory.
+ * ------------------------------------------------------------------------------------------ */
+
+/* upd_dts_ddim_step -- replaces model_predictions' clamp / predict_noise_from_start and the DDIM mean
+ *   (DiffusionTS.py:152-160, :294-303):  x_start = clamp(x0_raw,-1,1);
+ *   pred_noise = (sqrt_recip_ac*img - x_start)/sqrt_recipm1_ac; pred_mean = x_start*sqrt_alpha_next + c*pred_noise;
+ *   img_out = pred_mean + sigma*noise.  last != 0 (time_next < 0, :291-293): img_out = x_start.
+ *   x_start_dev / pred_mean_dev may be NULL; noise_dev may be NULL when sigma == 0 (eta = 0). */
+int upd_dts_ddim_step(const float* x0_raw_dev, const float* img_dev, long long n,
+                      float sqrt_recip_ac, float sqrt_recipm1_ac, float sqrt_alpha_next, float c, float sigma,
+                      const float* noise_dev, int last, float* x_start_dev, float* pred_mean_dev, float* img_out_dev,
+                      void* stream);
+
+/* upd_dts_adagrad_step -- replaces one iteration of langevin_fn's optimiser (DiffusionTS.py:384-401): a
+ *   torch.optim.Adagrad created anew each iteration, i.e. p -= lr * g / (sqrt(g*g) + 1e-10), in place. */
+int upd_dts_adagrad_step(float* p_dev, const float* grad_dev, long long n, float lr, void* stream);
+
+/* upd_dts_infill -- replaces `sample[~mask] = refined[~mask]` (:404) followed by
+ *   `img[mask] = q_sample(target, t)[mask]` (:305-306, q_sample :232-237) for the mask evaluation_step builds
+ *   (first L_obs positions observed, DiffusionTS_model.py:47-54).  target_dev [rows, L_obs, F];
+ *   noise_dev [rows, seq, F] = the full draw q_sample makes, or NULL: observed part = target (final
+ *   overwrite, :308).  img_dev [rows, seq, F] is written, refined_dev [rows, seq, F] is read (may alias img). */
+int upd_dts_infill(float* img_dev, const float* refined_dev, const float* target_dev, const float* noise_dev,
+                   long long rows, int seq, int L_obs, int F, float sqrt_ac, float sqrt_one_minus_ac, void* stream);
+
+/* upd_gauss_fill -- N(0,1) draws (Philox4x32-10 + Box-Muller) keyed by (seed, row_base + row, element, draw):
+ *   production replacement of torch.randn / randn_like in the DiffusionTS and DiffSTG loops, independent of how
+ *   rows are batched per launch or sharded over GPUs.  out_dev [rows, row_elems]. */
+int upd_gauss_fill(float* out_dev, long long rows, long long row_elems, uint64_t seed, uint64_t row_base,
+                   uint32_t draw, void* stream);
+
+/* upd_dts_fourier_topk / _bwd -- replaces FourierLayer.forward (diffusionts_transformer.py:52-103) and its
+ *   autograd backward.  spec_dev [rows, >= 2*NF, D] with row stride spec_row_stride floats: planes 0..NF-1 = Re,
+ *   NF..2NF-1 = Im of rfft bins low..low+NF-1 along the sequence axis (the caller folds the DFT into the 1x1
+ *   projection GEMM that precedes it).  top_k = int(log(NF)) <= 8 bins of largest |X| per (row, channel) are kept and
+ *   resynthesised over seq positions; season_dev [rows, seq, D] is overwritten or accumulated into; idx_dev
+ *   [rows, top_k, D] (int32) records the selection for the backward.  _bwd: gspec_dev must be zero-filled. */
+int upd_dts_fourier_topk(const float* spec_dev, long long spec_row_stride, long long rows, int NF, int low, int seq,
+                         int D, int top_k, int accumulate, float* season_dev, int* idx_dev, void* stream);
+int upd_dts_fourier_topk_bwd(const float* gseason_dev, const int* idx_dev, long long gspec_row_stride, long long rows,
+                             int NF, int low, int seq, int D, int top_k, float* gspec_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DiffSTG graph-conv sampler.
+ * ------------------------------------------------------------------------------------------ */
+
+/* upd_stg_posterior -- replaces gaussian_posterior (models/Diffusion_model/DiffSTG/graph_diffusion_model.py:46-73):
+ *   out = a*(xt - b*pred) + c*w with w = z_dev (DDPM branch, t <= 1: a = 1/sqrt(alpha_t),
+ *   b = (1-alpha_t)/sqrt(1-abar_t), c = sqrt(beta_tilde)) or w = pred (z_dev NULL, DDIM: a = sqrt(abar_target/abar_t),
+ *   b = sqrt(1-abar_t), c = sqrt(1-abar_target)).  The caller forms a, b, c in float64 like the reference. */
+int upd_stg_posterior(const float* xt_dev, const float* pred_dev, const float* z_dev, long long n,
+                      float a, float b, float c, float* out_dev, void* stream);
+
+/* upd_stg_gated_aggregate -- replaces SpatialBlock's relu(ResGatedGraphConv(x, edge_index))
+ *   (models/Diffusion_model/DiffSTG/ugnet.py:36-45; torch_geometric 2.5.3 layer, bias=True, root_weight=True) after
+ *   its four projections, and duplicate_edge_index (graph_diffusion_model.py:77-84):
+ *   kqvs_dev [N, 4C] = (key | query | value | skip) rows from ONE fused GEMM, N = n_rep * V nodes, replica r owns
+ *   nodes r*V..r*V+V-1 and shares the CSR of the V-node graph: rowptr_dev [V+1], col_dev [E] = sources j of the
+ *   edges j -> i, in edge order.  out[n,:] = act(sum_j sigmoid(k_n + q_j) * v_j + skip_n + bias). */
+int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const int* col_dev, const float* bias_dev,
+                            long long N, int V, int C, int relu, float* out_dev, void* stream);
+
 /* Known-answer self test of the tcgen05 descriptors this library relies on: D[128,N] = A[128,K] * B[N,K]^T
  * with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K=128; mode 1: tf32 hi/lo
  * 3-pass, K=8*k8); flags bit 0 swaps the descriptor's LBO/SBO (negative control: must give a wrong D).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */

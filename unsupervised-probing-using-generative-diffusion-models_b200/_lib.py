@@ -12,7 +12,8 @@ _LIB = None
 SYMBOLS = (
     "upd_error_string", "upd_last_cuda_error", "upd_abi_version", "upd_denoiser_pack_bytes", "upd_denoiser_pack",
     "upd_nsdiff_sample", "upd_tmdm_sample", "upd_mpv_scratch_bytes", "upd_mpv_reduce", "upd_sigma_estimation",
-    "upd_selftest_umma",
+    "upd_selftest_umma", "upd_dts_ddim_step", "upd_dts_adagrad_step", "upd_dts_infill", "upd_gauss_fill",
+    "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_stg_posterior", "upd_stg_gated_aggregate",
 )
 
 KIND_NSDIFF, KIND_TMDM = 0, 1
@@ -62,6 +63,23 @@ def lib():
     L.upd_sigma_estimation.argtypes = [ctypes.POINTER(UpdSigmaWeights), vp, i, i, i, i, i, i, ctypes.c_float, vp, vp]
     L.upd_selftest_umma.restype = ctypes.c_int
     L.upd_selftest_umma.argtypes = [vp, vp, vp, i, i, i, vp]
+    ll, f32, u32 = ctypes.c_longlong, ctypes.c_float, ctypes.c_uint32
+    L.upd_dts_ddim_step.restype = ctypes.c_int
+    L.upd_dts_ddim_step.argtypes = [vp, vp, ll, f32, f32, f32, f32, f32, vp, i, vp, vp, vp, vp]
+    L.upd_dts_adagrad_step.restype = ctypes.c_int
+    L.upd_dts_adagrad_step.argtypes = [vp, vp, ll, f32, vp]
+    L.upd_dts_infill.restype = ctypes.c_int
+    L.upd_dts_infill.argtypes = [vp, vp, vp, vp, ll, i, i, i, f32, f32, vp]
+    L.upd_gauss_fill.restype = ctypes.c_int
+    L.upd_gauss_fill.argtypes = [vp, ll, ll, u64, u64, u32, vp]
+    L.upd_dts_fourier_topk.restype = ctypes.c_int
+    L.upd_dts_fourier_topk.argtypes = [vp, ll, ll, i, i, i, i, i, i, vp, vp, vp]
+    L.upd_dts_fourier_topk_bwd.restype = ctypes.c_int
+    L.upd_dts_fourier_topk_bwd.argtypes = [vp, vp, ll, ll, i, i, i, i, i, vp, vp]
+    L.upd_stg_posterior.restype = ctypes.c_int
+    L.upd_stg_posterior.argtypes = [vp, vp, vp, ll, f32, f32, f32, vp, vp]
+    L.upd_stg_gated_aggregate.restype = ctypes.c_int
+    L.upd_stg_gated_aggregate.argtypes = [vp, vp, vp, vp, ll, i, i, i, vp, vp]
     _LIB = L
     return L
 

@@ -18,6 +18,25 @@ cudaError_t upd_launch_sigma(const UpdSigmaWeights& w, const float* x, int rows,
 cudaError_t upd_launch_selftest_umma(const float* a, const float* b, float* d, int K, int mode, int flags,
                                      cudaStream_t stream);
 
+cudaError_t upd_launch_dts_ddim(const float* x0_raw, const float* img, long long n, float sqrt_recip, float sqrt_recipm1,
+                                float sqrt_an, float c, float sigma, const float* noise, int last, float* x_start,
+                                float* pred_mean, float* img_out, int sms, cudaStream_t stream);
+cudaError_t upd_launch_dts_adagrad(float* p, const float* g, long long n, float lr, int sms, cudaStream_t stream);
+cudaError_t upd_launch_dts_infill(float* img, const float* refined, const float* target, const float* noise,
+                                  long long rows, int seq, int L_obs, int F, float sqrt_ac, float sqrt_1mac, int sms,
+                                  cudaStream_t stream);
+cudaError_t upd_launch_gauss_fill(float* out, long long rows, long long row_elems, uint64_t seed, uint64_t row_base,
+                                  uint32_t draw, int sms, cudaStream_t stream);
+cudaError_t upd_launch_dts_fourier_fwd(const float* spec, long long spec_row_stride, long long rows, int NF, int low,
+                                       int seq, int D, int top_k, int accumulate, float* season, int* idx,
+                                       cudaStream_t stream);
+cudaError_t upd_launch_dts_fourier_bwd(const float* gseason, const int* idx, long long gspec_row_stride, long long rows,
+                                       int NF, int low, int seq, int D, int top_k, float* gspec, cudaStream_t stream);
+cudaError_t upd_launch_stg_posterior(const float* xt, const float* pred, const float* z, long long n, float a, float b,
+                                     float c, float* out, int sms, cudaStream_t stream);
+cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr, const int* col, const float* bias,
+                                           long long N, int V, int C, int relu, float* out, int sms, cudaStream_t stream);
+
 namespace {
 
 thread_local int g_last_cuda_error = 0;
@@ -238,6 +257,76 @@ int upd_selftest_umma(const float* a_dev, const float* b_dev, float* d_dev, int 
   if (rc != UPD_OK) return rc;
   cudaError_t e = upd_launch_selftest_umma(a_dev, b_dev, d_dev, K, mode, flags, (cudaStream_t)stream);
   return e == cudaSuccess ? UPD_OK : cuda_fail(e);
+}
+
+#define UPD_DEVICE_OR_RETURN() int sms = 0; { int rc_ = device_info(&sms); if (rc_ != UPD_OK) return rc_; }
+#define UPD_FINISH(e) do { cudaError_t e_ = (e); if (e_ == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED; \
+                           return e_ == cudaSuccess ? UPD_OK : cuda_fail(e_); } while (0)
+
+int upd_dts_ddim_step(const float* x0_raw_dev, const float* img_dev, long long n, float sqrt_recip_ac,
+                      float sqrt_recipm1_ac, float sqrt_alpha_next, float c, float sigma, const float* noise_dev, int last,
+                      float* x_start_dev, float* pred_mean_dev, float* img_out_dev, void* stream) {
+  if (!x0_raw_dev || !img_out_dev || n <= 0) return UPD_ERR_BAD_ARG;
+  if (!last && (!img_dev || (sigma != 0.0f && !noise_dev))) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_ddim(x0_raw_dev, img_dev, n, sqrt_recip_ac, sqrt_recipm1_ac, sqrt_alpha_next, c, sigma,
+                                 noise_dev, last, x_start_dev, pred_mean_dev, img_out_dev, sms, (cudaStream_t)stream));
+}
+
+int upd_dts_adagrad_step(float* p_dev, const float* grad_dev, long long n, float lr, void* stream) {
+  if (!p_dev || !grad_dev || n <= 0) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_adagrad(p_dev, grad_dev, n, lr, sms, (cudaStream_t)stream));
+}
+
+int upd_dts_infill(float* img_dev, const float* refined_dev, const float* target_dev, const float* noise_dev,
+                   long long rows, int seq, int L_obs, int F, float sqrt_ac, float sqrt_one_minus_ac, void* stream) {
+  if (!img_dev || !refined_dev || !target_dev || rows <= 0 || seq <= 0 || F <= 0 || L_obs < 0 || L_obs > seq)
+    return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_infill(img_dev, refined_dev, target_dev, noise_dev, rows, seq, L_obs, F, sqrt_ac,
+                                   sqrt_one_minus_ac, sms, (cudaStream_t)stream));
+}
+
+int upd_gauss_fill(float* out_dev, long long rows, long long row_elems, uint64_t seed, uint64_t row_base, uint32_t draw,
+                   void* stream) {
+  if (!out_dev || rows <= 0 || row_elems <= 0 || row_elems > 0xffffffffLL) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_gauss_fill(out_dev, rows, row_elems, seed, row_base, draw, sms, (cudaStream_t)stream));
+}
+
+int upd_dts_fourier_topk(const float* spec_dev, long long spec_row_stride, long long rows, int NF, int low, int seq, int D,
+                         int top_k, int accumulate, float* season_dev, int* idx_dev, void* stream) {
+  if (!spec_dev || !season_dev || rows <= 0 || NF <= 0 || low < 0 || seq <= 0 || D <= 0 ||
+      spec_row_stride < 2LL * NF * D) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_fourier_fwd(spec_dev, spec_row_stride, rows, NF, low, seq, D, top_k, accumulate, season_dev,
+                                        idx_dev, (cudaStream_t)stream));
+}
+
+int upd_dts_fourier_topk_bwd(const float* gseason_dev, const int* idx_dev, long long gspec_row_stride, long long rows,
+                             int NF, int low, int seq, int D, int top_k, float* gspec_dev, void* stream) {
+  if (!gseason_dev || !idx_dev || !gspec_dev || rows <= 0 || NF <= 0 || low < 0 || seq <= 0 || D <= 0 ||
+      gspec_row_stride < 2LL * NF * D) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_fourier_bwd(gseason_dev, idx_dev, gspec_row_stride, rows, NF, low, seq, D, top_k, gspec_dev,
+                                        (cudaStream_t)stream));
+}
+
+int upd_stg_posterior(const float* xt_dev, const float* pred_dev, const float* z_dev, long long n, float a, float b,
+                      float c, float* out_dev, void* stream) {
+  if (!xt_dev || !pred_dev || !out_dev || n <= 0) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_stg_posterior(xt_dev, pred_dev, z_dev, n, a, b, c, out_dev, sms, (cudaStream_t)stream));
+}
+
+int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const int* col_dev, const float* bias_dev,
+                            long long N, int V, int C, int relu, float* out_dev, void* stream) {
+  if (!kqvs_dev || !rowptr_dev || !col_dev || !out_dev || N <= 0 || V <= 0 || C <= 0 || (N % V) != 0)
+    return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_stg_gated_aggregate(kqvs_dev, rowptr_dev, col_dev, bias_dev, N, V, C, relu, out_dev, sms,
+                                            (cudaStream_t)stream));
 }
 
 }  // extern "C"
