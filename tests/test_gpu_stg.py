@@ -1,0 +1,115 @@
+"""GPU parity of the DiffSTG sampler against fixtures made by the unmodified reference (with the
+published-definition stand-in for torch_geometric's ResGatedGraphConv: that one layer is "parity unpinned").
+Tolerances: eps prediction 1e-4 of its rms; whole evaluation_step (20 DDIM steps + the DDPM tail, injected noise)
+rel 1e-3 per value + 1e-4 x rms floor, as the north star states for trajectories."""
+import json
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import diffusionts_oracle as dto, diffstg_oracle as so
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _load(name):
+    g = np.load("{}/{}".format(GOLDEN, name))
+    return g, json.loads(str(g["cfg"])), json.loads(str(g["keys"])), int(g["seed"])
+
+
+def _weights(shapes, seed):
+    sd = dto.synth_state_dict(shapes, seed)
+    for k in shapes:
+        if ".net.0." in k:
+            sd[k] = sd[k.replace(".net.0.", ".conv.")]
+    return sd
+
+
+def _model(cfg, shapes, seed, **over):
+    from updgm_b200.diffstg import DiffSTG
+    m = DiffSTG(dict(cfg, device=DEV, **over)).eval()
+    own = {k: list(v.shape) for k, v in m.state_dict().items() if k.startswith("model.")}
+    assert own == shapes
+    sd = _weights(shapes, seed)
+    sd["scaler_mean"], sd["scaler_std"] = torch.zeros(cfg["F"]), torch.ones(cfg["F"])
+    m.load_state_dict(sd, strict=True)
+    return m, sd
+
+
+def _rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.pow(2).mean().sqrt())
+
+
+@pytest.mark.parametrize("name", ["stg_small_evalstep.npz", "stg_yaml_evalstep.npz"])
+def test_eps_prediction_matches_reference(name):
+    g, cfg, shapes, seed = _load(name)
+    m, _ = _model(cfg, shapes, seed)
+    x, ei = torch.from_numpy(g["x"]), torch.from_numpy(g["edge_index"])
+    V = x.shape[0]
+    xm = torch.cat([x, torch.zeros(V, cfg["T_p"], 1)], 1).to(DEV)
+    for t in (1, cfg["diffusion_steps"]):
+        e = m.predict_eps(torch.from_numpy(g["eps%d:xt" % t]).to(DEV), xm, t, ei, V)
+        assert _rel(e, torch.from_numpy(g["eps%d:out" % t])) < 1e-4, (t, _rel(e, torch.from_numpy(g["eps%d:out" % t])))
+
+
+@pytest.mark.parametrize("name", ["stg_small_evalstep.npz", "stg_yaml_evalstep.npz"])
+def test_evaluation_step_matches_reference(name):
+    from updgm_b200.diffstg import GraphData
+    g, cfg, shapes, seed = _load(name)
+    m, _ = _model(cfg, shapes, seed)
+    x, ei = torch.from_numpy(g["x"]), torch.from_numpy(g["edge_index"])
+    V = x.shape[0]
+    draws = [torch.from_numpy(g["z%03d" % i]) for i in range(int(g["n_draws"]))]
+    per = m.draws_per_round()
+    assert per * cfg["sequential_sampling"] == len(draws)
+    noise = [draws[r * per:(r + 1) * per] for r in range(cfg["sequential_sampling"])]
+    outs, truth = m.evaluation_step(GraphData(x=x.to(DEV), edge_index=ei, num_nodes=V), noise=noise)
+    ref = torch.from_numpy(g["outs"])
+    assert truth is None and tuple(outs.shape) == tuple(ref.shape) and outs.device.type == "cpu"
+    rms = ref.double().pow(2).mean().sqrt()
+    d = (outs.double() - ref.double()).abs()
+    assert (d <= 1e-3 * ref.abs().double() + 1e-4 * rms).all(), float(d.max() / rms)
+
+
+def test_batched_replicas_match_single_launches():
+    """Windows / rounds / replicas are all replicas of the graph: results must not depend on how they are cut."""
+    g, cfg, shapes, seed = _load("stg_small_evalstep.npz")
+    m, _ = _model(cfg, shapes, seed)
+    x, ei = torch.from_numpy(g["x"]), torch.from_numpy(g["edge_index"])
+    V = x.shape[0]
+    wins = torch.stack([x, x.flip(0), x * 0.5], 0).to(DEV)
+    a = m.sample_windows(wins, ei, V, seed=5, window_base=7)
+    m.rows_per_launch = V            # one replica per launch
+    b = m.sample_windows(wins, ei, V, seed=5, window_base=7)
+    c = m.sample_windows(wins[1:], ei, V, seed=5, window_base=8)
+    K = cfg["parallel_sampling"] * cfg["sequential_sampling"]
+    assert tuple(a.shape) == (3 * V, K, cfg["T_h"] + cfg["T_p"], 1)
+    assert _rel(a, b) < 1e-5 and _rel(a[V:], c) < 1e-5
+    assert float(a.var(dim=1).mean()) > 0
+
+
+def test_gated_aggregate_kernel_against_oracle():
+    from updgm_b200 import _lib
+    torch.manual_seed(0)
+    V, C, reps = 7, 48, 3
+    ei = torch.tensor([[0, 1, 2, 3, 4, 5, 6, 0, 2, 6, 6], [1, 2, 3, 4, 5, 6, 0, 3, 0, 1, 6]])
+    sd = {"g.lin_%s.weight" % n: torch.randn(C, C) * 0.2 for n in ("key", "query", "value", "skip")}
+    sd.update({"g.lin_%s.bias" % n: torch.randn(C) * 0.1 for n in ("key", "query", "value")})
+    sd["g.bias"] = torch.randn(C) * 0.1
+    x = torch.randn(reps * V, C)
+    ref = torch.relu(so.res_gated_graph_conv(sd, "g.", x, so.duplicate_edge_index(reps, ei, V)))
+    from updgm_b200.diffstg import graph_csr
+    rowptr, col = graph_csr(ei, V)
+    w = torch.cat([sd["g.lin_key.weight"], sd["g.lin_query.weight"], sd["g.lin_value.weight"], sd["g.lin_skip.weight"]], 0)
+    bb = torch.cat([sd["g.lin_key.bias"], sd["g.lin_query.bias"], sd["g.lin_value.bias"], torch.zeros(C)], 0)
+    kqvs = torch.addmm(bb.to(DEV), x.to(DEV), w.to(DEV).t()).contiguous()
+    out = torch.empty(reps * V, C, device=DEV)
+    bias = sd["g.bias"].to(DEV)
+    rp, cl = rowptr.to(DEV), col.to(DEV)
+    _lib.check(_lib.lib().upd_stg_gated_aggregate(_lib.ptr(kqvs), _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(bias), reps * V, V, C,
+                                                  1, _lib.ptr(out), _lib.stream_ptr(torch.device(DEV))), "agg")
+    assert _rel(out, ref) < 1e-5

@@ -6,7 +6,6 @@ import torch
 from . import _lib
 
 NOT_YET = {
-    "DiffSTG": "DiffSTG (graph-conv U-Net sampler) is scheduled after the MLP-denoiser families (SURVEY 8a15)",
     "NsDiff_spatial": "NsDiff_spatial is not referenced by any shipped configuration (SURVEY 8a11)",
 }
 
@@ -27,6 +26,9 @@ def diffusion_models(task_model, net_param, **kwargs):
     if task_model == "DiffusionTS":
         from .diffusionts import DiffusionTS_model
         return DiffusionTS_model(net_param=net_param)
+    if task_model == "DiffSTG":
+        from .diffstg import DiffSTG
+        return DiffSTG(net_param=net_param)
     if task_model in NOT_YET:
         raise NotImplementedError(NOT_YET[task_model])
     raise ValueError("the definition  don't exit\n\tyou can define it before using it")
