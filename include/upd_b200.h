@@ -226,6 +226,15 @@ int upd_stg_posterior(const float* xt_dev, const float* pred_dev, const float* z
 int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const int* col_dev, const float* bias_dev,
                             long long N, int V, int C, int relu, float* out_dev, void* stream);
 
+/* upd_stg_tcn_ln -- replaces the front half of ResidualBlock.forward (models/Diffusion_model/DiffSTG/ugnet.py:117-127):
+ *   tcn1 (causal 3-tap conv + its 1x1 shortcut) + t_conv(time embedding), tcn2, LayerNorm([1,c]) in ONE pass.
+ *   x_dev [N, CI, T] -> hn_dev [N, C, T].  w1_dev [C, CI, 3], w2_dev [C, C, 3]: the middle row of the reference's (3,3)
+ *   kernels (the image height is 1) with the shortcut (or identity) folded into tap 2; b1_dev [C] = conv bias +
+ *   shortcut bias + t_conv(emb(step)); b2_dev [C]; gamma/beta [C].  Limits: C in {4, 8, 16}, T <= 512 and a multiple of 4. */
+int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+                   const float* gamma_dev, const float* beta_dev, long long N, int CI, int C, int T, float* hn_dev,
+                   void* stream);
+
 /* Known-answer self test of the tcgen05 descriptors this library relies on: D[128,N] = A[128,K] * B[N,K]^T
  * with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K=128; mode 1: tf32 hi/lo
  * 3-pass, K=8*k8); flags bit 0 swaps the descriptor's LBO/SBO (negative control: must give a wrong D).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */

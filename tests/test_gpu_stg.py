@@ -113,3 +113,26 @@ def test_gated_aggregate_kernel_against_oracle():
     _lib.check(_lib.lib().upd_stg_gated_aggregate(_lib.ptr(kqvs), _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(bias), reps * V, V, C,
                                                   1, _lib.ptr(out), _lib.stream_ptr(torch.device(DEV))), "agg")
     assert _rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize("C,CI,T", [(8, 4, 400), (16, 32, 200), (4, 12, 40), (16, 16, 20)])
+def test_fused_tcn_layernorm_kernel_against_library_ops(C, CI, T):
+    """upd_stg_tcn_ln == causal conv -> causal conv -> LayerNorm over channels (torch fp32, TF32 off)."""
+    import torch.nn.functional as F
+    from updgm_b200 import _lib
+    torch.manual_seed(C * 1000 + T)
+    N = 37
+    x = torch.randn(N, CI, T, device=DEV)
+    w1, b1 = torch.randn(C, CI, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
+    w2, b2 = torch.randn(C, C, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
+    g, be = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        h = F.conv1d(F.pad(x, (2, 0)), w1, b1)
+        h = F.conv1d(F.pad(h, (2, 0)), w2, b2)
+    ref = F.layer_norm(h.transpose(1, 2), (C,), g, be).transpose(1, 2)
+    out = torch.empty(N, C, T, device=DEV)
+    _lib.check(_lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
+                                         _lib.ptr(be), N, CI, C, T, _lib.ptr(out), _lib.stream_ptr(torch.device(DEV))), "tcn")
+    assert _rel(out, ref) < 2e-5, _rel(out, ref)
+    assert _lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
+                                     _lib.ptr(be), N, CI, 5, T, _lib.ptr(out), None) == 2      # UPD_ERR_UNSUPPORTED

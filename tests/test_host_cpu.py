@@ -253,7 +253,7 @@ def test_factory_names():
     with pytest.raises(ValueError, match="don't exit"):
         loader.diffusion_models("Nope", {})
     with pytest.raises(NotImplementedError):
-        loader.diffusion_models("DiffSTG", {})
+        loader.diffusion_models("NsDiff_spatial", {})
 
 
 # ------------------------------------------------------------------------------------------ N > 1 host path (gloo)

@@ -50,6 +50,116 @@ __global__ void stg_gated_aggregate_kernel(const float* __restrict__ kqvs, const
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Front half of a ResidualBlock (ugnet.py:117-127) in one pass over the activations:
+//     h1 = causal_conv3(x) + b1[step]     (TcnBlock 1: conv + 1x1 shortcut folded into tap 2, + t_conv(time emb))
+//     h2 = causal_conv3(h1) + b2          (TcnBlock 2, identity shortcut folded)
+//     hn = LayerNorm_c(h2) * g + beta     (nn.LayerNorm([1, c]) over the channel axis, eps 1e-5)
+// x [N, CI, T] -> hn [N, C, T].  One CTA per row; x and h1 live in shared memory with a 2-column zero halo on the
+// left (both convolutions are causal and zero-padded); each thread owns 4 consecutive positions x all C channels in
+// registers, so the LayerNorm needs no cross-thread reduction and the store is one float4 per channel.
+// fp32 FFMA: C <= 16 channels is far below a tensor-core tile, and the pass is 3 B/FLOP away from HBM-bound.
+// ------------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict__ x, const float* __restrict__ w1,
+                                                         const float* __restrict__ b1, const float* __restrict__ w2,
+                                                         const float* __restrict__ b2, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, int CI, int T,
+                                                         float* __restrict__ hn) {
+  extern __shared__ __align__(16) float smem[];
+  const int TP = T + 4;                              // row pitch: data starts at column 4 (16-byte aligned, T % 4 == 0),
+                                                     // columns 2,3 are the zero halo of the causal convolutions
+  float* sx = smem;                                  // [CI][TP]
+  float* sh = sx + CI * TP;                          // [C][TP]
+  float* sw1 = sh + C * TP;                          // [CI][3][C]  (tap-major inside a channel, channels contiguous)
+  float* sw2 = sw1 + CI * 3 * C;                     // [C][3][C]
+  const long long n = blockIdx.x;
+  const float* xr = x + n * (long long)CI * T;
+  for (int i = threadIdx.x; i < CI * TP; i += blockDim.x) {
+    int ci = i / TP, t = i - ci * TP;
+    sx[i] = t < 4 ? 0.0f : xr[ci * T + (t - 4)];
+  }
+  for (int i = threadIdx.x; i < C * 4; i += blockDim.x) sh[(i >> 2) * TP + (i & 3)] = 0.0f;
+  for (int i = threadIdx.x; i < CI * 3 * C; i += blockDim.x) {       // w1 [C][CI][3] -> [CI][3][C]
+    int ci = i / (3 * C), r = i - ci * 3 * C, k = r / C, co = r - k * C;
+    sw1[i] = w1[(co * CI + ci) * 3 + k];
+  }
+  for (int i = threadIdx.x; i < C * 3 * C; i += blockDim.x) {
+    int ci = i / (3 * C), r = i - ci * 3 * C, k = r / C, co = r - k * C;
+    sw2[i] = w2[(co * C + ci) * 3 + k];
+  }
+  __syncthreads();
+  const int t0 = threadIdx.x * 4;                    // first of this thread's 4 positions
+  const bool active = t0 < T;
+  float acc[4][C];
+  if (active) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[p][c] = b1[c];
+    for (int ci = 0; ci < CI; ++ci) {
+      float xv[6];                                                                      // x[t0-2 .. t0+3]
+      {
+        const float2 a = *reinterpret_cast<const float2*>(sx + ci * TP + t0 + 2);
+        const float4 b = *reinterpret_cast<const float4*>(sx + ci * TP + t0 + 4);
+        xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y; xv[4] = b.z; xv[5] = b.w;
+      }
+      const float* w = sw1 + ci * 3 * C;
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          float wv = w[k * C + c];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) acc[p][c] = fmaf(wv, xv[p + k], acc[p][c]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      *reinterpret_cast<float4*>(sh + c * TP + 4 + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+  }
+  __syncthreads();
+  if (!active) return;
+#pragma unroll
+  for (int p = 0; p < 4; ++p)
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[p][c] = b2[c];
+  for (int ci = 0; ci < C; ++ci) {
+    float hv[6];
+    {
+      const float2 a = *reinterpret_cast<const float2*>(sh + ci * TP + t0 + 2);
+      const float4 b = *reinterpret_cast<const float4*>(sh + ci * TP + t0 + 4);
+      hv[0] = a.x; hv[1] = a.y; hv[2] = b.x; hv[3] = b.y; hv[4] = b.z; hv[5] = b.w;
+    }
+    const float* w = sw2 + ci * 3 * C;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float wv = w[k * C + c];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[p][c] = fmaf(wv, hv[p + k], acc[p][c]);
+      }
+  }
+  float* out = hn + n * (long long)C * T;
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    float m = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) m += acc[p][c];
+    m *= (1.0f / C);
+    float v = 0.0f;
+#pragma unroll
+    for (int c = 0; c < C; ++c) { float d = acc[p][c] - m; v = fmaf(d, d, v); }
+    float r = rsqrtf(v * (1.0f / C) + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[p][c] = fmaf((acc[p][c] - m) * r, gamma[c], beta[c]);
+  }
+#pragma unroll
+  for (int c = 0; c < C; ++c)
+    *reinterpret_cast<float4*>(out + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+}
+
 inline unsigned stream_grid(long long n, int block, int sms) {
   long long g = (n + block - 1) / block;
   long long cap = (long long)sms * 16;
@@ -67,5 +177,30 @@ cudaError_t upd_launch_stg_posterior(const float* xt, const float* pred, const f
 cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr, const int* col, const float* bias,
                                            long long N, int V, int C, int relu, float* out, int sms, cudaStream_t stream) {
   stg_gated_aggregate_kernel<<<stream_grid(N * C, 256, sms), 256, 0, stream>>>(kqvs, rowptr, col, bias, N, V, C, relu, out);
+  return cudaGetLastError();
+}
+
+cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                  const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
+                                  cudaStream_t stream) {
+  const int threads = ((T / 4) + 31) / 32 * 32;
+  if ((T & 3) != 0 || threads > 128 || CI < 1 || N > 0x7fffffffLL) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(hn) & 15) != 0) return cudaErrorInvalidValue;
+  const size_t smem = sizeof(float) * ((size_t)(CI + C) * (T + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C);
+  if (smem > 200 * 1024) return cudaErrorInvalidValue;
+#define UPD_TCN_CASE(CC)                                                                                             \
+  case CC: {                                                                                                         \
+    cudaError_t e = cudaFuncSetAttribute(stg_tcn_ln_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                  \
+    stg_tcn_ln_kernel<CC><<<(unsigned)N, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, CI, T, hn);         \
+    break;                                                                                                           \
+  }
+  switch (C) {
+    UPD_TCN_CASE(4)
+    UPD_TCN_CASE(8)
+    UPD_TCN_CASE(16)
+    default: return cudaErrorInvalidValue;
+  }
+#undef UPD_TCN_CASE
   return cudaGetLastError();
 }

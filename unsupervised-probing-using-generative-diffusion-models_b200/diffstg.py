@@ -168,6 +168,16 @@ def graph_csr(edge_index, num_nodes):
     return rowptr.to(torch.int32), src[order].to(torch.int32)
 
 
+def gated_aggregate(kqvs, rowptr, col, bias, V, C, relu=True):
+    """relu(sum_j sigmoid(k_i + q_j) * v_j + skip_i + bias) for every replica of the V-node graph (upd_stg_gated_aggregate)."""
+    N = kqvs.shape[0]
+    out = torch.empty((N, C), dtype=torch.float32, device=kqvs.device)
+    rc = _lib.lib().upd_stg_gated_aggregate(_lib.ptr(kqvs), _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(bias), N, V, C,
+                                            1 if relu else 0, _lib.ptr(out), _lib.stream_ptr(kqvs.device))
+    _lib.check(rc, "upd_stg_gated_aggregate")
+    return out
+
+
 class PreparedUGnet:
     """Inference-time weight layout of UGnet (fp32 on the device, built once per model load)."""
 
@@ -209,12 +219,16 @@ class PreparedUGnet:
                 kc = k.clamp(0, T_in)
                 wd = sd[pre + "downsampling.weight"][:, :, 0, :]                     # [co, ci, T+1]
                 md = wd[:, :, kc] * ok                                              # [co, ci, s, tau]
-                b["down_w"] = md.permute(2, 1, 3, 0).reshape(T_in * c_out, Td * c_out).contiguous()   # (s,ci) -> (tau,co)
+                b["down_w"] = md.permute(1, 2, 3, 0).reshape(c_out * T_in, Td * c_out).contiguous()   # (ci,s) -> (tau,co)
                 b["down_b"] = sd[pre + "downsampling.bias"].repeat(Td)
                 wu = sd[pre + "upsampling.weight"][:, :, 0, :]                       # [ci, co, T+1]
                 mu = wu[:, :, kc] * ok                                              # [ci, co, s, tau]
                 b["up_w"] = mu.permute(3, 0, 1, 2).reshape(Td * c_out, c_out * T_in).contiguous()     # (tau,ci) -> (co,s)
-                b["up_b"] = sd[pre + "upsampling.bias"]
+                up_b = sd[pre + "upsampling.bias"]
+                if c_in != c_out:
+                    up_b = up_b + sd[pre + "shortcut.bias"]
+                    b["sc_w2"] = sd[pre + "shortcut.weight"][:, :, 0, 0].contiguous()
+                b["up_b_full"] = up_b.repeat_interleave(T_in).contiguous()               # [c*T], (co, s) order
                 g = pre + "spatial.gnn."
                 C = Td * c_out
                 skip = sd.get(g + "lin_skip.weight")
@@ -224,8 +238,6 @@ class PreparedUGnet:
                       torch.zeros(C, device=dev)]
                 b["kqvs_w"], b["kqvs_b"] = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
                 b["gnn_bias"] = sd.get(g + "bias")
-                if c_in != c_out:
-                    b["sc_w"], b["sc_b"] = sd[pre + "shortcut.weight"][:, :, 0, :].contiguous(), sd[pre + "shortcut.bias"]
             else:
                 b["w"], b["b"] = sd[pre + "conv.weight"][:, :, 0, :].contiguous(), sd[pre + "conv.bias"]
             self.blocks[pre] = b
@@ -233,22 +245,34 @@ class PreparedUGnet:
         self.out0_w, self.out0_b = sd["out.0.weight"][:, :, 0, :].contiguous(), sd["out.0.bias"]
         self.out1_w, self.out1_b = sd["out.1.weight"], sd["out.1.bias"]
 
+    def _front(self, b, x, t, c_in, c_out, T_in):
+        """tcn1 (+ step embedding) -> tcn2 -> LayerNorm over channels: x [N, c_in, T] -> hn [N, c_out, T]."""
+        N = x.shape[0]
+        if c_out in (4, 8, 16) and T_in % 4 == 0 and T_in <= 512:
+            hn = torch.empty((N, c_out, T_in), dtype=torch.float32, device=x.device)
+            rc = _lib.lib().upd_stg_tcn_ln(_lib.ptr(x.contiguous()), _lib.ptr(b["tcn1.w"]), _lib.ptr(b["tcn1.b_step"][t]),
+                                           _lib.ptr(b["tcn2.w"]), _lib.ptr(b["tcn2.b"]), _lib.ptr(b["norm_w"]),
+                                           _lib.ptr(b["norm_b"]), N, c_in, c_out, T_in, _lib.ptr(hn),
+                                           _lib.stream_ptr(x.device))
+            _lib.check(rc, "upd_stg_tcn_ln")
+            return hn
+        # shapes outside the fused kernel's limits: the same arithmetic as library ops
+        h = F.conv1d(F.pad(x, (2, 0)), b["tcn1.w"], b["tcn1.b_step"][t])
+        h = F.conv1d(F.pad(h, (2, 0)), b["tcn2.w"], b["tcn2.b"])
+        var, mu = torch.var_mean(h, dim=1, unbiased=False, keepdim=True)
+        return (h - mu) * torch.rsqrt(var + 1e-5) * b["norm_w"][None, :, None] + b["norm_b"][None, :, None]
+
     def _res(self, pre, x, t, c_in, c_out, T_in, rowptr, col, V):
         b, Td = self.blocks[pre], self.Td_h
         N = x.shape[0]
-        h = F.conv1d(F.pad(x, (2, 0)), b["tcn1.w"], b["tcn1.b_step"][t])
-        h = F.conv1d(F.pad(h, (2, 0)), b["tcn2.w"], b["tcn2.b"])
-        hn = F.layer_norm(h.transpose(1, 2), (c_out,), b["norm_w"], b["norm_b"])            # [N, T, c]
-        sp = torch.addmm(b["down_b"], hn.reshape(N, T_in * c_out), b["down_w"])              # [N, Td*c]
+        hn = self._front(b, x, t, c_in, c_out, T_in)
+        sp = torch.addmm(b["down_b"], hn.view(N, c_out * T_in), b["down_w"])                  # [N, Td*c]
         kqvs = torch.addmm(b["kqvs_b"], sp, b["kqvs_w"].t())                                 # [N, 4C]
-        C = Td * c_out
-        agg = torch.empty((N, C), dtype=torch.float32, device=x.device)
-        rc = _lib.lib().upd_stg_gated_aggregate(_lib.ptr(kqvs), _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(b["gnn_bias"]),
-                                                N, V, C, 1, _lib.ptr(agg), _lib.stream_ptr(x.device))
-        _lib.check(rc, "upd_stg_gated_aggregate")
-        up = (agg @ b["up_w"]).view(N, c_out, T_in) + b["up_b"][None, :, None]
-        sc = x if c_in == c_out else F.conv1d(x, b["sc_w"], b["sc_b"])
-        return up + sc
+        agg = gated_aggregate(kqvs, rowptr, col, b["gnn_bias"], V, Td * c_out)
+        up = torch.addmm(b["up_b_full"], agg, b["up_w"]).view(N, c_out, T_in)                # + upsampling (+ shortcut) bias
+        if c_in == c_out:
+            return up.add_(x)
+        return torch.baddbmm(up, b["sc_w2"].expand(N, c_out, c_in), x)                       # + 1x1 shortcut(x)
 
     def forward(self, xt, x_masked, t, rowptr, col, V):
         """xt, x_masked [N, T, F]; t: int diffusion step shared by all rows -> eps prediction [N, T, F]."""

@@ -385,17 +385,23 @@ def partition_windows(n_windows, world_size, rank):
     return w0, min(n_windows, w0 + per)
 
 
-def sample_sweep(model, stacked_windows, device=None, pin=True, reduce=True, window_offset=0):
+def sample_sweep(model, stacked_windows, device=None, pin=True, reduce=True, window_offset=0, graph_data=None):
     """Sample every window of a sweep.  ``stacked_windows`` [W, B, L, F] in raw units (CPU or device).
     Returns the prediction cache as one CPU tensor [W, B, K, O, F] (pinned); element w of the reference's
     list is ``cache[w].permute(0, 2, 3, 1)``.  Work is cut into launches of at most SWEEP_BATCH_BYTES.
     With ``reduce`` the per-window MPV / mean statistics are computed on the device in the same pass
     (both in scaled units and, when the model has a scaler, in raw units) and remembered for the
-    summarize_* functions; they are also returned as ``cache.upd_stats`` (dict of CPU tensors)."""
+    summarize_* functions; they are also returned as ``cache.upd_stats`` (dict of CPU tensors).
+    ``graph_data`` (DiffSTG only): object with ``edge_index`` / ``num_nodes``; every window, sampling round and
+    parallel replica is then a replica of that graph inside one launch (:369-391)."""
     device = device or _model_device(model)
     W, B = stacked_windows.shape[0], stacked_windows.shape[1]
-    probe_k = _samples_per_row(model)
-    O, F = model.pred_len, model.dataset_nf
+    if graph_data is not None:
+        probe_k = int(model.parallel_sampling) * int(model.sequential_sampling)
+        O, F = model.T_p, model.F
+    else:
+        probe_k = _samples_per_row(model)
+        O, F = model.pred_len, model.dataset_nf
     per_window = B * probe_k * O * F * 4
     step = max(1, min(W, SWEEP_BATCH_BYTES // max(per_window, 1)))
     cache = torch.empty((W, B, probe_k, O, F), dtype=torch.float32, pin_memory=pin and torch.cuda.is_available())
@@ -405,7 +411,11 @@ def sample_sweep(model, stacked_windows, device=None, pin=True, reduce=True, win
     for w0 in range(0, W, step):
         w1 = min(W, w0 + step)
         x = _scale_windows(model, stacked_windows[w0:w1], device)
-        traj = model.sample_windows(x, window_base=base + w0)
+        if graph_data is not None:
+            traj = model.sample_windows(x, graph_data.edge_index, int(graph_data.num_nodes), window_base=base + w0)
+            traj = traj[:, :, -O:, :].contiguous()
+        else:
+            traj = model.sample_windows(x, window_base=base + w0)
         cache[w0:w1].copy_(traj.view(w1 - w0, B, probe_k, O, F), non_blocking=True)
         if reduce:
             parts["scaled"].append(kernels.mpv_reduce(traj, w1 - w0, B, want_mean=True))
@@ -543,15 +553,35 @@ def run_slbp_gx_cache_for_fig6(model, input_datas, cache_path, device, pred_dim=
 
 
 def load_diffstg_graph(graph_file):
-    raise NotImplementedError("DiffSTG is scheduled after the MLP-denoiser families (SURVEY 8a15)")
+    """:342-351: graphml -> graph object with ``edge_index`` [2,E] int64 and ``num_nodes``.  The reference goes through
+    networkx + torch_geometric.utils.from_networkx; the same edge order is produced here without torch_geometric:
+    nodes relabelled 0..V-1 in file order, an undirected graph contributes both directions, edges listed per source
+    node in adjacency (insertion) order -- what ``list(G.to_directed().edges)`` yields."""
+    import networkx as nx
+    from .diffstg import GraphData
+    if graph_file is None:
+        raise ValueError("graph_file is required for DiffSTG.")
+    graph_file = _resolve_project_path(graph_file)
+    nx_g = nx.read_graphml(graph_file)
+    nx_g = nx.convert_node_labels_to_integers(nx_g)
+    directed = nx_g if nx.is_directed(nx_g) else nx_g.to_directed()
+    edges = list(directed.edges)
+    edge_index = torch.tensor(edges, dtype=torch.long).t().contiguous() if edges else torch.zeros((2, 0), dtype=torch.long)
+    return GraphData(x=None, edge_index=edge_index.view(2, -1), num_nodes=nx_g.number_of_nodes())
 
 
 def run_diffstg_evaluation_cache(model, timeseries_datas, pred_len, graph_data, cache_path, device,
                                  force_recompute=False, max_windows=None):
+    """:369-397: read the cache, or sample every window on the graph (all windows batched as graph replicas)."""
     cache_path = Path(cache_path)
     if cache_path.exists() and not force_recompute:
         return normalize_diffstg_pred_future_list(_load_tensor_list(cache_path))
-    raise NotImplementedError("DiffSTG is scheduled after the MLP-denoiser families (SURVEY 8a15)")
+    iterable = timeseries_datas[:max_windows] if max_windows is not None else timeseries_datas
+    stacked = torch.stack([torch.as_tensor(w) for w in iterable])
+    cache = sample_sweep(model, stacked, device=device, graph_data=graph_data)
+    pred_future_list = [el[:, -pred_len:, :, :] for el in _as_cache_list(cache)]
+    _save_tensor_list(pred_future_list, cache_path)
+    return pred_future_list
 
 
 # ------------------------------------------------------------------------------------------------
@@ -1099,21 +1129,22 @@ def gather_window_stats(local, n_windows, group=None):
     return torch.cat(out)[:n_windows]
 
 
-def distributed_sweep(model, stacked_windows, device=None, group=None):
+def distributed_sweep(model, stacked_windows, device=None, group=None, graph_data=None):
     """Sweep sharded over the ranks of ``group``: rank r samples its contiguous block of windows (Philox
     keys use the global window index, so the union equals the single-GPU sweep), reduces it on its GPU,
     and the ranks exchange only [W, 2+F] floats.  Returns (local_cache [w1-w0,B,K,O,F], (w0,w1), stats) with
-    stats = dict(mpv [W], pred_mean [W], mpv_f [W,F]) identical on every rank."""
+    stats = dict(mpv [W], pred_mean [W], mpv_f [W,F]) identical on every rank.  ``graph_data``: DiffSTG only (windows and
+    sample replicas shard; nodes are coupled by the graph conv and do not)."""
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     W = stacked_windows.shape[0]
     w0, w1 = partition_windows(W, world, rank)
     device = device or _model_device(model)
-    F = model.dataset_nf
+    F = model.F if graph_data is not None else model.dataset_nf
     start = getattr(model, "_windows_drawn", 0)
     if w1 > w0:
-        cache = sample_sweep(model, stacked_windows[w0:w1], device=device, window_offset=w0)
+        cache = sample_sweep(model, stacked_windows[w0:w1], device=device, window_offset=w0, graph_data=graph_data)
         st = cache.upd_stats.get("raw", cache.upd_stats["scaled"])
         local = torch.cat([st["mpv"].view(-1, 1), st["pred_mean"].view(-1, 1), st["mpv_f"].view(-1, F)], dim=1)
     else:
