@@ -49,16 +49,24 @@ int cuda_fail(cudaError_t e) {
   return UPD_ERR_CUDA;
 }
 
-// Device checks shared by every launch: sm_100 family, SM count for persistent grids.
+// Device checks shared by every launch: sm_100 family, SM count for persistent grids.  The two attributes are
+// immutable per device, so they are looked up once per (thread, device): cudaDeviceGetAttribute costs ~15 us,
+// more than the launch itself for the small per-step kernels.
 int device_info(int* sms) {
-  int dev = 0, major = 0;
+  thread_local int cached_dev = -1, cached_major = 0, cached_sms = 0;
+  int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return cuda_fail(e);
-  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-  if (e != cudaSuccess) return cuda_fail(e);
-  if (major != 10) return UPD_ERR_NO_DEVICE;
-  e = cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, dev);
-  if (e != cudaSuccess) return cuda_fail(e);
+  if (dev != cached_dev) {
+    int major = 0, n = 0;
+    e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return cuda_fail(e);
+    cached_dev = dev; cached_major = major; cached_sms = n;
+  }
+  if (cached_major != 10) return UPD_ERR_NO_DEVICE;
+  *sms = cached_sms;
   return UPD_OK;
 }
 
