@@ -235,6 +235,27 @@ int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev,
                    const float* gamma_dev, const float* beta_dev, long long N, int CI, int C, int T, float* hn_dev,
                    void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * f(x) condition encoder (ns-Transformer; models/Diffusion_model/NsDiff/mu_backbone.py:53-183,
+ * TMDM/tmdm_ns_transformer.py:40-174; blocks from torch-timeseries 0.1.10 -- parity unpinned).
+ * Every dense layer runs as one fp16 tensor-core GEMM (fp32 accumulate) on the error-compensated operand
+ *   A3(x) = [x_hi | x_lo | x_hi | 1 1 0 0 0 0 0 0]  (fp16, [rows, 3K+8]; hi = fp16(x), lo = fp16(x - hi))
+ * against [W_hi | W_hi | W_lo | b_hi b_lo 0..] ; the two calls below produce A3 fused with what precedes the GEMM.
+ * ------------------------------------------------------------------------------------------ */
+
+/* upd_fx_split -- A3(act(x)).  act: 0 none, 1 ReLU, 2 GELU (erf) = the feed-forward activation between conv1 and conv2
+ *   (EncoderLayer/DecoderLayer of torch-timeseries as called at mu_backbone.py:70-104).  H > 1: x_dev is an attention
+ *   output [B, H, L, K/H] and the row (b,l) gathers its heads (the `out.transpose(1,2).reshape(B, L, -1)` of
+ *   AttentionLayer) -- rows = B*L.  K multiple of 4 (K/H too), K <= 1024. */
+int upd_fx_split(const float* x_dev, long long rows, int K, int H, int L, int act, void* a3_dev, void* stream);
+
+/* upd_fx_add_ln_split -- y = LayerNorm_2(LayerNorm_1(x + res)) (eps 1e-5; res, the second norm, y_dev or a3_dev may be
+ *   NULL): the `norm(x + sublayer(x))` of every encoder/decoder layer, with the stack's final norm folded into the
+ *   last one; writes y [rows,K] fp32 and A3(y).  K multiple of 128, K <= 1024. */
+int upd_fx_add_ln_split(const float* x_dev, const float* res_dev, const float* g1_dev, const float* b1_dev,
+                        const float* g2_dev, const float* b2_dev, long long rows, int K, float* y_dev, void* a3_dev,
+                        void* stream);
+
 /* Known-answer self test of the tcgen05 descriptors this library relies on: D[128,N] = A[128,K] * B[N,K]^T
  * with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K=128; mode 1: tf32 hi/lo
  * 3-pass, K=8*k8); flags bit 0 swaps the descriptor's LBO/SBO (negative control: must give a wrong D).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */

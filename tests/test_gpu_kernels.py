@@ -316,3 +316,62 @@ def test_c_abi_rejects_bad_arguments():
         kernels.nsdiff_sample(packed, None, gx, 1, 1, 1, 1, 10, 5, 20)
     with pytest.raises(RuntimeError, match="bad argument"):
         kernels.nsdiff_sample(packed, None, gx, 1, 1, 6, 4, 10, 2, 20, noise=torch.zeros(4, device=dev))
+
+
+# ------------------------------------------------------------------------------------------ f(x) glue kernels
+def _a3_decode(a3, K):
+    """[hi | lo | hi | 1 1 0..] -> (hi + lo as fp32, tail)."""
+    a = a3.float()
+    assert torch.equal(a3[:, :K], a3[:, 2 * K:3 * K])
+    return a[:, :K] + a[:, K:2 * K], a[:, 3 * K:]
+
+
+@pytest.mark.parametrize("K,act", [(512, 0), (256, 2), (256, 1), (64, 0)])
+def test_fx_split_operand(K, act):
+    from updgm_b200 import fx_encoder
+    torch.manual_seed(K + act)
+    x = torch.randn(1000, K, device=_dev()) * 3
+    a3 = fx_encoder.a3_split(x, act=act)
+    ref = {0: x, 1: torch.relu(x), 2: torch.nn.functional.gelu(x)}[act]
+    val, tail = _a3_decode(a3, K)
+    assert float((val - ref).abs().max() / ref.abs().max()) < 2e-6          # 22 mantissa bits
+    assert torch.equal(tail, torch.tensor([1., 1., 0, 0, 0, 0, 0, 0], device=_dev()).expand(1000, 8))
+    # head merge: attention output [B,H,L,dk] -> rows (b,l), columns (h,j)
+    B, H, L, dk = 3, 8, 50, K // 8
+    o = torch.randn(B, H, L, dk, device=_dev())
+    val, _ = _a3_decode(fx_encoder.a3_split(o, heads=(B, H, L)), K)
+    assert float((val - o.transpose(1, 2).reshape(B * L, K)).abs().max()) < 2e-6 * float(o.abs().max())
+
+
+@pytest.mark.parametrize("K", [128, 512])
+def test_fx_add_layernorm_split(K):
+    from updgm_b200 import fx_encoder
+    torch.manual_seed(K)
+    dev = _dev()
+    x, r = torch.randn(777, K, device=dev), torch.randn(777, K, device=dev)
+    ln1, ln2 = torch.nn.LayerNorm(K).to(dev), torch.nn.LayerNorm(K).to(dev)
+    for ln in (ln1, ln2):
+        ln.weight.data.uniform_(0.5, 1.5)
+        ln.bias.data.uniform_(-0.5, 0.5)
+    with torch.no_grad():
+        y, a3 = fx_encoder.add_ln_split(x, r, ln1)
+        ref = ln1(x + r)
+        assert float((y - ref).abs().max()) < 5e-6
+        val, _ = _a3_decode(a3, K)
+        assert float((val - ref).abs().max()) < 5e-6
+        y2, a32 = fx_encoder.add_ln_split(x, None, ln1, ln2, want_y=False)
+        assert y2 is None
+        val, _ = _a3_decode(a32, K)
+        assert float((val - ln2(ln1(x))).abs().max()) < 1e-5
+
+
+def test_fx_compensated_gemm_accuracy():
+    """One fp16 GEMM on the split operand reproduces the fp32 linear layer to ~1e-6 (bias inside the GEMM)."""
+    from updgm_b200 import fx_encoder
+    torch.manual_seed(1)
+    lin = fx_encoder.SLinear(512, 264).to(_dev())
+    x = torch.randn(4096, 512, device=_dev())
+    with torch.no_grad():
+        y = fx_encoder.gemm3(fx_encoder.a3_split(x), lin.w3(), 264)
+        ref = (x.double() @ lin.weight.double().t() + lin.bias.double())
+    assert tuple(y.shape) == (4096, 264) and float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5

@@ -39,6 +39,10 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
 cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
                                   cudaStream_t stream);
+cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, int L, int act, void* a3, cudaStream_t stream);
+cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const float* g1, const float* b1,
+                                       const float* g2, const float* b2, long long rows, int K, float* y, void* a3,
+                                       cudaStream_t stream);
 
 namespace {
 
@@ -349,6 +353,22 @@ int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev,
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_tcn_ln(x_dev, w1_dev, b1_dev, w2_dev, b2_dev, gamma_dev, beta_dev, N, CI, C, T, hn_dev,
                                    (cudaStream_t)stream));
+}
+
+int upd_fx_split(const float* x_dev, long long rows, int K, int H, int L, int act, void* a3_dev, void* stream) {
+  if (!x_dev || !a3_dev || rows <= 0 || act < 0 || act > 2) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_fx_split(x_dev, rows, K, H, L, act, a3_dev, (cudaStream_t)stream));
+}
+
+int upd_fx_add_ln_split(const float* x_dev, const float* res_dev, const float* g1_dev, const float* b1_dev,
+                        const float* g2_dev, const float* b2_dev, long long rows, int K, float* y_dev, void* a3_dev,
+                        void* stream) {
+  if (!x_dev || !g1_dev || !b1_dev || rows <= 0 || (!y_dev && !a3_dev) || ((g2_dev == nullptr) != (b2_dev == nullptr)))
+    return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_fx_add_ln_split(x_dev, res_dev, g1_dev, b1_dev, g2_dev, b2_dev, rows, K, y_dev, a3_dev,
+                                        (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -11,15 +11,22 @@ dependency packages: de-stationary attention softmax(scale * (Q K^T * tau + delt
 encoder/decoder layers with 1x1-conv feed-forward, circular-conv token embedding + sinusoidal positions.
 Parameter names follow that lineage so such checkpoints would load by name.
 
-This encoder is off the roofline-critical path (once per window vs K*T denoiser evaluations per window):
-it runs as PyTorch library ops (cuBLAS GEMMs, fused SDPA) on the same stream, as SURVEY section 8(f)
-row 1 ("next") schedules its hand-written replacement after the sampler.
+Execution on the GPU (``NsTransformer._forward_fused``, d_model a multiple of 128): every dense layer is ONE fp16
+tensor-core GEMM with fp32 accumulation on an error-compensated operand, [x_hi | x_lo | x_hi | 1 1 0..] against
+[W_hi | W_hi | W_lo | b_hi b_lo 0..] (22 mantissa bits per factor, bias inside the GEMM; 3e-6 of max|y| measured, and
+2-3x faster than three TF32 passes), and the memory-bound glue between the GEMMs is two hand-written kernels behind the
+C ABI (csrc/fx_fused.cu): ``upd_fx_split`` (operand split fused with the activation or with the attention output's head
+merge) and ``upd_fx_add_ln_split`` (residual + LayerNorm (+ the stack's final norm) -> fp32 + split operand).
+The GEMMs themselves and the de-stationary attention are library calls (cuBLAS, fp32 memory-efficient SDPA).
+Other widths (TMDM's d_model = 64) and CPU tensors take the module-by-module path below (TF32x3 / plain fp32).
 """
 import math
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import _lib
 
 
 def _tf32_hi(x):
@@ -71,15 +78,80 @@ def split_linear(x, weight, bias, cache, pre=None):
     return y.view(*x.shape[:-1], weight.shape[0])
 
 
+class _W3Cache:
+    """[W_hi | W_hi | W_lo | b_hi b_lo 0..] fp16, [N (padded to 8), 3K+8], cached until a parameter changes."""
+
+    def __init__(self):
+        self.key, self.w3 = None, None
+
+    def get(self, parts):
+        """parts: list of (weight [N,K(,1)], bias [N] or None) stacked along N (fused projections)."""
+        key = tuple((w.data_ptr(), w._version, None if b is None else b._version) for w, b in parts) + (parts[0][0].device,)
+        if key != self.key:
+            rows = []
+            for w, b in parts:
+                w2 = w.detach().reshape(w.shape[0], -1).float()
+                n, k = w2.shape
+                hi = w2.half()
+                lo = (w2 - hi.float()).half()
+                blk = torch.zeros(n, 3 * k + 8, dtype=torch.float16, device=w2.device)
+                blk[:, :k], blk[:, k:2 * k], blk[:, 2 * k:3 * k] = hi, hi, lo
+                if b is not None:
+                    bh = b.detach().float().half()
+                    blk[:, 3 * k], blk[:, 3 * k + 1] = bh, (b.detach().float() - bh.float()).half()
+                rows.append(blk)
+            w3 = torch.cat(rows, 0)
+            if w3.shape[0] % 8:
+                w3 = torch.cat([w3, w3.new_zeros(8 - w3.shape[0] % 8, w3.shape[1])], 0)
+            self.w3, self.key = w3.contiguous(), key
+        return self.w3
+
+
+def a3_split(x2d, act=0, heads=None):
+    """A3(act(x)) [rows, 3K+8] fp16 (upd_fx_split).  heads=(B, H, L): x2d is an attention output [B,H,L,dk]."""
+    if heads is None:
+        rows, K, H, L = x2d.shape[0], x2d.shape[1], 1, 1
+    else:
+        B, H, L = heads
+        rows, K = B * L, x2d.shape[1] * x2d.shape[3]
+    a3 = torch.empty((rows, 3 * K + 8), dtype=torch.float16, device=x2d.device)
+    rc = _lib.lib().upd_fx_split(_lib.ptr(x2d), rows, K, H, L, act, _lib.ptr(a3), _lib.stream_ptr(x2d.device))
+    _lib.check(rc, "upd_fx_split")
+    return a3
+
+
+def add_ln_split(x2d, res2d, ln1, ln2=None, want_y=True, want_a3=True):
+    """(y, A3(y)) with y = ln2(ln1(x + res)) (upd_fx_add_ln_split)."""
+    rows, K = x2d.shape
+    y = torch.empty_like(x2d) if want_y else None
+    a3 = torch.empty((rows, 3 * K + 8), dtype=torch.float16, device=x2d.device) if want_a3 else None
+    rc = _lib.lib().upd_fx_add_ln_split(
+        _lib.ptr(x2d), _lib.ptr(res2d), _lib.ptr(ln1.weight.detach()), _lib.ptr(ln1.bias.detach()),
+        None if ln2 is None else _lib.ptr(ln2.weight.detach()), None if ln2 is None else _lib.ptr(ln2.bias.detach()),
+        rows, K, _lib.ptr(y), _lib.ptr(a3), _lib.stream_ptr(x2d.device))
+    _lib.check(rc, "upd_fx_add_ln_split")
+    return y, a3
+
+
+def gemm3(a3, w3, n_out):
+    """One fp16 tensor-core GEMM, fp32 accumulate and output: [rows, 3K+8] x [N, 3K+8]^T -> [rows, n_out]."""
+    y = torch.mm(a3, w3.t(), out_dtype=torch.float32)
+    return y if y.shape[1] == n_out else y[:, :n_out]
+
+
 class SLinear(nn.Linear):
     """nn.Linear (same parameters / state-dict keys) evaluated with split_linear."""
 
     def __init__(self, *a, **k):
         super().__init__(*a, **k)
         self._split = _SplitWeight()
+        self._w3 = _W3Cache()
 
     def forward(self, x, pre=None):
         return split_linear(x, self.weight, self.bias, self._split, pre)
+
+    def w3(self):
+        return self._w3.get([(self.weight, self.bias)])
 
 
 class PointwiseConv(nn.Conv1d):
@@ -88,9 +160,13 @@ class PointwiseConv(nn.Conv1d):
     def __init__(self, c_in, c_out):
         super().__init__(c_in, c_out, 1)
         self._split = _SplitWeight()
+        self._w3 = _W3Cache()
 
     def forward(self, x):
         return split_linear(x, self.weight, self.bias, self._split)
+
+    def w3(self):
+        return self._w3.get([(self.weight, self.bias)])
 
 
 class Projector(nn.Module):
@@ -192,6 +268,49 @@ class AttentionLayer(nn.Module):
         out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, scale=scale)
         return self.out_projection(out.transpose(1, 2).reshape(B, Lq, -1))
 
+    def fused(self, a3_q, a3_kv, B, Lq, S, tau, delta):
+        """Same attention on pre-split operands: a3_q [B*Lq, 3d+8], a3_kv [B*S, 3d+8] (None: self-attention).
+        Returns the out-projection [B*Lq, d] fp32."""
+        H = self.n_heads
+        d = self.query_projection.out_features
+        dk = d // H
+        if a3_kv is None:
+            if not hasattr(self, "_w3_qkv"):
+                self._w3_qkv = _W3Cache()
+            w3 = self._w3_qkv.get([(p.weight, p.bias) for p in (self.query_projection, self.key_projection,
+                                                                self.value_projection)])
+            qkv = gemm3(a3_q, w3, 3 * d).view(B, Lq, 3, H, dk)
+            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+        else:
+            if not hasattr(self, "_w3_kv"):
+                self._w3_kv = _W3Cache()
+            q = gemm3(a3_q, self.query_projection.w3(), d).view(B, Lq, H, dk).transpose(1, 2)
+            w3 = self._w3_kv.get([(p.weight, p.bias) for p in (self.key_projection, self.value_projection)])
+            kv = gemm3(a3_kv, w3, 2 * d).view(B, S, 2, H, dk)
+            k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
+        scale = 1.0 / math.sqrt(dk)
+        if tau is not None:
+            q = q * tau.view(B, 1, 1, 1)
+        causal_flag, mask = False, None
+        if delta is not None:
+            # [B,S] scaled delta in a buffer whose row pitch is a multiple of 16 floats: the broadcast view then meets the
+            # fused attention's alignment rule and is read as B*S floats instead of being materialised as [B,H,Lq,S]
+            mask = delta.view(B, 1, 1, S).expand(B, H, Lq, S)
+        if self.causal:
+            if mask is None and Lq == S:
+                causal_flag = True                      # plain lower-triangular mask: no mask tensor at all
+            else:
+                tri = torch.ones(Lq, S, dtype=torch.bool, device=q.device).triu(1)
+                cm = torch.zeros(Lq, S, dtype=q.dtype, device=q.device).masked_fill(tri, float("-inf"))
+                mask = cm if mask is None else mask + cm
+        out = F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal_flag, scale=scale)  # [B,H,Lq,dk]
+        merged = out.transpose(1, 2)
+        if merged.is_contiguous():
+            a3_o = a3_split(merged.reshape(B * Lq, d))
+        else:
+            a3_o = a3_split(out.contiguous(), heads=(B, H, Lq))
+        return gemm3(a3_o, self.out_projection.w3(), d)
+
 
 def _act(name):
     return F.relu if name == "relu" else F.gelu
@@ -205,11 +324,19 @@ class EncoderLayer(nn.Module):
         self.conv2 = PointwiseConv(d_ff, d_model)
         self.norm1, self.norm2 = nn.LayerNorm(d_model), nn.LayerNorm(d_model)
         self.activation = _act(activation)
+        self.act_code = 1 if activation == "relu" else 2
 
     def forward(self, x, tau, delta):
         x = self.norm1(x + self.attention(x, x, x, tau, delta))
         y = self.conv2(self.activation(self.conv1(x)))
         return self.norm2(x + y)
+
+    def fused(self, x, a3, B, L, tau, delta, final_norm=None):
+        """x [B*L, d] fp32 with its split operand a3 -> (layer output, its split operand)."""
+        x, a3 = add_ln_split(self.attention.fused(a3, None, B, L, L, tau, delta), x, self.norm1)
+        h = gemm3(a3, self.conv1.w3(), self.conv1.out_channels)
+        y = gemm3(a3_split(h, act=self.act_code), self.conv2.w3(), self.conv2.out_channels)
+        return add_ln_split(y, x, self.norm2, final_norm)
 
 
 class Encoder(nn.Module):
@@ -233,12 +360,20 @@ class DecoderLayer(nn.Module):
         self.conv2 = PointwiseConv(d_ff, d_model)
         self.norm1, self.norm2, self.norm3 = nn.LayerNorm(d_model), nn.LayerNorm(d_model), nn.LayerNorm(d_model)
         self.activation = _act(activation)
+        self.act_code = 1 if activation == "relu" else 2
 
     def forward(self, x, cross, tau, delta):
         x = self.norm1(x + self.self_attention(x, x, x, tau, None))
         x = self.norm2(x + self.cross_attention(x, cross, cross, tau, delta))
         y = self.conv2(self.activation(self.conv1(x)))
         return self.norm3(x + y)
+
+    def fused(self, x, a3, a3_cross, B, Lq, S, tau, delta, final_norm=None, want_y=True):
+        x, a3 = add_ln_split(self.self_attention.fused(a3, None, B, Lq, Lq, tau, None), x, self.norm1)
+        x, a3 = add_ln_split(self.cross_attention.fused(a3, a3_cross, B, Lq, S, tau, delta), x, self.norm2)
+        h = gemm3(a3, self.conv1.w3(), self.conv1.out_channels)
+        y = gemm3(a3_split(h, act=self.act_code), self.conv2.w3(), self.conv2.out_channels)
+        return add_ln_split(y, x, self.norm3, final_norm, want_y=want_y)
 
 
 class Decoder(nn.Module):
@@ -278,6 +413,40 @@ class NsTransformer(nn.Module):
             def mlp():
                 return nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, d))
             self.z_mean, self.z_logvar, self.z_out = mlp(), mlp(), mlp()
+        # limits of the fused kernels (csrc/fx_fused.cu): LayerNorm width a multiple of 128, 16-byte aligned heads
+        self.fused_ok = (d % 128 == 0 and d <= 1024 and configs.d_ff % 4 == 0 and configs.d_ff <= 1024
+                         and (d // configs.n_heads) % 4 == 0 and len(self.encoder.attn_layers) > 0
+                         and len(self.decoder.layers) > 0)
+
+    def _forward_fused(self, x_enc, x_dec_new, tau, delta):
+        """Normalised encoder / decoder inputs -> decoder output [B, label+pred, F] (before de-normalisation)."""
+        B, L, _ = x_enc.shape
+        Ld = x_dec_new.shape[1]
+        d = self.enc_embedding.value_embedding.tokenConv.out_channels
+        x = self.enc_embedding(x_enc).reshape(B * L, d).contiguous()
+        a3 = a3_split(x)
+        # scale * delta, stored with a 16-float-aligned row pitch (see AttentionLayer.fused)
+        S = delta.shape[1]
+        pitch = (S + 15) // 16 * 16
+        dbuf = torch.zeros((B, pitch), dtype=torch.float32, device=delta.device)
+        dbuf[:, :S] = delta * (1.0 / math.sqrt(d // self.encoder.attn_layers[0].attention.n_heads))
+        delta = dbuf[:, :S]
+        layers = self.encoder.attn_layers
+        for i, layer in enumerate(layers):
+            x, a3 = layer.fused(x, a3, B, L, tau, delta, self.encoder.norm if i == len(layers) - 1 else None)
+        if self.vae:
+            x = self.z_out(self.z_mean(x))                    # eval: z = posterior mean (:133-134)
+            a3 = a3_split(x.contiguous())
+        a3_enc = a3
+        xd = self.dec_embedding(x_dec_new).reshape(B * Ld, d).contiguous()
+        a3 = a3_split(xd)
+        layers = self.decoder.layers
+        for i, layer in enumerate(layers):
+            last = i == len(layers) - 1
+            xd, a3 = layer.fused(xd, a3, a3_enc, B, Ld, L, tau, delta, self.decoder.norm if last else None,
+                                 want_y=not last)
+        proj = self.decoder.projection
+        return gemm3(a3, proj.w3(), proj.out_features).reshape(B, Ld, proj.out_features)
 
     def forward(self, x_enc, x_dec, *unused):
         if self.vae and len(unused) >= 2:            # TMDM call signature (x_enc, x_mark_enc, x_dec, x_mark_dec)
@@ -290,6 +459,11 @@ class NsTransformer(nn.Module):
         x_dec_new = torch.cat([x_enc[:, -self.label_len:, :], torch.zeros_like(x_dec[:, -self.pred_len:, :])], dim=1)
         tau = self.tau_learner(x_raw, std_enc).exp()          # B x 1
         delta = self.delta_learner(x_raw, mean_enc)           # B x S
+        if x_enc.is_cuda and self.fused_ok and not torch.is_grad_enabled():
+            dec_out = self._forward_fused(x_enc, x_dec_new, tau, delta) * std_enc + mean_enc
+            if self.vae:
+                return dec_out[:, -self.pred_len:, :], dec_out, None, None
+            return dec_out[:, -self.pred_len:, :], dec_out
         enc_out = self.encoder(self.enc_embedding(x_enc), tau, delta)
         if self.vae:
             enc_out = self.z_out(self.z_mean(enc_out))        # eval: z = posterior mean (:133-134)
