@@ -256,6 +256,17 @@ int upd_fx_add_ln_split(const float* x_dev, const float* res_dev, const float* g
                         const float* g2_dev, const float* b2_dev, long long rows, int K, float* y_dev, void* a3_dev,
                         void* stream);
 
+/* upd_fx_attention -- replaces DSAttention + the head merge of AttentionLayer (torch-timeseries 0.1.10, called from
+ *   mu_backbone.py:70-104): out = softmax(scale * (tau_b * Q K^T + delta_b)) V on tcgen05 tensor cores (fp16 hi/lo
+ *   operands, fp32 accumulation), written directly as the split operand A3 [B*Lq, 3*H*64+8] of the out-projection GEMM.
+ *   q_dev: row (b*Lq + l) at q_dev + row*q_row_stride floats, head h at + h*64; k_dev / v_dev likewise with rows
+ *   (b*S + s) and kv_row_stride (so Q|K|V may live in one fused projection buffer).  tau_dev [B] or NULL;
+ *   delta_dev [B, delta_pitch] ALREADY multiplied by scale, or NULL; causal != 0 masks keys s > l (self-attention).
+ *   Limits: head_dim == 64, S <= 192. */
+int upd_fx_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                     long long kv_row_stride, const float* tau_dev, const float* delta_dev, int delta_pitch, int B, int H,
+                     int Lq, int S, int head_dim, int causal, float scale, void* a3_dev, void* stream);
+
 /* Known-answer self test of the tcgen05 descriptors this library relies on: D[128,N] = A[128,K] * B[N,K]^T
  * with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K=128; mode 1: tf32 hi/lo
  * 3-pass, K=8*k8); flags bit 0 swaps the descriptor's LBO/SBO (negative control: must give a wrong D).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */

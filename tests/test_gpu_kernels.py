@@ -375,3 +375,45 @@ def test_fx_compensated_gemm_accuracy():
         y = fx_encoder.gemm3(fx_encoder.a3_split(x), lin.w3(), 264)
         ref = (x.double() @ lin.weight.double().t() + lin.bias.double())
     assert tuple(y.shape) == (4096, 264) and float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("Lq,S,causal,use_delta", [(100, 100, False, True), (150, 150, True, False), (150, 100, False, True),
+                                                   (7, 33, False, False), (130, 192, False, True)])
+def test_fx_tcgen05_attention_against_fp64(Lq, S, causal, use_delta):
+    """upd_fx_attention == softmax(scale*(tau*QK^T + delta)) V in float64, read back from the split operand it emits."""
+    import ctypes
+    import math
+    from updgm_b200 import _lib
+    torch.manual_seed(Lq * 1000 + S)
+    dev = _dev()
+    B, H, dk = 3, 8, 64
+    d = H * dk
+    qkv = torch.randn(B * max(Lq, S), 3 * d, device=dev)          # fused-projection style buffer: strided heads
+    tau = torch.rand(B, device=dev) * 1.5 + 0.5
+    scale = 1.0 / math.sqrt(dk)
+    pitch = (S + 15) // 16 * 16
+    dbuf = torch.zeros(B, pitch, device=dev)
+    delta = torch.randn(B, S, device=dev)
+    dbuf[:, :S] = delta * scale
+    a3 = torch.full((B * Lq, 3 * d + 8), float("nan"), dtype=torch.float16, device=dev)
+    q_rows = qkv[: B * Lq]
+    kv_rows = qkv[: B * S]
+    rc = _lib.lib().upd_fx_attention(
+        _lib.ptr(qkv), 3 * d, ctypes.c_void_p(qkv.data_ptr() + 4 * d), ctypes.c_void_p(qkv.data_ptr() + 8 * d), 3 * d,
+        _lib.ptr(tau), ctypes.c_void_p(dbuf.data_ptr()) if use_delta else None, pitch, B, H, Lq, S, dk, int(causal),
+        scale, _lib.ptr(a3), _lib.stream_ptr(dev))
+    _lib.check(rc, "upd_fx_attention")
+    q = q_rows[:, :d].double().view(B, Lq, H, dk).transpose(1, 2)
+    k = kv_rows[:, d:2 * d].double().view(B, S, H, dk).transpose(1, 2)
+    v = kv_rows[:, 2 * d:].double().view(B, S, H, dk).transpose(1, 2)
+    sc = (q @ k.transpose(-1, -2)) * tau.double().view(B, 1, 1, 1)
+    if use_delta:
+        sc = sc + delta.double().view(B, 1, 1, S)
+    sc = sc * scale
+    if causal:
+        sc = sc.masked_fill(torch.ones(Lq, S, dtype=torch.bool, device=dev).triu(1), float("-inf"))
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * Lq, d)
+    val, tail = _a3_decode(a3, d)
+    assert torch.isfinite(val).all()
+    assert float((val.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+    assert torch.equal(tail, torch.tensor([1., 1., 0, 0, 0, 0, 0, 0], device=dev).expand(B * Lq, 8))

@@ -43,6 +43,9 @@ cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, in
 cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const float* g1, const float* b1,
                                        const float* g2, const float* b2, long long rows, int K, float* y, void* a3,
                                        cudaStream_t stream);
+cudaError_t upd_launch_fx_attention(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
+                                    const float* tau, const float* delta, int delta_pitch, int B, int H, int Lq, int S,
+                                    int causal, float scale, void* a3, cudaStream_t stream);
 
 namespace {
 
@@ -369,6 +372,17 @@ int upd_fx_add_ln_split(const float* x_dev, const float* res_dev, const float* g
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_fx_add_ln_split(x_dev, res_dev, g1_dev, b1_dev, g2_dev, b2_dev, rows, K, y_dev, a3_dev,
                                         (cudaStream_t)stream));
+}
+
+int upd_fx_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                     long long kv_row_stride, const float* tau_dev, const float* delta_dev, int delta_pitch, int B, int H,
+                     int Lq, int S, int head_dim, int causal, float scale, void* a3_dev, void* stream) {
+  if (!q_dev || !k_dev || !v_dev || !a3_dev || B <= 0 || H <= 0 || Lq <= 0 || S <= 0) return UPD_ERR_BAD_ARG;
+  if (delta_dev && delta_pitch < S) return UPD_ERR_BAD_ARG;
+  if (head_dim != 64 || S > 192 || (long long)B * H > 0x7fffffffLL) return UPD_ERR_UNSUPPORTED;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_fx_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, tau_dev, delta_dev, delta_pitch, B,
+                                     H, Lq, S, causal, scale, a3_dev, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -59,6 +59,31 @@ __device__ __forceinline__ float lg2_1p_ex2(float z) {
   return l;
 }
 
+// The same function with ONE MUFU op: lg2(1 + 2^z) = max(z,0) + lg2(1 + u), u = 2^-|z| in (0,1], and lg2(1+u) as a
+// degree-8 minimax polynomial on the FMA pipe (|error| 4e-8 exact, 1.8e-7 in fp32 Horner -- the size of lg2.approx's own
+// error on these arguments).  Inside a MUFU turn the epilogue is MUFU-bound (32768 MUFU ops per tile-phase = 2048 clk
+// at 16/clk/SM); evaluating UPD_POLY_LG2 of every 4 elements this way trades 1 MUFU op for 10 FMA-pipe instructions.
+// MEASURED (B200, bench shape, parity green in every variant): 0 of 4: 3.72 G row-steps/s, 1 of 4: 3.73, 2 of 4: 3.48,
+// 3 of 4: 3.29, 4 of 4: 3.14 -- inside a MUFU turn the issue slots are as full as the MUFU pipe, so the trade does not
+// pay.  Kept (default off) as the record of that experiment.
+#ifndef UPD_POLY_LG2
+#define UPD_POLY_LG2 0
+#endif
+__device__ __forceinline__ float lg2_1p_ex2_poly(float z) {
+  float u;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(-fabsf(z)));
+  float p = -9.0889083222e-03f;
+  p = fmaf(p, u, 5.1134437323e-02f);
+  p = fmaf(p, u, -1.3592693210e-01f);
+  p = fmaf(p, u, 2.4041023850e-01f);
+  p = fmaf(p, u, -3.4654855728e-01f);
+  p = fmaf(p, u, 4.7846421599e-01f);
+  p = fmaf(p, u, -7.2113221884e-01f);
+  p = fmaf(p, u, 1.4426876307e+00f);
+  p = fmaf(p, u, 4.2314418636e-08f);
+  return fmaxf(z, 0.0f) + p;
+}
+
 // softplus(x) for x in [0,1] without MUFU: x/2 + P(x^2), P = degree-4 near-minimax fit of log(2 cosh(sqrt(u)/2))
 // on u in [0,1] (|error| < 4e-9 before fp32 rounding, 1e-7 after).  The sigma head applies softplus to the
 // L2-normalised, non-negative hidden vector, whose components always lie in [0,1]; taking those 128 of the 514
@@ -91,7 +116,11 @@ __device__ __forceinline__ float epilogue_group(const uint32_t (&r)[16], uint32_
     float z2 = FIRST ? __uint_as_float(r[j + 2]) * e4.z : fmaf(__uint_as_float(r[j + 2]), inv, b4.z) * e4.z;
     float z3 = FIRST ? __uint_as_float(r[j + 3]) * e4.w : fmaf(__uint_as_float(r[j + 3]), inv, b4.w) * e4.w;
     if (CLAMP) { z0 = fminf(z0, 126.f); z1 = fminf(z1, 126.f); z2 = fminf(z2, 126.f); z3 = fminf(z3, 126.f); }
-    float h0 = lg2_1p_ex2(z0), h1 = lg2_1p_ex2(z1), h2 = lg2_1p_ex2(z2), h3 = lg2_1p_ex2(z3);
+    // UPD_POLY_LG2 of these four go through the one-MUFU form (0: none, 1: h3, 2: h1 and h3, 4: all)
+    float h0 = (UPD_POLY_LG2 >= 4) ? lg2_1p_ex2_poly(z0) : lg2_1p_ex2(z0);
+    float h1 = (UPD_POLY_LG2 >= 2) ? lg2_1p_ex2_poly(z1) : lg2_1p_ex2(z1);
+    float h2 = (UPD_POLY_LG2 >= 3) ? lg2_1p_ex2_poly(z2) : lg2_1p_ex2(z2);
+    float h3 = (UPD_POLY_LG2 >= 1) ? lg2_1p_ex2_poly(z3) : lg2_1p_ex2(z3);
     ss = fmaf(h0, h0, ss); ss = fmaf(h1, h1, ss); ss = fmaf(h2, h2, ss); ss = fmaf(h3, h3, ss);
     tc::split_f16x2(h0, h1, o[j / 2], o[8 + j / 2]);
     tc::split_f16x2(h2, h3, o[j / 2 + 1], o[8 + j / 2 + 1]);

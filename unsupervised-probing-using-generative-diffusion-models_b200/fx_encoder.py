@@ -20,6 +20,7 @@ merge) and ``upd_fx_add_ln_split`` (residual + LayerNorm (+ the stack's final no
 The GEMMs themselves and the de-stationary attention are library calls (cuBLAS, fp32 memory-efficient SDPA).
 Other widths (TMDM's d_model = 64) and CPU tensors take the module-by-module path below (TF32x3 / plain fp32).
 """
+import ctypes
 import math
 
 import torch
@@ -274,21 +275,40 @@ class AttentionLayer(nn.Module):
         H = self.n_heads
         d = self.query_projection.out_features
         dk = d // H
+        scale = 1.0 / math.sqrt(dk)
         if a3_kv is None:
             if not hasattr(self, "_w3_qkv"):
                 self._w3_qkv = _W3Cache()
             w3 = self._w3_qkv.get([(p.weight, p.bias) for p in (self.query_projection, self.key_projection,
                                                                 self.value_projection)])
-            qkv = gemm3(a3_q, w3, 3 * d).view(B, Lq, 3, H, dk)
-            q, k, v = (qkv[:, :, i].transpose(1, 2) for i in range(3))
+            qkv = gemm3(a3_q, w3, 3 * d)
+            q_buf, q_stride, kv_buf, k_off, v_off, kv_stride = qkv, 3 * d, qkv, d, 2 * d, 3 * d
         else:
             if not hasattr(self, "_w3_kv"):
                 self._w3_kv = _W3Cache()
-            q = gemm3(a3_q, self.query_projection.w3(), d).view(B, Lq, H, dk).transpose(1, 2)
+            q_buf = gemm3(a3_q, self.query_projection.w3(), d)
             w3 = self._w3_kv.get([(p.weight, p.bias) for p in (self.key_projection, self.value_projection)])
-            kv = gemm3(a3_kv, w3, 2 * d).view(B, S, 2, H, dk)
+            kv_buf = gemm3(a3_kv, w3, 2 * d)
+            q_stride, k_off, v_off, kv_stride = d, 0, d, 2 * d
+        if dk == 64 and S <= 192 and not (self.causal and (delta is not None or Lq != S)):
+            # tcgen05 attention (csrc/fx_attention.cu): tau, delta, causal mask, softmax, head merge and operand split
+            a3_o = torch.empty((B * Lq, 3 * d + 8), dtype=torch.float16, device=q_buf.device)
+            base = kv_buf.data_ptr()
+            rc = _lib.lib().upd_fx_attention(
+                _lib.ptr(q_buf), q_stride, ctypes.c_void_p(base + 4 * k_off), ctypes.c_void_p(base + 4 * v_off), kv_stride,
+                None if tau is None else _lib.ptr(tau.reshape(-1).contiguous()),
+                None if delta is None else ctypes.c_void_p(delta.data_ptr()), 0 if delta is None else delta.stride(0),
+                B, H, Lq, S, dk, 1 if self.causal else 0, scale, _lib.ptr(a3_o), _lib.stream_ptr(q_buf.device))
+            _lib.check(rc, "upd_fx_attention")
+            return gemm3(a3_o, self.out_projection.w3(), d)
+        # other head sizes / longer sequences: library attention on strided views of the projection buffers
+        q = q_buf.view(B, Lq, -1)[:, :, :d].reshape(B, Lq, H, dk).transpose(1, 2) if a3_kv is not None else \
+            q_buf.view(B, Lq, 3, H, dk)[:, :, 0].transpose(1, 2)
+        if a3_kv is None:
+            k, v = (q_buf.view(B, Lq, 3, H, dk)[:, :, i].transpose(1, 2) for i in (1, 2))
+        else:
+            kv = kv_buf.view(B, S, 2, H, dk)
             k, v = kv[:, :, 0].transpose(1, 2), kv[:, :, 1].transpose(1, 2)
-        scale = 1.0 / math.sqrt(dk)
         if tau is not None:
             q = q * tau.view(B, 1, 1, 1)
         causal_flag, mask = False, None
