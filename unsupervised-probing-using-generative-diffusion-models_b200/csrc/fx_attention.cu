@@ -47,16 +47,22 @@ __device__ __forceinline__ uint32_t idesc_f16(int n) {      // D fp32, A/B fp16 
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | (8u << 24);
 }
 
+template <bool CAUSAL>
 __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ AttnSync sync;
   const int tid = threadIdx.x, warp = tid >> 5;
   const int bh = blockIdx.x, b = bh / p.H, h = bh - b * p.H;
   const int S = p.S, SP = (S + 15) & ~15, NIT = SP >> 4;
-  unsigned char* k_hi = smem;                               // [SP x 64]  elem(s,c) at (c/8)*SP*16 + s*16 + (c%8)*2
-  unsigned char* k_lo = k_hi + SP * DK * 2;
-  unsigned char* v_hi = k_lo + SP * DK * 2;                 // V^T [64 x SP] elem(c,s) at (s/8)*64*16 + c*16 + (s%8)*2
+  // K [SP x 64]: elem(s,c) at (c/8)*KLBO + s*16 + (c%8)*2 with KLBO = SP*16 + 16: the extra 16 bytes between
+  // K-adjacent core-matrix columns spread the eight 16-byte rows a quarter-warp stores over all banks (8-way conflicts
+  // otherwise, 53 M per launch in the first ncu capture); the MMA sees it only as the descriptor's LBO.
+  const uint32_t KLBO = (uint32_t)SP * 16u + 16u;
+  unsigned char* k_hi = smem;
+  unsigned char* k_lo = k_hi + 8 * KLBO;
+  unsigned char* v_hi = k_lo + 8 * KLBO;                    // V^T [64 x SP] elem(c,s) at (s/8)*64*16 + c*16 + (s%8)*2
   unsigned char* v_lo = v_hi + SP * DK * 2;
+  float* sdelta = reinterpret_cast<float*>(v_lo + SP * DK * 2);   // [SP] delta*log2e, -inf for the padding keys
   if (tid == 0) { tc::mbar_init(tc::smem_u32(&sync.mma_bar), 1); tc::fence_mbar_init(); }
   if (warp == 0) tc::tmem_alloc<256>(tc::smem_u32(&sync.tmem_base));
 
@@ -65,6 +71,8 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
   // three HBM round trips here instead of one per iteration (the projections were just written: 2.5 GB, not in L2).
   //   K: task (s, 8 consecutive channels) -> one 16-byte core-matrix row each for hi and lo
   //   V: task (channel c, 8 consecutive keys) -> one 16-byte row of V^T; global reads coalesced over c
+  for (int s0 = tid; s0 < SP; s0 += 128)
+    sdelta[s0] = s0 < S ? (p.delta ? p.delta[(long long)b * p.delta_pitch + s0] * LOG2E : 0.0f) : -INFINITY;
   const float* kb = p.k + (long long)b * S * p.kv_stride + h * DK;
   const float* vb = p.v + (long long)b * S * p.kv_stride + h * DK;
   for (int bt = 0; bt < NIT; bt += 4) {
@@ -97,7 +105,7 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
         uint4 hi, lo;
         tc::split_f16x2(ka[u].x, ka[u].y, hi.x, lo.x); tc::split_f16x2(ka[u].z, ka[u].w, hi.y, lo.y);
         tc::split_f16x2(kc[u].x, kc[u].y, hi.z, lo.z); tc::split_f16x2(kc[u].z, kc[u].w, hi.w, lo.w);
-        const uint32_t off = (uint32_t)c8 * (uint32_t)SP * 16u + (uint32_t)s * 16u;
+        const uint32_t off = (uint32_t)c8 * KLBO + (uint32_t)s * 16u;
         *reinterpret_cast<uint4*>(k_hi + off) = hi;
         *reinterpret_cast<uint4*>(k_lo + off) = lo;
       }
@@ -122,7 +130,6 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
   const uint32_t s_cols = q_cols + 64u;                     // columns [64, 64+SP): scores, then P operand
   const uint32_t bar = tc::smem_u32(&sync.mma_bar);
   const float qs = (p.tau ? p.tau[b] : 1.0f) * p.scale * LOG2E;
-  const float* dl = p.delta ? p.delta + (long long)b * p.delta_pitch : nullptr;
   const int Kd = p.H * DK;
   uint32_t parity = 0;
 
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
     __syncthreads();
     if (tid == 0) {                                         // S = Q K^T
       tc::fence_after_sync();
-      const uint32_t lbo = (uint32_t)SP * 16u, id = idesc_f16(SP);
+      const uint32_t lbo = KLBO, id = idesc_f16(SP);
 #pragma unroll
       for (int j = 0; j < DK / 16; ++j) {
         const uint32_t a_hi = tmem_base + 16u * j, a_lo = a_hi + 8u;
@@ -168,50 +175,69 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
     parity ^= 1u;
     tc::fence_after_sync();
 
-    // ---- softmax over this thread's row.  Scores are base-2 exponents (Q was pre-scaled); delta joins here.
-    // TMEM loads run one 16-column group ahead of the arithmetic. ----
-    const int s_end = p.causal ? min(S, l + 1) : S;          // keys >= s_end are masked
+    // ---- softmax over this thread's row.  Scores are base-2 exponents (Q was pre-scaled); delta (and the -inf of
+    // the padding keys) comes from shared memory as a broadcast.  TMEM loads run one 16-column group ahead. ----
+    const int s_end = CAUSAL ? min(S, l + 1) : S;            // causal: keys >= s_end are masked
     float m = -INFINITY;
     {
-      uint32_t r[16], rn[16];
-      tc::tmem_ld16(s_cols, r);
-      for (int g = 0; g < NIT; ++g) {
+      uint32_t ra[16], rb[16];
+      tc::tmem_ld16(s_cols, ra);
+      for (int g = 0; g < NIT; g += 2) {
         tc::wait_ld();
-        if (g + 1 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 1), rn);
+        if (g + 1 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 1), rb);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int s = 16 * g + j;
-          float x = __uint_as_float(r[j]);
-          if (dl && s < S) x = fmaf(dl[s], LOG2E, x);
-          if (s < s_end) m = fmaxf(m, x);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 d4 = *reinterpret_cast<const float4*>(sdelta + 16 * g + j);
+          float x0 = __uint_as_float(ra[j]) + d4.x, x1 = __uint_as_float(ra[j + 1]) + d4.y;
+          float x2 = __uint_as_float(ra[j + 2]) + d4.z, x3 = __uint_as_float(ra[j + 3]) + d4.w;
+          if (CAUSAL) {
+            const int s = 16 * g + j;
+            x0 = s < s_end ? x0 : -INFINITY; x1 = s + 1 < s_end ? x1 : -INFINITY;
+            x2 = s + 2 < s_end ? x2 : -INFINITY; x3 = s + 3 < s_end ? x3 : -INFINITY;
+          }
+          m = fmaxf(fmaxf(m, fmaxf(x0, x1)), fmaxf(x2, x3));
         }
+        if (g + 1 < NIT) {
+          tc::wait_ld();
+          if (g + 2 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 2), ra);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = rn[j];
+          for (int j = 0; j < 16; j += 4) {
+            const float4 d4 = *reinterpret_cast<const float4*>(sdelta + 16 * (g + 1) + j);
+            float x0 = __uint_as_float(rb[j]) + d4.x, x1 = __uint_as_float(rb[j + 1]) + d4.y;
+            float x2 = __uint_as_float(rb[j + 2]) + d4.z, x3 = __uint_as_float(rb[j + 3]) + d4.w;
+            if (CAUSAL) {
+              const int s = 16 * (g + 1) + j;
+              x0 = s < s_end ? x0 : -INFINITY; x1 = s + 1 < s_end ? x1 : -INFINITY;
+              x2 = s + 2 < s_end ? x2 : -INFINITY; x3 = s + 3 < s_end ? x3 : -INFINITY;
+            }
+            m = fmaxf(fmaxf(m, fmaxf(x0, x1)), fmaxf(x2, x3));
+          }
+        }
       }
     }
     float sum = 0.0f;
     {
-      uint32_t r[16], rn[16], o[16];
-      tc::tmem_ld16(s_cols, r);
+      uint32_t ra[16], rb[16], o[16];
+      tc::tmem_ld16(s_cols, ra);
       for (int g = 0; g < NIT; ++g) {
+        uint32_t (&cur)[16] = (g & 1) ? rb : ra;
+        uint32_t (&nxt)[16] = (g & 1) ? ra : rb;
         tc::wait_ld();
-        if (g + 1 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 1), rn);
-        float pr[16];
+        if (g + 1 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 1), nxt);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int s = 16 * g + j;
-          float x = __uint_as_float(r[j]);
-          if (dl && s < S) x = fmaf(dl[s], LOG2E, x);
-          float e;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x - m));
-          pr[j] = (s < s_end) ? e : 0.0f;
-          sum += pr[j];
+        for (int j = 0; j < 16; j += 2) {
+          const float2 d2 = *reinterpret_cast<const float2*>(sdelta + 16 * g + j);
+          float e0, e1;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"((__uint_as_float(cur[j]) + d2.x) - m));
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"((__uint_as_float(cur[j + 1]) + d2.y) - m));
+          if (CAUSAL) {
+            const int s = 16 * g + j;
+            e0 = s < s_end ? e0 : 0.0f; e1 = s + 1 < s_end ? e1 : 0.0f;
+          }
+          sum += e0 + e1;
+          tc::split_f16x2(e0, e1, o[j / 2], o[8 + j / 2]);
         }
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) tc::split_f16x2(pr[j], pr[j + 1], o[j / 2], o[8 + j / 2]);
         tc::tmem_st16(s_cols + 16u * g, o);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) r[j] = rn[j];
       }
     }
     tc::wait_st();
@@ -281,9 +307,16 @@ cudaError_t upd_launch_fx_attention(const float* q, long long q_stride, const fl
   p.q = q; p.q_stride = q_stride; p.k = k; p.v = v; p.kv_stride = kv_stride; p.tau = tau; p.delta = delta;
   p.delta_pitch = delta_pitch; p.B = B; p.H = H; p.Lq = Lq; p.S = S; p.causal = causal; p.scale = scale;
   p.a3 = reinterpret_cast<__half*>(a3);
-  const size_t smem = (size_t)4 * SP * DK * 2;
-  cudaError_t e = cudaFuncSetAttribute(fx_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  fx_attention_kernel<<<(unsigned)(B * H), 128, smem, stream>>>(p);
+  const size_t smem = (size_t)2 * 8 * (SP * 16 + 16) + (size_t)2 * SP * DK * 2 + (size_t)SP * sizeof(float);
+  cudaError_t e;
+  if (causal) {
+    e = cudaFuncSetAttribute(fx_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fx_attention_kernel<true><<<(unsigned)(B * H), 128, smem, stream>>>(p);
+  } else {
+    e = cudaFuncSetAttribute(fx_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    fx_attention_kernel<false><<<(unsigned)(B * H), 128, smem, stream>>>(p);
+  }
   return cudaGetLastError();
 }
