@@ -16,7 +16,8 @@ import re
 import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-OWN = ("sampler_tc_kernel", "sampler_simt_kernel", "welford_over_samples", "window_means", "sigma_estimation_kernel")
+OWN = ("sampler_tc_kernel", "sampler_simt_kernel", "welford_over_samples", "window_means", "sigma_estimation_kernel",
+       "fx_attention_kernel", "fx_add_ln_split_kernel", "fx_split_kernel")
 
 # ---- launch list -> shares ----
 lines = [l for l in open("gpurun_out/launches.csv") if not l.startswith("==")]
@@ -25,7 +26,7 @@ tot = 0.0
 for row in csv.DictReader(lines):
     v = float(row["Metric Value"].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}[row["Metric Unit"]]
     m = re.search("(" + "|".join(OWN) + ")", row["Kernel Name"])
-    short = m.group(1) if m else re.sub(r"<.*", "", row["Kernel Name"]).replace("void ", "")[:70]
+    short = m.group(1) if m else re.sub(r"<.*", "", row["Kernel Name"].replace("<unnamed>::", "")).replace("void ", "")[:70]
     agg[short][0] += 1
     agg[short][1] += v
     tot += v
@@ -38,7 +39,7 @@ with open("profiles/%s_bench_launches_summary.txt" % tag, "w") as f:
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
         f.write("%12.2f %7.2f%% %7d  %s\n" % (t / 1e6, 100 * t / tot, n, k))
     mine = sum(t for k, (n, t) in agg.items() if k in OWN)
-    f.write("# own kernels: %.2f%% of GPU time; the rest is f(x) (ns-Transformer condition encoder) as PyTorch library kernels\n" % (100 * mine / tot))
+    f.write("# own kernels: %.2f%% of GPU time; the rest are the f(x) encoder's library GEMMs (cuBLAS fp16, nvjet_hss) and embedding elementwise ops\n" % (100 * mine / tot))
 
 # ---- sampler: ncu --set full ----
 rows = list(csv.reader(open("gpurun_out/sampler_raw.csv")))
