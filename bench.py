@@ -224,11 +224,11 @@ def run_own_arm(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from updgm_b200 import _lib
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
-    sampler_ms, launches = [], 0
+    sampler_ms = []
 
     def step_resident(i, timed):
-        nonlocal launches
         with torch.no_grad():
             y0, gx = model.condition(x_dev.view(W * B, L, F))
             a, b = ev(), ev()
@@ -238,12 +238,12 @@ def run_own_arm(args, rank, world, local_rank):
             red = kernels.mpv_reduce(traj, W, B)
         if timed:
             sampler_ms.append((a, b))
-            launches += 4                              # g(x) + sampler + welford + window_means
         return red
 
     for i in range(args.warmup):
         step_resident(i, False)
     barrier()
+    launches0 = _lib.kernel_launches()                 # own kernels only: every C-ABI launch is counted in _lib.check
     with ClockSampler(local_rank) as clocks:
         t0, t1 = ev(), ev()
         t0.record()
@@ -252,6 +252,8 @@ def run_own_arm(args, rank, world, local_rank):
         t1.record()
         barrier()
         resident_ms = t0.elapsed_time(t1)
+    launches = _lib.kernel_launches() - launches0      # per step: sampler, g(x), Welford + window means, and f(x)'s
+                                                       # attention / LayerNorm-split / split kernels per 4096-row chunk
     if world > 1:                                      # the one collective of a sweep (outside no stage of compute)
         local = torch.cat([red["mpv"].view(-1, 1), red["pred_mean"].view(-1, 1), red["mpv_f"]], dim=1)
         stats = U.gather_window_stats(local, W * world)
@@ -299,6 +301,26 @@ def run_own_arm(args, rank, world, local_rank):
                      "note": "algorithmic FLOPs = 2*33408 MAC per denoiser row-step (SURVEY 8a7); the MLP is MUFU-bound "
                              "(514 softplus per row-step), see DESIGN.md"},
     }
+    if world == 1:
+        # BASELINE's second metric: MPV sweep wall time = windows -> sample -> reduce -> per-window MPV list, cache file
+        # written (reference: diffusion_model_uncertainy.py:323-339 + :286-303).  One sweep, outside the timed region.
+        import shutil
+        import tempfile
+        tmp = tempfile.mkdtemp(prefix="upd_bench_")
+        try:
+            torch.cuda.synchronize(dev)
+            w0 = time.perf_counter()
+            wins, _ = U.build_sliding_windows(series, torch.arange(series.shape[1]).numpy(), L, 5)
+            preds = U.run_evaluation_cache(model, wins, O, os.path.join(tmp, "sweep.pt"), dev, force_recompute=True)
+            _, ews = U.summarize_pred_future_list(preds, model=model)
+            w1 = time.perf_counter()
+            U.flush_cache_writes()
+            w2 = time.perf_counter()
+            line["sweep_wall"] = {"mpv_list_ms": (w1 - w0) * 1e3, "cache_file_written_ms": (w2 - w0) * 1e3,
+                                  "windows": len(ews), "cache_bytes": os.path.getsize(os.path.join(tmp, "sweep.pt")),
+                                  "note": "cache written by the background writer; MPV list is available at mpv_list_ms"}
+        finally:
+            shutil.rmtree(tmp, ignore_errors=True)
     if world == 1 and not os.environ.get("UPD_BENCH_SKIP_CPU"):   # (set only when the run is wrapped in ncu)
         threads = os.cpu_count() or 1
         rows = 100

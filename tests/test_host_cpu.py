@@ -300,3 +300,35 @@ def test_gather_window_stats_gloo_world2(W):
         assert p.exitcode == 0
     want = [[float(i), float(i) * 10] for i in range(W)]
     assert res[0] == want and res[1] == want
+
+
+# ------------------------------------------------------------------------------------------ cache writer
+def test_background_cache_writer_roundtrip(tmp_path, monkeypatch):
+    """Cache files are written by a background thread, appear atomically, and every reader waits for them."""
+    data = [torch.arange(12.).view(3, 4), torch.ones(2, 2)]
+    p = tmp_path / "a" / "cache.pt"
+    U._save_tensor_list(data, p)
+    assert U._cache_ready(p)                                  # waits for the pending write
+    back = U._load_tensor_list(p)
+    assert torch.equal(back[0], data[0]) and torch.equal(back[1], data[1])
+    assert not [f for f in os.listdir(p.parent) if ".tmp" in f]
+    U._save_tensor_list([torch.zeros(1)], p)                  # overwrite, then read straight away
+    assert torch.equal(U._load_tensor_list(p)[0], torch.zeros(1))
+    U._save_tensor_list({"not": "a list"}, p)
+    with pytest.raises(TypeError, match="must contain a list"):
+        U._load_tensor_list(p)
+    monkeypatch.setenv("UPD_SYNC_CACHE_WRITES", "1")
+    q = tmp_path / "sync.pt"
+    U._save_tensor_list(data, q)
+    assert q.exists()
+    U.flush_cache_writes()
+    # a failing write surfaces at the next synchronisation point
+    monkeypatch.delenv("UPD_SYNC_CACHE_WRITES")
+    bad = tmp_path / "dir_in_the_way.pt"
+    U._save_tensor_list(data, bad)
+    U.flush_cache_writes()
+    os.remove(bad)
+    os.mkdir(bad)
+    U._save_tensor_list(data, bad)
+    with pytest.raises(OSError):
+        U.flush_cache_writes()

@@ -92,7 +92,19 @@ def lib():
     return L
 
 
+# C-ABI calls made so far, by entry point (bench.py reports its own kernel launches from this; every launcher in the
+# package funnels its return code through check()).
+CALLS = {}
+KERNELS_PER_CALL = {"upd_mpv_reduce": 2, "upd_denoiser_pack": 0}
+
+
+def kernel_launches():
+    """Number of this library's kernels launched so far (upd_mpv_reduce = Welford + window means)."""
+    return sum(n * KERNELS_PER_CALL.get(k, 1) for k, n in CALLS.items())
+
+
 def check(code, what):
+    CALLS[what] = CALLS.get(what, 0) + 1
     if code != 0:
         L = lib()
         msg = L.upd_error_string(code).decode()

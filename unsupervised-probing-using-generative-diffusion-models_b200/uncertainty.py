@@ -8,7 +8,10 @@ dictionaries (evaluation_and_analysis/diffusion_model_uncertainy.py), re-organis
 
 Line references in docstrings are to the reference file above unless another file is named.
 """
+import atexit
+import concurrent.futures
 import os
+import threading
 from pathlib import Path
 
 import numpy as np
@@ -268,16 +271,63 @@ def resolve_figure_path(cache_file_path):
     return Path(cache_file_path).with_suffix(".png")
 
 
+# Cache files are written by one background thread (at B200 rates the 0.15-0.7 GB ``torch.save`` of a
+# sweep costs as much as sampling it).  A file appears atomically (temp file + rename) and every reader in this module
+# waits for a pending write of the path it is about to open; ``flush_cache_writes()`` (also run at interpreter exit)
+# waits for all of them and re-raises a failed write.  UPD_SYNC_CACHE_WRITES=1 restores the reference's blocking write.
+_WRITER = None
+_PENDING = {}
+_PENDING_LOCK = threading.Lock()
+
+
+def _write_tensor_list(data_list, cache_path):
+    tmp = cache_path.with_name(cache_path.name + ".tmp{}".format(os.getpid()))
+    with open(tmp, "wb") as f:
+        torch.save(data_list, f)
+    os.replace(tmp, cache_path)
+
+
 def _save_tensor_list(data_list, cache_path):
     """:252-256: the cache is ``torch.save(list[Tensor])``."""
+    global _WRITER
     cache_path = Path(cache_path)
     cache_path.parent.mkdir(parents=True, exist_ok=True)
-    with open(cache_path, "wb") as f:
-        torch.save(data_list, f)
+    _await_write(cache_path)
+    if os.environ.get("UPD_SYNC_CACHE_WRITES"):
+        _write_tensor_list(data_list, cache_path)
+        return
+    with _PENDING_LOCK:
+        if _WRITER is None:
+            _WRITER = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="upd-cache-writer")
+            atexit.register(flush_cache_writes)
+        _PENDING[str(cache_path.resolve())] = _WRITER.submit(_write_tensor_list, data_list, cache_path)
+
+
+def _await_write(cache_path):
+    with _PENDING_LOCK:
+        fut = _PENDING.pop(str(Path(cache_path).resolve()), None)
+    if fut is not None:
+        fut.result()
+
+
+def flush_cache_writes():
+    """Wait for every cache file queued by this process; raises the first write error."""
+    with _PENDING_LOCK:
+        futs = list(_PENDING.values())
+        _PENDING.clear()
+    for fut in futs:
+        fut.result()
+
+
+def _cache_ready(cache_path):
+    """``Path.exists()`` that first waits for a pending background write of that file."""
+    _await_write(cache_path)
+    return Path(cache_path).exists()
 
 
 def _load_tensor_list(cache_path):
     """:259-264."""
+    _await_write(cache_path)
     with open(cache_path, "rb") as f:
         data_list = torch.load(f, map_location="cpu", weights_only=False)
     if not isinstance(data_list, list):
@@ -478,7 +528,7 @@ def run_evaluation_cache(model, timeseries_datas, pred_len, cache_path, device, 
                          max_windows=None):
     """:323-339: read the cache, or sample every window (batched on the GPU) and write it."""
     cache_path = Path(cache_path)
-    if cache_path.exists() and not force_recompute:
+    if _cache_ready(cache_path) and not force_recompute:
         return _load_tensor_list(cache_path)
     iterable = timeseries_datas[:max_windows] if max_windows is not None else timeseries_datas
     stacked = torch.stack([torch.as_tensor(w) for w in iterable])
@@ -491,7 +541,7 @@ def run_evaluation_cache(model, timeseries_datas, pred_len, cache_path, device, 
 def run_slbp_sensitivity_cache(model, input_datas, cache_path, device, force_recompute=False, max_windows=None):
     """:502-526: SLBP windows [L,F] -> list of [O,F,K]; a corrupt cache is recomputed (:494-499)."""
     cache_path = Path(cache_path)
-    if cache_path.exists() and not force_recompute:
+    if _cache_ready(cache_path) and not force_recompute:
         cached = read_sensitivity_pred_future_cache(cache_path)
         if cached is not None:
             return cached
@@ -524,7 +574,7 @@ def run_nsdiff_g_cache(model, timeseries_datas, cache_path, device, pred_dim=0, 
                        max_windows=None):
     """:400-422 -> list of [Node,O,F] (None when the model has no g(x))."""
     cache_path = Path(cache_path)
-    if cache_path.exists() and not force_recompute:
+    if _cache_ready(cache_path) and not force_recompute:
         return _load_tensor_list(cache_path)
     if not hasattr(model, "cond_pred_model_g") or model.cond_pred_model_g is None:
         return None
@@ -541,7 +591,7 @@ def run_slbp_gx_cache_for_fig6(model, input_datas, cache_path, device, pred_dim=
                                max_windows=None):
     """:731-765 -> list of [O,F]."""
     cache_path = Path(cache_path)
-    if cache_path.exists() and not force_recompute:
+    if _cache_ready(cache_path) and not force_recompute:
         gx_list = _load_tensor_list(cache_path)
         if _slbp_cache_elements_are_gx(gx_list):
             return gx_list
@@ -578,7 +628,7 @@ def run_diffstg_evaluation_cache(model, timeseries_datas, pred_len, graph_data, 
                                  force_recompute=False, max_windows=None):
     """:369-397: read the cache, or sample every window on the graph (all windows batched as graph replicas)."""
     cache_path = Path(cache_path)
-    if cache_path.exists() and not force_recompute:
+    if _cache_ready(cache_path) and not force_recompute:
         return normalize_diffstg_pred_future_list(_load_tensor_list(cache_path))
     iterable = timeseries_datas[:max_windows] if max_windows is not None else timeseries_datas
     stacked = torch.stack([torch.as_tensor(w) for w in iterable])
@@ -812,20 +862,20 @@ def slbp_sampling_analysis(model_root, model_name, torch_time_series, time_data,
     try:
         active, pred_future_list = cache_path, None
         if not force_recompute:
-            if cache_path.exists():
+            if _cache_ready(cache_path):
                 cand = _load_tensor_list(cache_path)
                 if _slbp_cache_elements_have_ndim(cand, 3):
                     pred_future_list = cand
                 else:
                     active = sampling_cache_path
-            if pred_future_list is None and sampling_cache_path.exists():
+            if pred_future_list is None and _cache_ready(sampling_cache_path):
                 cand = _load_tensor_list(sampling_cache_path)
                 if not _slbp_cache_elements_have_ndim(cand, 3):
                     raise ValueError("sampling cache exists but is not [pred_len, F, n_z_samples]: {}".format(
                         sampling_cache_path))
                 pred_future_list, active = cand, sampling_cache_path
         if pred_future_list is None:
-            if cache_path.exists() and active == cache_path:
+            if _cache_ready(cache_path) and active == cache_path:
                 active = sampling_cache_path
             device = _default_device(device)
             model, _, _ = load_sensitivity_model(model_root, model_name, device=device, infer_params=infer_params)
@@ -839,7 +889,7 @@ def slbp_sampling_analysis(model_root, model_name, torch_time_series, time_data,
         if not allow_unavailable:
             raise
         return dict(base, available=False, time_points=time_points, mpv=[], intrinsic_dimension=[],
-                    pred_future_list=None, cache_path=str(sampling_cache_path if cache_path.exists() else cache_path),
+                    pred_future_list=None, cache_path=str(sampling_cache_path if _cache_ready(cache_path) else cache_path),
                     reason=str(exc))
 
 
@@ -864,16 +914,16 @@ def slbp_gx_analysis(model_root, model_name, torch_time_series, time_data, data_
 
     gx_list = None
     if not force_recompute:
-        if gx_cache_path.exists():
+        if _cache_ready(gx_cache_path):
             gx_list = _load_tensor_list(gx_cache_path)
-        elif old_gx.exists():
+        elif _cache_ready(old_gx):
             gx_list = _load_tensor_list(old_gx)
             if not _slbp_cache_elements_are_gx(gx_list):
                 raise ValueError("gx cache exists but is not a gx cache: {}".format(old_gx))
             gx_cache_path = old_gx
         else:
             for cand_path in (legacy, legacy_name):
-                if cand_path.exists():
+                if _cache_ready(cand_path):
                     cand = _load_tensor_list(cand_path)
                     if _slbp_cache_elements_are_gx(cand):
                         gx_list, gx_cache_path = cand, cand_path
@@ -897,7 +947,7 @@ def slbp_mpv_analysis(model_root, model_name, torch_time_series, time_data, cach
     sampled_time = torch_data_preprocessing_like_slbp(time_data, sampling_t=cfg["sampling_t"], return_numpy=True)
     base = {"cache_path": str(cache_path), "windows": cfg["windows"], "pred_len": cfg["pred_len"],
             "sampling_t": cfg["sampling_t"]}
-    if cache_path.exists() and not force_recompute:
+    if _cache_ready(cache_path) and not force_recompute:
         data_list = _load_tensor_list(cache_path)
         step = infer_sample_window_step_from_cache(len(sampled_time), cfg["windows"], len(data_list), sample_window_step)
         mpv, source = summarize_slbp_mpv_cache_for_fig5(data_list, pred_dim=pred_dim)
@@ -927,7 +977,7 @@ def slbp_direct_model_cache_analysis(model_save_file, torch_time_series, time_da
     cache_path = _resolve_project_path(cache_path)
     sampled_time = torch_data_preprocessing_like_slbp(time_data, sampling_t=sampling_t, return_numpy=True)
     model = None
-    if cache_path.exists() and not force_recompute:
+    if _cache_ready(cache_path) and not force_recompute:
         data_list = _load_tensor_list(cache_path)
     else:
         if cache_kind not in {"gx", "sampling"}:
@@ -1025,11 +1075,11 @@ def uncertainty_ews(model_save_file=None, data_file=None, torch_time_series=None
                                          model_save_file, data_file, dynamic_type, suffix="_gx")
 
     cached_pred, cached_g = None, None
-    if need_sampling and cache_path.exists() and not force_recompute:
+    if need_sampling and _cache_ready(cache_path) and not force_recompute:
         cached_pred = _load_tensor_list(cache_path)
         if task_model == "DiffSTG":
             cached_pred = normalize_diffstg_pred_future_list(cached_pred)
-    if need_gx and nsdiff_path is not None and nsdiff_path.exists() and not force_recompute:
+    if need_gx and nsdiff_path is not None and _cache_ready(nsdiff_path) and not force_recompute:
         cached_g = _load_tensor_list(nsdiff_path)
 
     if sampling_t is None:
