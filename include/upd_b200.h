@@ -206,6 +206,21 @@ int upd_dts_fourier_topk(const float* spec_dev, long long spec_row_stride, long 
 int upd_dts_fourier_topk_bwd(const float* gseason_dev, const int* idx_dev, long long gspec_row_stride, long long rows,
                              int NF, int low, int seq, int D, int top_k, float* gspec_dev, void* stream);
 
+/* upd_dts_attention / _bwd -- replaces FullAttention / CrossAttention (diffusionts_transformer.py:126-203; head size 16)
+ *   and their autograd backward (the refinement gradient of langevin_fn, DiffusionTS.py:384-399):
+ *   o = softmax(scale * q k^T) v per (row r, head h), heads merged in o_dev [R*Lq, H*16].  q_dev: position (r*Lq + i) at
+ *   q_dev + (r*Lq+i)*q_row_stride floats, head h at + h*16; k_dev / v_dev likewise over (r*S + j) with kv_row_stride, so
+ *   Q|K|V may be one fused projection buffer.  lse_dev [R*H, Lq] (may be NULL in the forward) keeps the base-2
+ *   log-sum-exp the backward needs; _bwd writes dq / dk / dv with the same addressing (dq_row_stride, dkv_row_stride).
+ *   Limits: head_dim == 16; (S + Lq) * 136 bytes of shared memory. */
+int upd_dts_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                      long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale, float* o_dev,
+                      float* lse_dev, void* stream);
+int upd_dts_attention_bwd(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                          long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale,
+                          const float* o_dev, const float* lse_dev, const float* do_dev, float* dq_dev,
+                          long long dq_row_stride, float* dk_dev, float* dv_dev, long long dkv_row_stride, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * DiffSTG graph-conv sampler.
  * ------------------------------------------------------------------------------------------ */

@@ -135,3 +135,32 @@ def test_full_loop_runs_and_is_distributionally_sane():
     assert tuple(outs.shape) == (2, cfg["pred_len"], 1, 4) and torch.isfinite(outs).all()
     assert float(outs.abs().max()) <= 1.0 + 1e-6
     assert float(outs.var(dim=-1).mean()) > 0
+
+
+@pytest.mark.parametrize("Lq,S,cross", [(200, 200, False), (48, 48, False), (200, 120, True), (33, 70, True)])
+def test_fused_attention_forward_backward_against_autograd(Lq, S, cross):
+    """upd_dts_attention(_bwd) vs materialised-score attention differentiated by torch autograd (float64)."""
+    import math
+    from updgm_b200.diffusionts import FusedAttention
+    torch.manual_seed(Lq + S)
+    R, H, hs = 5, 4, 16
+    d = H * hs
+    if cross:
+        qb = torch.randn(R, Lq, d, device=DEV, requires_grad=True)
+        kvb = torch.randn(R, S, 2 * d, device=DEV, requires_grad=True)
+        out = FusedAttention.apply(qb, kvb, 0, 0, d, H, d)
+        q64, k64, v64 = qb.double(), kvb.double()[..., :d], kvb.double()[..., d:]
+    else:
+        qb = torch.randn(R, Lq, 3 * d, device=DEV, requires_grad=True)
+        kvb = qb
+        out = FusedAttention.apply(qb, qb, 0, d, 2 * d, H, d)
+        q64, k64, v64 = qb.double()[..., :d], qb.double()[..., d:2 * d], qb.double()[..., 2 * d:]
+    heads = lambda t: t.reshape(R, -1, H, hs).transpose(1, 2)
+    att = torch.softmax(heads(q64) @ heads(k64).transpose(-1, -2) / math.sqrt(hs), -1)
+    ref = (att @ heads(v64)).transpose(1, 2).reshape(R, Lq, d)
+    assert _rel(out.detach(), ref.detach()) < 2e-5
+    w = torch.randn(R, Lq, d, device=DEV)
+    grads = torch.autograd.grad((out * w).sum(), [qb] if not cross else [qb, kvb])
+    refs = torch.autograd.grad((ref * w.double()).sum(), [qb] if not cross else [qb, kvb])
+    for g, r in zip(grads, refs):
+        assert _rel(g, r) < 2e-5, _rel(g, r)

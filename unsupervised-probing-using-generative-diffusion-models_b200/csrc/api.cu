@@ -46,6 +46,12 @@ cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const f
 cudaError_t upd_launch_fx_attention(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
                                     const float* tau, const float* delta, int delta_pitch, int B, int H, int Lq, int S,
                                     int causal, float scale, void* a3, cudaStream_t stream);
+cudaError_t upd_launch_dts_attention(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
+                                     int R, int H, int Lq, int S, float scale, float* o, float* lse, cudaStream_t stream);
+cudaError_t upd_launch_dts_attention_bwd(const float* q, long long q_stride, const float* k, const float* v,
+                                         long long kv_stride, int R, int H, int Lq, int S, float scale, const float* o,
+                                         const float* lse, const float* d_o, float* dq, long long dq_stride, float* dk,
+                                         float* dv, long long dkv_stride, cudaStream_t stream);
 
 namespace {
 
@@ -383,6 +389,30 @@ int upd_fx_attention(const float* q_dev, long long q_row_stride, const float* k_
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_fx_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, tau_dev, delta_dev, delta_pitch, B,
                                      H, Lq, S, causal, scale, a3_dev, (cudaStream_t)stream));
+}
+
+int upd_dts_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                      long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale, float* o_dev,
+                      float* lse_dev, void* stream) {
+  if (!q_dev || !k_dev || !v_dev || !o_dev || R <= 0 || H <= 0 || Lq <= 0 || S <= 0) return UPD_ERR_BAD_ARG;
+  if (head_dim != 16 || (long long)R * H > 0x7fffffffLL) return UPD_ERR_UNSUPPORTED;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev, lse_dev,
+                                      (cudaStream_t)stream));
+}
+
+int upd_dts_attention_bwd(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                          long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale,
+                          const float* o_dev, const float* lse_dev, const float* do_dev, float* dq_dev,
+                          long long dq_row_stride, float* dk_dev, float* dv_dev, long long dkv_row_stride, void* stream) {
+  if (!q_dev || !k_dev || !v_dev || !o_dev || !lse_dev || !do_dev || !dq_dev || !dk_dev || !dv_dev || R <= 0 || H <= 0 ||
+      Lq <= 0 || S <= 0)
+    return UPD_ERR_BAD_ARG;
+  if (head_dim != 16 || (long long)R * H > 0x7fffffffLL) return UPD_ERR_UNSUPPORTED;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_attention_bwd(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev,
+                                          lse_dev, do_dev, dq_dev, dq_row_stride, dk_dev, dv_dev, dkv_row_stride,
+                                          (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -15,6 +15,7 @@ checkpoints load with ``strict=True``.  The modules are parameter containers; th
 
 There is no CPU path.
 """
+import ctypes
 import math
 from types import SimpleNamespace
 
@@ -168,6 +169,51 @@ class FourierTopK(torch.autograd.Function):
         return gy, None, None, None, None
 
 
+class FusedAttention(torch.autograd.Function):
+    """softmax(q k^T / sqrt(hs)) v on projection buffers (upd_dts_attention / _bwd).  ``qbuf`` [R, Lq, *] holds q at
+    column offset ``q_off``; ``kvbuf`` [R, S, *] holds k at ``k_off`` and v at ``v_off`` (the same tensor as qbuf for
+    self-attention).  Returns [R, Lq, d] with the heads merged."""
+
+    @staticmethod
+    def forward(ctx, qbuf, kvbuf, q_off, k_off, v_off, n_heads, d):
+        qbuf, kvbuf = qbuf.contiguous(), kvbuf.contiguous()
+        R, Lq, S = qbuf.shape[0], qbuf.shape[1], kvbuf.shape[1]
+        hs = d // n_heads
+        dev = qbuf.device
+        out = torch.empty((R, Lq, d), dtype=torch.float32, device=dev)
+        need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        lse = torch.empty((R * n_heads, Lq), dtype=torch.float32, device=dev) if need else None
+        scale = 1.0 / math.sqrt(hs)
+        kb = kvbuf.data_ptr()
+        rc = _lib.lib().upd_dts_attention(
+            ctypes.c_void_p(qbuf.data_ptr() + 4 * q_off), qbuf.shape[2], ctypes.c_void_p(kb + 4 * k_off),
+            ctypes.c_void_p(kb + 4 * v_off), kvbuf.shape[2], R, n_heads, Lq, S, hs, scale, _lib.ptr(out), _lib.ptr(lse),
+            _lib.stream_ptr(dev))
+        _lib.check(rc, "upd_dts_attention")
+        if need:
+            ctx.save_for_backward(qbuf, kvbuf, out, lse)
+            ctx.meta = (q_off, k_off, v_off, n_heads, d, scale, qbuf.data_ptr() == kvbuf.data_ptr())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qbuf, kvbuf, out, lse = ctx.saved_tensors
+        q_off, k_off, v_off, n_heads, d, scale, same = ctx.meta
+        g = g.contiguous()
+        R, Lq, S = qbuf.shape[0], qbuf.shape[1], kvbuf.shape[1]
+        dev = g.device
+        dqbuf = torch.empty_like(qbuf)          # (q | k | v) resp. q and (k | v): every column is written
+        dkvbuf = dqbuf if same else torch.empty_like(kvbuf)
+        kb, dkb = kvbuf.data_ptr(), dkvbuf.data_ptr()
+        rc = _lib.lib().upd_dts_attention_bwd(
+            ctypes.c_void_p(qbuf.data_ptr() + 4 * q_off), qbuf.shape[2], ctypes.c_void_p(kb + 4 * k_off),
+            ctypes.c_void_p(kb + 4 * v_off), kvbuf.shape[2], R, n_heads, Lq, S, d // n_heads, scale, _lib.ptr(out),
+            _lib.ptr(lse), _lib.ptr(g), ctypes.c_void_p(dqbuf.data_ptr() + 4 * q_off), dqbuf.shape[2],
+            ctypes.c_void_p(dkb + 4 * k_off), ctypes.c_void_p(dkb + 4 * v_off), dkvbuf.shape[2], _lib.stream_ptr(dev))
+        _lib.check(rc, "upd_dts_attention_bwd")
+        return dqbuf, (None if same else dkvbuf), None, None, None, None, None
+
+
 def _sinusoidal(t, dim):
     half = dim // 2
     e = math.log(10000) / (half - 1)
@@ -274,20 +320,27 @@ class PreparedTransformer:
         return x.view(R, c, self.nh, self.d // self.nh).transpose(1, 2)
 
     def _attend(self, q, k, v):
-        """softmax(q k^T / sqrt(hs)) v with materialised scores: head size is 16 and the sequence 200, where the
-        library's fused fp32 attention (fwd 2.3 ms, bwd 7.3 ms per call at 2000 rows) loses to three batched GEMMs."""
+        """Materialised-score attention (library ops): only for head sizes the fused kernel is not built for."""
         q, k, v = self._heads(q), self._heads(k), self._heads(v)
         att = torch.softmax((q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(q.shape[-1])), dim=-1)
         return (att @ v).transpose(1, 2).reshape(q.shape[0], q.shape[2], self.d)
 
     def _self_attn(self, a, w):
-        q, k, v = F.linear(a, w["wqkv"], w["bqkv"]).split(self.d, dim=-1)
-        return F.linear(self._attend(q, k, v), w["wo"], w["bo"])
+        qkv = F.linear(a, w["wqkv"], w["bqkv"])                                   # [R, c, 3d] = (q | k | v)
+        if self.d // self.nh == 16:
+            y = FusedAttention.apply(qkv, qkv, 0, self.d, 2 * self.d, self.nh, self.d)
+        else:
+            y = self._attend(*qkv.split(self.d, dim=-1))
+        return F.linear(y, w["wo"], w["bo"])
 
     def _cross_attn(self, a, enc, w):
         q = F.linear(a, w["wq"], w["bq"])
-        k, v = F.linear(enc, w["wkv"], w["bkv"]).split(self.d, dim=-1)
-        return F.linear(self._attend(q, k, v), w["wo"], w["bo"])
+        kv = F.linear(enc, w["wkv"], w["bkv"])                                    # [R, c_enc, 2d] = (k | v)
+        if self.d // self.nh == 16:
+            y = FusedAttention.apply(q, kv, 0, 0, self.d, self.nh, self.d)
+        else:
+            y = self._attend(q, *kv.split(self.d, dim=-1))
+        return F.linear(y, w["wo"], w["bo"])
 
     def _mlp(self, x, w):
         h = F.layer_norm(x, (self.d,), w["ln2_w"], w["ln2_b"])
