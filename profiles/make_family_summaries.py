@@ -19,7 +19,7 @@ import sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 OWN = ("stg_tcn_ln_kernel", "stg_gated_aggregate_kernel", "stg_posterior_kernel", "gauss_fill_kernel",
        "dts_fourier_topk_fwd_kernel", "dts_fourier_topk_bwd_kernel", "dts_ddim_step_kernel", "dts_adagrad_kernel",
-       "dts_infill_kernel")
+       "dts_infill_kernel", "dts_attn_fwd_kernel", "dts_attn_bwd_kernel")
 lines = [l for l in open("gpurun_out/%s_families_launches.csv" % tag) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 # split the launch list at the first DiffusionTS-only kernel: everything before belongs to DiffSTG
@@ -35,7 +35,7 @@ with open("profiles/%s_families_launches_summary.txt" % tag, "w") as f:
         for r in rs:
             v = float(r["Metric Value"].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}[r["Metric Unit"]]
             m = re.search("(" + "|".join(OWN) + ")", r["Kernel Name"])
-            short = m.group(1) if m else re.sub(r"<.*", "", r["Kernel Name"]).replace("void ", "")[:72]
+            short = m.group(1) if m else re.sub(r"<.*", "", r["Kernel Name"].replace("<unnamed>::", "")).replace("void ", "")[:72]
             agg[short][0] += 1
             agg[short][1] += v
             tot += v

@@ -64,22 +64,16 @@ template <int C>
 __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                          const float* __restrict__ b1, const float* __restrict__ w2,
                                                          const float* __restrict__ b2, const float* __restrict__ gamma,
-                                                         const float* __restrict__ beta, int CI, int T,
-                                                         float* __restrict__ hn) {
+                                                         const float* __restrict__ beta, long long N, int CI, int T,
+                                                         int rows_per_cta, float* __restrict__ hn) {
   extern __shared__ __align__(16) float smem[];
   const int TP = T + 4;                              // row pitch: data starts at column 4 (16-byte aligned, T % 4 == 0),
-                                                     // columns 2,3 are the zero halo of the causal convolutions
+                                                     // columns 0..3 are zero: the halo of the causal convolutions
   float* sx = smem;                                  // [CI][TP]
   float* sh = sx + CI * TP;                          // [C][TP]
   float* sw1 = sh + C * TP;                          // [CI][3][C]  (tap-major inside a channel, channels contiguous)
   float* sw2 = sw1 + CI * 3 * C;                     // [C][3][C]
-  const long long n = blockIdx.x;
-  const float* xr = x + n * (long long)CI * T;
-  for (int i = threadIdx.x; i < CI * TP; i += blockDim.x) {
-    int ci = i / TP, t = i - ci * TP;
-    sx[i] = t < 4 ? 0.0f : xr[ci * T + (t - 4)];
-  }
-  for (int i = threadIdx.x; i < C * 4; i += blockDim.x) sh[(i >> 2) * TP + (i & 3)] = 0.0f;
+  // weights once per CTA (they were a third of a row's load traffic when staged per row)
   for (int i = threadIdx.x; i < CI * 3 * C; i += blockDim.x) {       // w1 [C][CI][3] -> [CI][3][C]
     int ci = i / (3 * C), r = i - ci * 3 * C, k = r / C, co = r - k * C;
     sw1[i] = w1[(co * CI + ci) * 3 + k];
@@ -88,76 +82,98 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
     int ci = i / (3 * C), r = i - ci * 3 * C, k = r / C, co = r - k * C;
     sw2[i] = w2[(co * C + ci) * 3 + k];
   }
-  __syncthreads();
+  for (int i = threadIdx.x; i < (CI + C) * 4; i += blockDim.x) sx[(i >> 2) * TP + (i & 3)] = 0.0f;   // halos of sx and sh
   const int t0 = threadIdx.x * 4;                    // first of this thread's 4 positions
   const bool active = t0 < T;
-  float acc[4][C];
-  if (active) {
+  const int T4 = T >> 2;
+  for (int rr = 0; rr < rows_per_cta; ++rr) {
+    const long long n = (long long)blockIdx.x * rows_per_cta + rr;
+    if (n >= N) break;
+    __syncthreads();                                 // previous row's readers of sx / sh are done
+    const float* xr = x + n * (long long)CI * T;
+    for (int i = threadIdx.x; i < CI * T4; i += blockDim.x) {
+      const int ci = i / T4, q = i - ci * T4;
+      *reinterpret_cast<float4*>(sx + ci * TP + 4 + 4 * q) = *reinterpret_cast<const float4*>(xr + ci * T + 4 * q);
+    }
+    __syncthreads();
+    float acc[4][C];
+    if (active) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[p][c] = b1[c];
+      for (int ci = 0; ci < CI; ++ci) {
+        float xv[6];                                                                    // x[t0-2 .. t0+3]
+        {
+          const float4 a = *reinterpret_cast<const float4*>(sx + ci * TP + t0);        // columns t0..t0+3 = x[t0-4..t0-1]
+          const float4 b = *reinterpret_cast<const float4*>(sx + ci * TP + t0 + 4);
+          xv[0] = a.z; xv[1] = a.w; xv[2] = b.x; xv[3] = b.y; xv[4] = b.z; xv[5] = b.w;
+        }
+        const float* w = sw1 + ci * 3 * C;
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int c = 0; c < C; c += 4) {
+            const float4 wv = *reinterpret_cast<const float4*>(w + k * C + c);
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              acc[p][c] = fmaf(wv.x, xv[p + k], acc[p][c]);
+              acc[p][c + 1] = fmaf(wv.y, xv[p + k], acc[p][c + 1]);
+              acc[p][c + 2] = fmaf(wv.z, xv[p + k], acc[p][c + 2]);
+              acc[p][c + 3] = fmaf(wv.w, xv[p + k], acc[p][c + 3]);
+            }
+          }
+      }
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4*>(sh + c * TP + 4 + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    }
+    __syncthreads();
+    if (!active) continue;
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
-      for (int c = 0; c < C; ++c) acc[p][c] = b1[c];
-    for (int ci = 0; ci < CI; ++ci) {
-      float xv[6];                                                                      // x[t0-2 .. t0+3]
+      for (int c = 0; c < C; ++c) acc[p][c] = b2[c];
+    for (int ci = 0; ci < C; ++ci) {
+      float hv[6];
       {
-        const float2 a = *reinterpret_cast<const float2*>(sx + ci * TP + t0 + 2);
-        const float4 b = *reinterpret_cast<const float4*>(sx + ci * TP + t0 + 4);
-        xv[0] = a.x; xv[1] = a.y; xv[2] = b.x; xv[3] = b.y; xv[4] = b.z; xv[5] = b.w;
+        const float4 a = *reinterpret_cast<const float4*>(sh + ci * TP + t0);
+        const float4 b = *reinterpret_cast<const float4*>(sh + ci * TP + t0 + 4);
+        hv[0] = a.z; hv[1] = a.w; hv[2] = b.x; hv[3] = b.y; hv[4] = b.z; hv[5] = b.w;
       }
-      const float* w = sw1 + ci * 3 * C;
+      const float* w = sw2 + ci * 3 * C;
 #pragma unroll
       for (int k = 0; k < 3; ++k)
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-          float wv = w[k * C + c];
+        for (int c = 0; c < C; c += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + k * C + c);
 #pragma unroll
-          for (int p = 0; p < 4; ++p) acc[p][c] = fmaf(wv, xv[p + k], acc[p][c]);
+          for (int p = 0; p < 4; ++p) {
+            acc[p][c] = fmaf(wv.x, hv[p + k], acc[p][c]);
+            acc[p][c + 1] = fmaf(wv.y, hv[p + k], acc[p][c + 1]);
+            acc[p][c + 2] = fmaf(wv.z, hv[p + k], acc[p][c + 2]);
+            acc[p][c + 3] = fmaf(wv.w, hv[p + k], acc[p][c + 3]);
+          }
         }
+    }
+    float* out = hn + n * (long long)C * T;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float m = 0.0f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) m += acc[p][c];
+      m *= (1.0f / C);
+      float v = 0.0f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { float d = acc[p][c] - m; v = fmaf(d, d, v); }
+      float r = rsqrtf(v * (1.0f / C) + 1e-5f);
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[p][c] = fmaf((acc[p][c] - m) * r, gamma[c], beta[c]);
     }
 #pragma unroll
     for (int c = 0; c < C; ++c)
-      *reinterpret_cast<float4*>(sh + c * TP + 4 + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      *reinterpret_cast<float4*>(out + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
   }
-  __syncthreads();
-  if (!active) return;
-#pragma unroll
-  for (int p = 0; p < 4; ++p)
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[p][c] = b2[c];
-  for (int ci = 0; ci < C; ++ci) {
-    float hv[6];
-    {
-      const float2 a = *reinterpret_cast<const float2*>(sh + ci * TP + t0 + 2);
-      const float4 b = *reinterpret_cast<const float4*>(sh + ci * TP + t0 + 4);
-      hv[0] = a.x; hv[1] = a.y; hv[2] = b.x; hv[3] = b.y; hv[4] = b.z; hv[5] = b.w;
-    }
-    const float* w = sw2 + ci * 3 * C;
-#pragma unroll
-    for (int k = 0; k < 3; ++k)
-#pragma unroll
-      for (int c = 0; c < C; ++c) {
-        float wv = w[k * C + c];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) acc[p][c] = fmaf(wv, hv[p + k], acc[p][c]);
-      }
-  }
-  float* out = hn + n * (long long)C * T;
-#pragma unroll
-  for (int p = 0; p < 4; ++p) {
-    float m = 0.0f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) m += acc[p][c];
-    m *= (1.0f / C);
-    float v = 0.0f;
-#pragma unroll
-    for (int c = 0; c < C; ++c) { float d = acc[p][c] - m; v = fmaf(d, d, v); }
-    float r = rsqrtf(v * (1.0f / C) + 1e-5f);
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[p][c] = fmaf((acc[p][c] - m) * r, gamma[c], beta[c]);
-  }
-#pragma unroll
-  for (int c = 0; c < C; ++c)
-    *reinterpret_cast<float4*>(out + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
 }
 
 inline unsigned stream_grid(long long n, int block, int sms) {
@@ -188,11 +204,14 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
   if ((reinterpret_cast<uintptr_t>(hn) & 15) != 0) return cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * ((size_t)(CI + C) * (T + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorInvalidValue;
+  const int rpc = N >= 8192 ? 8 : 1;                   // rows per CTA: amortises the weight staging on big launches
+  const unsigned grid = (unsigned)((N + rpc - 1) / rpc);
 #define UPD_TCN_CASE(CC)                                                                                             \
   case CC: {                                                                                                         \
     cudaError_t e = cudaFuncSetAttribute(stg_tcn_ln_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                  \
-    stg_tcn_ln_kernel<CC><<<(unsigned)N, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, CI, T, hn);         \
+    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn);        \
     break;                                                                                                           \
   }
   switch (C) {
