@@ -46,7 +46,8 @@ enum {
 /* Sampler implementations (same results within fp32 round-off). */
 enum {
   UPD_IMPL_TCGEN05 = 0,      /* tcgen05/TMEM tensor-core kernel (default, the product path)    */
-  UPD_IMPL_SIMT = 1          /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
+  UPD_IMPL_SIMT = 1,         /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
+  UPD_IMPL_TCGEN05_X3 = 2    /* tcgen05 kernel with three tiles per SM in rotation (sampler_tc3.cu) */
 };
 
 const char* upd_error_string(int code);

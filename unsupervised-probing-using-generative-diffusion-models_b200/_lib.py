@@ -17,7 +17,7 @@ SYMBOLS = (
 )
 
 KIND_NSDIFF, KIND_TMDM = 0, 1
-IMPL_TCGEN05, IMPL_SIMT = 0, 1
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X3 = 0, 1, 2
 _fp = ctypes.POINTER(ctypes.c_float)
 
 
