@@ -47,7 +47,8 @@ enum {
 enum {
   UPD_IMPL_TCGEN05 = 0,      /* tcgen05/TMEM tensor-core kernel (default, the product path)    */
   UPD_IMPL_SIMT = 1,         /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
-  UPD_IMPL_TCGEN05_X3 = 2    /* tcgen05 kernel with three tiles per SM in rotation (sampler_tc3.cu) */
+  UPD_IMPL_TCGEN05_X3 = 2,   /* tcgen05 kernel with three tiles per SM in rotation (sampler_tc3.cu) */
+  UPD_IMPL_TCGEN05_X3W = 3   /* three tiles x eight warps, 768 threads (sampler_tc3w.cu)          */
 };
 
 const char* upd_error_string(int code);

@@ -43,7 +43,7 @@ def _pack_ns(sd, F, T=20, schedule="linear"):
     return kernels.pack_denoiser(sd, kernels.KIND_NSDIFF, F, T, schedules.stack_rows(tab, schedules.NSDIFF_ROWS), _dev())
 
 
-IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param(2, id="tcgen05x3")]
+IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param(2, id="tcgen05x3"), pytest.param(3, id="tcgen05x3w")]
 
 
 # ---------------------------------------------------------------- tcgen05 descriptor known-answer

@@ -17,7 +17,7 @@ SYMBOLS = (
 )
 
 KIND_NSDIFF, KIND_TMDM = 0, 1
-IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X3 = 0, 1, 2
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X3, IMPL_TCGEN05_X3W = 0, 1, 2, 3
 _fp = ctypes.POINTER(ctypes.c_float)
 
 

@@ -203,7 +203,8 @@ static int sample_common(int kind, const void* packed, const float* y0_hat, cons
   if (kind == UPD_KIND_TMDM && !y0_hat) return UPD_ERR_BAD_ARG;
   if (!dims_ok(kind, F, T)) return UPD_ERR_UNSUPPORTED;
   if (noise && (K % S) != 0) return UPD_ERR_BAD_ARG;
-  if (impl != UPD_IMPL_TCGEN05 && impl != UPD_IMPL_SIMT && impl != UPD_IMPL_TCGEN05_X3) return UPD_ERR_BAD_ARG;
+  if (impl != UPD_IMPL_TCGEN05 && impl != UPD_IMPL_SIMT && impl != UPD_IMPL_TCGEN05_X3 && impl != UPD_IMPL_TCGEN05_X3W)
+    return UPD_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0) return UPD_ERR_BAD_ARG;
   int sms = 0;
   int rc = device_info(&sms);
@@ -218,6 +219,7 @@ static int sample_common(int kind, const void* packed, const float* y0_hat, cons
 #endif
   cudaError_t e = (impl == UPD_IMPL_SIMT)         ? upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream)
                   : (impl == UPD_IMPL_TCGEN05_X3) ? upd_launch_sampler_tc3(p, kind, F, sms, (cudaStream_t)stream)
+                  : (impl == UPD_IMPL_TCGEN05_X3W) ? upd_launch_sampler_tc3w(p, kind, F, sms, (cudaStream_t)stream)
                                                   : upd_launch_sampler_tc(p, kind, F, sms, (cudaStream_t)stream);
   if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
   return e == cudaSuccess ? UPD_OK : cuda_fail(e);

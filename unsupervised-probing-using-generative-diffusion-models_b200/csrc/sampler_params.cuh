@@ -50,3 +50,4 @@ __device__ __forceinline__ float upd_draw(const UpdSamplerParams& p, const UpdRo
 cudaError_t upd_launch_sampler_simt(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);
 cudaError_t upd_launch_sampler_tc(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);
 cudaError_t upd_launch_sampler_tc3(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);
+cudaError_t upd_launch_sampler_tc3w(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);
