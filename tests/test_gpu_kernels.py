@@ -159,15 +159,17 @@ def _random_ns_weights(F, T):
     return sd
 
 
-def test_tc_matches_simt_bitwise_structure_large():
-    """Full-size tile coverage: 5 windows x K=100 x O=200 (100k rows) -- both implementations agree."""
+@pytest.mark.parametrize("tc_impl", [0, 2, 3])
+def test_tc_matches_simt_bitwise_structure_large(tc_impl):
+    """Full-size tile coverage: 5 windows x K=100 x O=200 (100k rows; 782 tiles = several rotations of the persistent
+    grid for the 2-tile and both 3-tile kernels) -- every tensor-core implementation agrees with the FFMA kernel."""
     kernels, _ = _k()
     _, sd = load_wo_fx_checkpoint()
     dev = _dev()
     packed = _pack_ns(sd, 2)
     torch.manual_seed(3)
     gx = (torch.rand(5, 200, 2) * 0.06 + 0.01).to(dev)
-    a = kernels.nsdiff_sample(packed, None, gx, 5, 1, 100, 100, 200, 2, 20, seed=11, window_base=7, impl=0)
+    a = kernels.nsdiff_sample(packed, None, gx, 5, 1, 100, 100, 200, 2, 20, seed=11, window_base=7, impl=tc_impl)
     b = kernels.nsdiff_sample(packed, None, gx, 5, 1, 100, 100, 200, 2, 20, seed=11, window_base=7, impl=1)
     _assert_traj(a, b, "tc vs simt")
 
@@ -417,3 +419,23 @@ def test_fx_tcgen05_attention_against_fp64(Lq, S, causal, use_delta):
     assert torch.isfinite(val).all()
     assert float((val.double() - ref).abs().max() / ref.abs().max()) < 2e-5
     assert torch.equal(tail, torch.tensor([1., 1., 0, 0, 0, 0, 0, 0], device=dev).expand(B * Lq, 8))
+
+
+@pytest.mark.parametrize("impl", [2, 3])
+def test_three_tile_kernels_full_bench_shape_against_two_tile(impl):
+    """BASELINE config-2 shape at a size where every SM runs many rotations (30 windows x 100 rows x K=100 x O=100 =
+    30 M rows): the three-tile kernels reproduce the two-tile kernel (same Philox noise) to reordering error."""
+    kernels, schedules = _k()
+    dev = _dev()
+    g = load_golden("psample_loop_randF1.npz")
+    tab = schedules.nsdiff_tables("linear", 20, 1e-4, 0.02)
+    packed = kernels.pack_denoiser(g["sd"], 0, 1, 20, schedules.stack_rows(tab, schedules.NSDIFF_ROWS), dev)
+    torch.manual_seed(8)
+    n_win, B, K, O = 30, 100, 100, 100
+    gx = torch.rand(n_win * B, O, 1, device=dev) * 0.3 + 0.05
+    y0 = torch.randn(n_win * B, O, 1, device=dev)
+    a = kernels.nsdiff_sample(packed, y0, gx, n_win, B, K, 10, O, 1, 20, seed=5, window_base=3, impl=0)
+    b = kernels.nsdiff_sample(packed, y0, gx, n_win, B, K, 10, O, 1, 20, seed=5, window_base=3, impl=impl)
+    rms = float(a.pow(2).mean().sqrt())
+    assert torch.isfinite(b).all()
+    assert float((a - b).abs().max()) / rms < 2e-5
