@@ -1,11 +1,11 @@
 """profiles/r01_families_*: launch shares and ncu --set full metrics of the DiffSTG / DiffusionTS kernels.
 
     python profiles/make_family_summaries.py r01
-Inputs (gpurun_out/, produced by scratch/gpu_job30.sh on a B200):
+Inputs (gpurun_out/, produced on a B200):
     ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_families_launches.csv \
-        python scratch/gpu_prof_families.py
+        python profiles/tools/gpu_prof_families.py
     ncu --set full --clock-control none --import-source on -k 'regex:stg_tcn_ln|dts_fourier_topk|stg_gated_aggregate' -c 8 \
-        -o gpurun_out/prof_families python scratch/gpu_prof_families.py
+        -o gpurun_out/prof_families python profiles/tools/gpu_prof_families.py
 The profiled command: 2 DiffSTG denoise steps on 16 384 replica rows (BASELINE config 5 architecture, BA-100 graph) and one
 DiffusionTS loop iteration t=99->98 (x0 prediction, DDIM mean, 3 Langevin iterations, infill) on 1000 rows (config 4).
 """
@@ -28,7 +28,7 @@ first_dts = next(i for i, r in enumerate(rows) if "dts_" in r["Kernel Name"] or 
 last_stg = max(i for i, r in enumerate(rows) if "stg_" in r["Kernel Name"])
 parts = {"DiffSTG (2 denoise steps, 16384 rows)": rows[: last_stg + 1], "DiffusionTS (1 loop iteration, K=3, 1000 rows)": rows[last_stg + 1:]}
 with open("profiles/%s_families_launches_summary.txt" % tag, "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none   python scratch/gpu_prof_families.py\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none   python profiles/tools/gpu_prof_families.py\n")
     f.write("# per-launch times are cold-cache and serialised: compare SHARES\n")
     for name, rs in parts.items():
         agg, tot = collections.defaultdict(lambda: [0, 0.0]), 0.0
