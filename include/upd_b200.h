@@ -273,6 +273,12 @@ int upd_fx_add_ln_split(const float* x_dev, const float* res_dev, const float* g
                         const float* g2_dev, const float* b2_dev, long long rows, int K, float* y_dev, void* a3_dev,
                         void* stream);
 
+/* upd_fx_embed_split -- DataEmbedding (circular token Conv1d(k=3, no bias) + positional table; torch-timeseries block used
+ *   at mu_backbone.py:66-69): x_dev [rows/L, L, NF], w_dev [K, NF, 3], pe_dev [>= L, K] -> y_dev [rows, K] fp32 and its
+ *   split operand a3_dev [rows, 3K+8].  K multiple of 4, K <= 1024. */
+int upd_fx_embed_split(const float* x_dev, const float* w_dev, const float* pe_dev, long long rows, int L, int NF, int K,
+                       float* y_dev, void* a3_dev, void* stream);
+
 /* upd_fx_attention -- replaces DSAttention + the head merge of AttentionLayer (torch-timeseries 0.1.10, called from
  *   mu_backbone.py:70-104): out = softmax(scale * (tau_b * Q K^T + delta_b)) V on tcgen05 tensor cores (fp16 hi/lo
  *   operands, fp32 accumulation), written directly as the split operand A3 [B*Lq, 3*H*64+8] of the out-projection GEMM.

@@ -52,6 +52,8 @@ cudaError_t upd_launch_dts_attention_bwd(const float* q, long long q_stride, con
                                          long long kv_stride, int R, int H, int Lq, int S, float scale, const float* o,
                                          const float* lse, const float* d_o, float* dq, long long dq_stride, float* dk,
                                          float* dv, long long dkv_stride, cudaStream_t stream);
+cudaError_t upd_launch_fx_embed_split(const float* x, const float* w, const float* pe, long long rows, int L, int NF, int K,
+                                      float* y, void* a3, cudaStream_t stream);
 
 namespace {
 
@@ -416,6 +418,13 @@ int upd_dts_attention_bwd(const float* q_dev, long long q_row_stride, const floa
   UPD_FINISH(upd_launch_dts_attention_bwd(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev,
                                           lse_dev, do_dev, dq_dev, dq_row_stride, dk_dev, dv_dev, dkv_row_stride,
                                           (cudaStream_t)stream));
+}
+
+int upd_fx_embed_split(const float* x_dev, const float* w_dev, const float* pe_dev, long long rows, int L, int NF, int K,
+                       float* y_dev, void* a3_dev, void* stream) {
+  if (!x_dev || !w_dev || !pe_dev || !y_dev || !a3_dev || rows <= 0) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_fx_embed_split(x_dev, w_dev, pe_dev, rows, L, NF, K, y_dev, a3_dev, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -125,6 +125,37 @@ __global__ void fx_add_ln_split_kernel(const float* __restrict__ x, const float*
   }
 }
 
+// DataEmbedding of the condition encoder: circular Conv1d(c_in -> d, k=3, no bias) over the sequence + sinusoidal
+// positional table, written as fp32 AND as the split operand of the first projection GEMM in one pass
+// (TokenEmbedding / PositionalEmbedding of torch-timeseries as used at mu_backbone.py:66-69; three einsum + roll + add
+// launches over [B,L,d] before).  One warp per (b,l) row; x [B,L,NF], w [d,NF,3], pe [>=L, d].
+__global__ void fx_embed_split_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ pe,
+                                      long long rows, int L, int NF, int K, float* __restrict__ y, __half* __restrict__ a3) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const long long b = r / L;
+  const int l = (int)(r - b * L);
+  const float* xb = x + b * (long long)L * NF;
+  const int lm = (l + L - 1) % L, lp = (l + 1) % L;
+  __half* out = a3 + r * (3 * K + 8);
+  for (int c = lane * 4; c < K; c += 128) {
+    float4 v = *reinterpret_cast<const float4*>(pe + (long long)l * K + c);
+    for (int f = 0; f < NF; ++f) {
+      const float x0 = xb[lm * NF + f], x1 = xb[l * NF + f], x2 = xb[lp * NF + f];
+      const float* wc = w + ((long long)c * NF + f) * 3;          // w[c][f][0..2], next channel NF*3 further
+      const int st = NF * 3;
+      v.x += wc[0] * x0 + wc[1] * x1 + wc[2] * x2;
+      v.y += wc[st] * x0 + wc[st + 1] * x1 + wc[st + 2] * x2;
+      v.z += wc[2 * st] * x0 + wc[2 * st + 1] * x1 + wc[2 * st + 2] * x2;
+      v.w += wc[3 * st] * x0 + wc[3 * st + 1] * x1 + wc[3 * st + 2] * x2;
+    }
+    *reinterpret_cast<float4*>(y + r * K + c) = v;
+    fx_store4(out, K, c, v);
+  }
+  if (lane == 0) fx_store_tail(out, K);
+}
+
 }  // namespace
 
 cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, int L, int act, void* a3,
@@ -152,5 +183,15 @@ cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const f
     default: return cudaErrorInvalidValue;
   }
 #undef UPD_LN_CASE
+  return cudaGetLastError();
+}
+
+cudaError_t upd_launch_fx_embed_split(const float* x, const float* w, const float* pe, long long rows, int L, int NF, int K,
+                                      float* y, void* a3, cudaStream_t stream) {
+  if (K < 4 || K > FX_MAX_K || (K & 3) || L < 1 || NF < 1 || rows % L) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(pe) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(a3) & 15))
+    return cudaErrorInvalidValue;
+  const int wpb = 8;
+  fx_embed_split_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(x, w, pe, rows, L, NF, K, y, (__half*)a3);
   return cudaGetLastError();
 }

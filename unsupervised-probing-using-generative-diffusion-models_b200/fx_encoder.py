@@ -234,6 +234,19 @@ class DataEmbedding(nn.Module):
     def forward(self, x, x_mark=None):
         return self.value_embedding(x) + self.position_embedding(x)
 
+    def fused(self, x):
+        """x [B, L, c_in] -> (embedding [B*L, d] fp32, its split operand) in one kernel (upd_fx_embed_split)."""
+        B, L, nf = x.shape
+        w = self.value_embedding.tokenConv.weight.detach()
+        d = w.shape[0]
+        pe = self.position_embedding.pe[0]
+        y = torch.empty((B * L, d), dtype=torch.float32, device=x.device)
+        a3 = torch.empty((B * L, 3 * d + 8), dtype=torch.float16, device=x.device)
+        rc = _lib.lib().upd_fx_embed_split(_lib.ptr(x.contiguous()), _lib.ptr(w.contiguous()), _lib.ptr(pe), B * L, L, nf, d,
+                                           _lib.ptr(y), _lib.ptr(a3), _lib.stream_ptr(x.device))
+        _lib.check(rc, "upd_fx_embed_split")
+        return y, a3
+
 
 class AttentionLayer(nn.Module):
     """Projections + de-stationary attention: softmax(scale * (Q K^T * tau + delta)) V."""
@@ -443,8 +456,7 @@ class NsTransformer(nn.Module):
         B, L, _ = x_enc.shape
         Ld = x_dec_new.shape[1]
         d = self.enc_embedding.value_embedding.tokenConv.out_channels
-        x = self.enc_embedding(x_enc).reshape(B * L, d).contiguous()
-        a3 = a3_split(x)
+        x, a3 = self.enc_embedding.fused(x_enc)
         # scale * delta, stored with a 16-float-aligned row pitch (see AttentionLayer.fused)
         S = delta.shape[1]
         pitch = (S + 15) // 16 * 16
@@ -458,8 +470,7 @@ class NsTransformer(nn.Module):
             x = self.z_out(self.z_mean(x))                    # eval: z = posterior mean (:133-134)
             a3 = a3_split(x.contiguous())
         a3_enc = a3
-        xd = self.dec_embedding(x_dec_new).reshape(B * Ld, d).contiguous()
-        a3 = a3_split(xd)
+        xd, a3 = self.dec_embedding.fused(x_dec_new)
         layers = self.decoder.layers
         for i, layer in enumerate(layers):
             last = i == len(layers) - 1
