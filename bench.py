@@ -274,10 +274,23 @@ def run_own_arm(args, rank, world, local_rank):
     h2d = host_windows.numel() * 4
     d2h = cache.numel() * 4 + sum(v.numel() * 4 for part in cache.upd_stats.values() for v in part.values())
 
-    times = torch.tensor([resident_ms, e2e_ms], dtype=torch.float64, device=dev)
+    # ---- N > 1: ONE sweep (rank 0's series) sharded over the ranks: contiguous window blocks, rank-local caches, the
+    # single all-gather of per-window statistics -- the strong-scaling wall time of BASELINE's second metric
+    dist_ms = 0.0
+    if world > 1:
+        shared = U.stacked_sliding_windows(make_series(0), L, 5).contiguous().pin_memory()
+        U.distributed_sweep(model, shared, device=dev)                     # warm-up (NCCL communicator, allocator)
+        barrier()
+        w0 = time.perf_counter()
+        _, (lo, hi), stats = U.distributed_sweep(model, shared, device=dev)
+        torch.cuda.synchronize(dev)
+        dist_ms = (time.perf_counter() - w0) * 1e3
+        assert stats["mpv"].shape[0] == shared.shape[0]
+
+    times = torch.tensor([resident_ms, e2e_ms, dist_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    resident_ms, e2e_ms = times.tolist()
+    resident_ms, e2e_ms, dist_ms = times.tolist()
     if rank != 0:
         return
     peaks = measured_peaks()
@@ -301,6 +314,10 @@ def run_own_arm(args, rank, world, local_rank):
                      "note": "algorithmic FLOPs = 2*33408 MAC per denoiser row-step (SURVEY 8a7); the MLP is MUFU-bound "
                              "(514 softplus per row-step), see DESIGN.md"},
     }
+    if world > 1:
+        line["sweep_wall"] = {"one_sweep_sharded_ms": dist_ms, "windows": W, "ranks": world,
+                              "note": "one 181-window sweep split over the ranks (contiguous blocks) + one all-gather of "
+                                      "per-window MPV; max over ranks, wall clock"}
     if world == 1:
         # BASELINE's second metric: MPV sweep wall time = windows -> sample -> reduce -> per-window MPV list, cache file
         # written (reference: diffusion_model_uncertainy.py:323-339 + :286-303).  One sweep, outside the timed region.
