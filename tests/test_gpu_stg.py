@@ -132,7 +132,15 @@ def test_fused_tcn_layernorm_kernel_against_library_ops(C, CI, T):
     ref = F.layer_norm(h.transpose(1, 2), (C,), g, be).transpose(1, 2)
     out = torch.empty(N, C, T, device=DEV)
     _lib.check(_lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
-                                         _lib.ptr(be), N, CI, C, T, _lib.ptr(out), _lib.stream_ptr(torch.device(DEV))), "tcn")
+                                         _lib.ptr(be), N, CI, C, T, _lib.ptr(out), None, _lib.stream_ptr(torch.device(DEV))), "tcn")
     assert _rel(out, ref) < 2e-5, _rel(out, ref)
+    # the same row emitted as the fp16 split operand [hi | lo | hi | 1 1 0..] of the GEMM that follows
+    K = C * T
+    a3 = torch.empty(N, 3 * K + 8, dtype=torch.float16, device=DEV)
+    _lib.check(_lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
+                                         _lib.ptr(be), N, CI, C, T, None, _lib.ptr(a3), _lib.stream_ptr(torch.device(DEV))), "tcn")
+    val = a3[:, :K].float() + a3[:, K:2 * K].float()
+    assert torch.equal(a3[:, :K], a3[:, 2 * K:3 * K]) and float(a3[:, 3 * K].min()) == 1.0 and float(a3[:, 3 * K + 2:].abs().max()) == 0.0
+    assert _rel(val, ref.reshape(N, K)) < 2e-5
     assert _lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
-                                     _lib.ptr(be), N, CI, 5, T, _lib.ptr(out), None) == 2      # UPD_ERR_UNSUPPORTED
+                                     _lib.ptr(be), N, CI, 5, T, _lib.ptr(out), None, None) == 2      # UPD_ERR_UNSUPPORTED

@@ -3,6 +3,7 @@
 //   SpatialBlock = relu(ResGatedGraphConv) ..... models/Diffusion_model/DiffSTG/ugnet.py:36-45, models/layer/gnn_conv.py:18-19
 //   duplicate_edge_index ....................... graph_diffusion_model.py:77-84 (replicas share one CSR here)
 // HBM/L2-bound gather kernels; no tensor-core work.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -65,7 +66,8 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
                                                          const float* __restrict__ b1, const float* __restrict__ w2,
                                                          const float* __restrict__ b2, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, long long N, int CI, int T,
-                                                         int rows_per_cta, float* __restrict__ hn) {
+                                                         int rows_per_cta, float* __restrict__ hn,
+                                                         __half* __restrict__ a3) {
   extern __shared__ __align__(16) float smem[];
   const int TP = T + 4;                              // row pitch: data starts at column 4 (16-byte aligned, T % 4 == 0),
                                                      // columns 0..3 are zero: the halo of the causal convolutions
@@ -170,9 +172,30 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
 #pragma unroll
       for (int c = 0; c < C; ++c) acc[p][c] = fmaf((acc[p][c] - m) * r, gamma[c], beta[c]);
     }
+    if (a3 == nullptr) {
 #pragma unroll
-    for (int c = 0; c < C; ++c)
-      *reinterpret_cast<float4*>(out + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4*>(out + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    } else {
+      // the row as the split operand [hi | lo | hi | 1 1 0..] (K = C*T) of the fp16 tensor-core GEMM that follows
+      const int K = C * T;
+      __half* row = a3 + n * (long long)(3 * K + 8);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        __half2 h01 = __floats2half2_rn(acc[0][c], acc[1][c]), h23 = __floats2half2_rn(acc[2][c], acc[3][c]);
+        float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        __half2 l01 = __floats2half2_rn(acc[0][c] - f01.x, acc[1][c] - f01.y);
+        __half2 l23 = __floats2half2_rn(acc[2][c] - f23.x, acc[3][c] - f23.y);
+        uint2 hi, lo;
+        hi.x = *reinterpret_cast<uint32_t*>(&h01); hi.y = *reinterpret_cast<uint32_t*>(&h23);
+        lo.x = *reinterpret_cast<uint32_t*>(&l01); lo.y = *reinterpret_cast<uint32_t*>(&l23);
+        const int col = c * T + t0;
+        *reinterpret_cast<uint2*>(row + col) = hi;
+        *reinterpret_cast<uint2*>(row + K + col) = lo;
+        *reinterpret_cast<uint2*>(row + 2 * K + col) = hi;
+      }
+      if (threadIdx.x == 0) *reinterpret_cast<uint4*>(row + 3 * K) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+    }
   }
 }
 
@@ -198,10 +221,11 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
 
 cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
-                                  cudaStream_t stream) {
+                                  void* a3, cudaStream_t stream) {
   const int threads = ((T / 4) + 31) / 32 * 32;
   if ((T & 3) != 0 || threads > 128 || CI < 1 || N > 0x7fffffffLL) return cudaErrorInvalidValue;
-  if ((reinterpret_cast<uintptr_t>(hn) & 15) != 0) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(hn) & 15) != 0 || (reinterpret_cast<uintptr_t>(a3) & 15) != 0) return cudaErrorInvalidValue;
+  if (hn == nullptr && a3 == nullptr) return cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * ((size_t)(CI + C) * (T + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C);
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorInvalidValue;
@@ -211,7 +235,7 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
   case CC: {                                                                                                         \
     cudaError_t e = cudaFuncSetAttribute(stg_tcn_ln_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                  \
-    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn);        \
+    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn, (__half*)a3); \
     break;                                                                                                           \
   }
   switch (C) {

@@ -29,6 +29,7 @@ import torch.nn.functional as F
 
 from . import _lib
 from .diffusionts import ParamTree
+from .fx_encoder import _W3Cache, a3_split, gemm3
 
 ROWS_PER_LAUNCH = 32768
 
@@ -238,6 +239,13 @@ class PreparedUGnet:
                       torch.zeros(C, device=dev)]
                 b["kqvs_w"], b["kqvs_b"] = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
                 b["gnn_bias"] = sd.get(g + "bias")
+                # split-operand weights of the three dense maps for the fp16 tensor-core path (K multiple of 4)
+                if (c_out * T_in) % 4 == 0 and C % 4 == 0:
+                    b["down_w3"] = _W3Cache().get([(b["down_w"].t().contiguous(), b["down_b"])])
+                    b["kqvs_w3"] = _W3Cache().get([(b["kqvs_w"], b["kqvs_b"])])
+                    b["up_w3"] = _W3Cache().get([(b["up_w"].t().contiguous(), b["up_b_full"])])
+                else:
+                    b["down_w3"] = b["kqvs_w3"] = b["up_w3"] = None
             else:
                 b["w"], b["b"] = sd[pre + "conv.weight"][:, :, 0, :].contiguous(), sd[pre + "conv.bias"]
             self.blocks[pre] = b
@@ -245,31 +253,47 @@ class PreparedUGnet:
         self.out0_w, self.out0_b = sd["out.0.weight"][:, :, 0, :].contiguous(), sd["out.0.bias"]
         self.out1_w, self.out1_b = sd["out.1.weight"], sd["out.1.bias"]
 
-    def _front(self, b, x, t, c_in, c_out, T_in):
-        """tcn1 (+ step embedding) -> tcn2 -> LayerNorm over channels: x [N, c_in, T] -> hn [N, c_out, T]."""
+    def _front(self, b, x, t, c_in, c_out, T_in, as_operand):
+        """tcn1 (+ step embedding) -> tcn2 -> LayerNorm over channels: x [N, c_in, T] -> hn [N, c_out*T] fp32, or -- when
+        ``as_operand`` -- directly the fp16 split operand [N, 3*c_out*T+8] of the down-sampling GEMM."""
         N = x.shape[0]
         if c_out in (4, 8, 16) and T_in % 4 == 0 and T_in <= 512:
-            hn = torch.empty((N, c_out, T_in), dtype=torch.float32, device=x.device)
+            K = c_out * T_in
+            hn = None if as_operand else torch.empty((N, K), dtype=torch.float32, device=x.device)
+            a3 = torch.empty((N, 3 * K + 8), dtype=torch.float16, device=x.device) if as_operand else None
             rc = _lib.lib().upd_stg_tcn_ln(_lib.ptr(x.contiguous()), _lib.ptr(b["tcn1.w"]), _lib.ptr(b["tcn1.b_step"][t]),
                                            _lib.ptr(b["tcn2.w"]), _lib.ptr(b["tcn2.b"]), _lib.ptr(b["norm_w"]),
-                                           _lib.ptr(b["norm_b"]), N, c_in, c_out, T_in, _lib.ptr(hn),
+                                           _lib.ptr(b["norm_b"]), N, c_in, c_out, T_in, _lib.ptr(hn), _lib.ptr(a3),
                                            _lib.stream_ptr(x.device))
             _lib.check(rc, "upd_stg_tcn_ln")
-            return hn
+            return a3 if as_operand else hn
         # shapes outside the fused kernel's limits: the same arithmetic as library ops
         h = F.conv1d(F.pad(x, (2, 0)), b["tcn1.w"], b["tcn1.b_step"][t])
         h = F.conv1d(F.pad(h, (2, 0)), b["tcn2.w"], b["tcn2.b"])
         var, mu = torch.var_mean(h, dim=1, unbiased=False, keepdim=True)
-        return (h - mu) * torch.rsqrt(var + 1e-5) * b["norm_w"][None, :, None] + b["norm_b"][None, :, None]
+        hn = ((h - mu) * torch.rsqrt(var + 1e-5) * b["norm_w"][None, :, None] + b["norm_b"][None, :, None]).reshape(N, -1)
+        return a3_split(hn.contiguous()) if as_operand else hn
 
     def _res(self, pre, x, t, c_in, c_out, T_in, rowptr, col, V):
+        """One ResidualBlock.  The three dense maps (down-sampling, K|Q|V|skip, up-sampling) run as error-compensated
+        fp16 tensor-core GEMMs (fx_encoder.gemm3: [x_hi | x_lo | x_hi | 1 1 0..] x [W_hi | W_hi | W_lo | b..]^T, 3e-6
+        accuracy) when their widths allow it, else as fp32 library GEMMs."""
         b, Td = self.blocks[pre], self.Td_h
         N = x.shape[0]
-        hn = self._front(b, x, t, c_in, c_out, T_in)
-        sp = torch.addmm(b["down_b"], hn.view(N, c_out * T_in), b["down_w"])                  # [N, Td*c]
-        kqvs = torch.addmm(b["kqvs_b"], sp, b["kqvs_w"].t())                                 # [N, 4C]
-        agg = gated_aggregate(kqvs, rowptr, col, b["gnn_bias"], V, Td * c_out)
-        up = torch.addmm(b["up_b_full"], agg, b["up_w"]).view(N, c_out, T_in)                # + upsampling (+ shortcut) bias
+        C = Td * c_out
+        tc_ok = b["down_w3"] is not None
+        if tc_ok:
+            sp = gemm3(self._front(b, x, t, c_in, c_out, T_in, True), b["down_w3"], C)           # [N, Td*c]
+            kqvs = gemm3(a3_split(sp.contiguous()), b["kqvs_w3"], 4 * C)                        # [N, 4C]
+        else:
+            hn = self._front(b, x, t, c_in, c_out, T_in, False)
+            sp = torch.addmm(b["down_b"], hn, b["down_w"])
+            kqvs = torch.addmm(b["kqvs_b"], sp, b["kqvs_w"].t())
+        agg = gated_aggregate(kqvs.contiguous(), rowptr, col, b["gnn_bias"], V, C)
+        if tc_ok:
+            up = gemm3(a3_split(agg), b["up_w3"], c_out * T_in).view(N, c_out, T_in)            # bias inside the GEMM
+        else:
+            up = torch.addmm(b["up_b_full"], agg, b["up_w"]).view(N, c_out, T_in)
         if c_in == c_out:
             return up.add_(x)
         return torch.baddbmm(up, b["sc_w2"].expand(N, c_out, c_in), x)                       # + 1x1 shortcut(x)
