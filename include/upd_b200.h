@@ -248,10 +248,11 @@ int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const 
  *   x_dev [N, CI, T] -> hn_dev [N, C, T].  w1_dev [C, CI, 3], w2_dev [C, C, 3]: the middle row of the reference's (3,3)
  *   kernels (the image height is 1) with the shortcut (or identity) folded into tap 2; b1_dev [C] = conv bias +
  *   shortcut bias + t_conv(emb(step)); b2_dev [C]; gamma/beta [C].  Exactly one of hn_dev (fp32) and a3_dev (the row as the
- *   fp16 split operand [N, 3*C*T+8] of the down-sampling GEMM, see the f(x) section) is written; the other is NULL.  Limits: C in {4, 8, 16}, T <= 512 and a multiple of 4. */
+ *   fp16 split operand [N, 3*C*T+8] of the down-sampling GEMM, see the f(x) section) is written; the other is NULL.  wsc_dev [C, CI] / sc_dev [N, C, T] (both or neither): the block's 1x1 shortcut W_sc x
+ *   (ugnet.py:129) evaluated in the same pass.  Limits: C in {4, 8, 16}, T <= 512 and a multiple of 4. */
 int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
                    const float* gamma_dev, const float* beta_dev, long long N, int CI, int C, int T, float* hn_dev,
-                   void* a3_dev, void* stream);
+                   void* a3_dev, const float* wsc_dev, float* sc_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * f(x) condition encoder (ns-Transformer; models/Diffusion_model/NsDiff/mu_backbone.py:53-183,

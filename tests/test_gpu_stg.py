@@ -126,21 +126,23 @@ def test_fused_tcn_layernorm_kernel_against_library_ops(C, CI, T):
     w1, b1 = torch.randn(C, CI, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
     w2, b2 = torch.randn(C, C, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
     g, be = torch.randn(C, device=DEV), torch.randn(C, device=DEV)
+    wsc, sc = torch.randn(C, CI, device=DEV) * 0.3, torch.empty(N, C, T, device=DEV)
     with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
         h = F.conv1d(F.pad(x, (2, 0)), w1, b1)
         h = F.conv1d(F.pad(h, (2, 0)), w2, b2)
     ref = F.layer_norm(h.transpose(1, 2), (C,), g, be).transpose(1, 2)
     out = torch.empty(N, C, T, device=DEV)
     _lib.check(_lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
-                                         _lib.ptr(be), N, CI, C, T, _lib.ptr(out), None, _lib.stream_ptr(torch.device(DEV))), "tcn")
+                                         _lib.ptr(be), N, CI, C, T, _lib.ptr(out), None, _lib.ptr(wsc), _lib.ptr(sc), _lib.stream_ptr(torch.device(DEV))), "tcn")
     assert _rel(out, ref) < 2e-5, _rel(out, ref)
+    assert _rel(sc, torch.matmul(wsc, x)) < 1e-5
     # the same row emitted as the fp16 split operand [hi | lo | hi | 1 1 0..] of the GEMM that follows
     K = C * T
     a3 = torch.empty(N, 3 * K + 8, dtype=torch.float16, device=DEV)
     _lib.check(_lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
-                                         _lib.ptr(be), N, CI, C, T, None, _lib.ptr(a3), _lib.stream_ptr(torch.device(DEV))), "tcn")
+                                         _lib.ptr(be), N, CI, C, T, None, _lib.ptr(a3), None, None, _lib.stream_ptr(torch.device(DEV))), "tcn")
     val = a3[:, :K].float() + a3[:, K:2 * K].float()
     assert torch.equal(a3[:, :K], a3[:, 2 * K:3 * K]) and float(a3[:, 3 * K].min()) == 1.0 and float(a3[:, 3 * K + 2:].abs().max()) == 0.0
     assert _rel(val, ref.reshape(N, K)) < 2e-5
     assert _lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
-                                     _lib.ptr(be), N, CI, 5, T, _lib.ptr(out), None, None) == 2      # UPD_ERR_UNSUPPORTED
+                                     _lib.ptr(be), N, CI, 5, T, _lib.ptr(out), None, None, None, None) == 2      # UPD_ERR_UNSUPPORTED

@@ -93,7 +93,7 @@ def lib():
     L.upd_fx_attention.restype = ctypes.c_int
     L.upd_fx_attention.argtypes = [vp, ll, vp, vp, ll, vp, vp, i, i, i, i, i, i, i, f32, vp, vp]
     L.upd_stg_tcn_ln.restype = ctypes.c_int
-    L.upd_stg_tcn_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, vp, vp, vp]
+    L.upd_stg_tcn_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, vp, vp, vp, vp, vp]
     _LIB = L
     return L
 

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
                                                          const float* __restrict__ b2, const float* __restrict__ gamma,
                                                          const float* __restrict__ beta, long long N, int CI, int T,
                                                          int rows_per_cta, float* __restrict__ hn,
-                                                         __half* __restrict__ a3) {
+                                                         __half* __restrict__ a3, const float* __restrict__ wsc,
+                                                         float* __restrict__ sc_out) {
   extern __shared__ __align__(16) float smem[];
   const int TP = T + 4;                              // row pitch: data starts at column 4 (16-byte aligned, T % 4 == 0),
                                                      // columns 0..3 are zero: the halo of the causal convolutions
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
   float* sh = sx + CI * TP;                          // [C][TP]
   float* sw1 = sh + C * TP;                          // [CI][3][C]  (tap-major inside a channel, channels contiguous)
   float* sw2 = sw1 + CI * 3 * C;                     // [C][3][C]
+  float* swsc = sw2 + C * 3 * C;                     // [CI][C]   1x1 block shortcut (optional)
   // weights once per CTA (they were a third of a row's load traffic when staged per row)
   for (int i = threadIdx.x; i < CI * 3 * C; i += blockDim.x) {       // w1 [C][CI][3] -> [CI][3][C]
     int ci = i / (3 * C), r = i - ci * 3 * C, k = r / C, co = r - k * C;
@@ -84,6 +86,8 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
     int ci = i / (3 * C), r = i - ci * 3 * C, k = r / C, co = r - k * C;
     sw2[i] = w2[(co * C + ci) * 3 + k];
   }
+  if (wsc)
+    for (int i = threadIdx.x; i < CI * C; i += blockDim.x) swsc[i] = wsc[(i % C) * CI + i / C];       // [C][CI] -> [CI][C]
   for (int i = threadIdx.x; i < (CI + C) * 4; i += blockDim.x) sx[(i >> 2) * TP + (i & 3)] = 0.0f;   // halos of sx and sh
   const int t0 = threadIdx.x * 4;                    // first of this thread's 4 positions
   const bool active = t0 < T;
@@ -196,6 +200,34 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
       }
       if (threadIdx.x == 0) *reinterpret_cast<uint4*>(row + 3 * K) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
     }
+    if (wsc) {
+      // the block's 1x1 shortcut W_sc x (ugnet.py:129, c_in != c_out) while x is still in shared memory: it becomes the
+      // accumulator input of the up-sampling GEMM instead of a batched [c_out x c_in] matmul over the whole tensor
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int c = 0; c < C; ++c) acc[p][c] = 0.0f;
+      for (int ci = 0; ci < CI; ++ci) {
+        const float4 xb = *reinterpret_cast<const float4*>(sx + ci * TP + t0 + 4);
+        const float* w = swsc + ci * C;
+#pragma unroll
+        for (int c = 0; c < C; c += 4) {
+          const float4 wv = *reinterpret_cast<const float4*>(w + c);
+          acc[0][c] = fmaf(wv.x, xb.x, acc[0][c]); acc[1][c] = fmaf(wv.x, xb.y, acc[1][c]);
+          acc[2][c] = fmaf(wv.x, xb.z, acc[2][c]); acc[3][c] = fmaf(wv.x, xb.w, acc[3][c]);
+          acc[0][c + 1] = fmaf(wv.y, xb.x, acc[0][c + 1]); acc[1][c + 1] = fmaf(wv.y, xb.y, acc[1][c + 1]);
+          acc[2][c + 1] = fmaf(wv.y, xb.z, acc[2][c + 1]); acc[3][c + 1] = fmaf(wv.y, xb.w, acc[3][c + 1]);
+          acc[0][c + 2] = fmaf(wv.z, xb.x, acc[0][c + 2]); acc[1][c + 2] = fmaf(wv.z, xb.y, acc[1][c + 2]);
+          acc[2][c + 2] = fmaf(wv.z, xb.z, acc[2][c + 2]); acc[3][c + 2] = fmaf(wv.z, xb.w, acc[3][c + 2]);
+          acc[0][c + 3] = fmaf(wv.w, xb.x, acc[0][c + 3]); acc[1][c + 3] = fmaf(wv.w, xb.y, acc[1][c + 3]);
+          acc[2][c + 3] = fmaf(wv.w, xb.z, acc[2][c + 3]); acc[3][c + 3] = fmaf(wv.w, xb.w, acc[3][c + 3]);
+        }
+      }
+      float* so = sc_out + n * (long long)C * T;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4*>(so + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+    }
   }
 }
 
@@ -221,12 +253,13 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
 
 cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
-                                  void* a3, cudaStream_t stream) {
+                                  void* a3, const float* wsc, float* sc_out, cudaStream_t stream) {
   const int threads = ((T / 4) + 31) / 32 * 32;
   if ((T & 3) != 0 || threads > 128 || CI < 1 || N > 0x7fffffffLL) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(hn) & 15) != 0 || (reinterpret_cast<uintptr_t>(a3) & 15) != 0) return cudaErrorInvalidValue;
   if (hn == nullptr && a3 == nullptr) return cudaErrorInvalidValue;
-  const size_t smem = sizeof(float) * ((size_t)(CI + C) * (T + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C);
+  const size_t smem = sizeof(float) * ((size_t)(CI + C) * (T + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C + (size_t)CI * C);
+  if ((wsc == nullptr) != (sc_out == nullptr) || (reinterpret_cast<uintptr_t>(sc_out) & 15) != 0) return cudaErrorInvalidValue;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorInvalidValue;
   const int rpc = N >= 8192 ? 8 : 1;                   // rows per CTA: amortises the weight staging on big launches
@@ -235,7 +268,7 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
   case CC: {                                                                                                         \
     cudaError_t e = cudaFuncSetAttribute(stg_tcn_ln_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                  \
-    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn, (__half*)a3); \
+    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn, (__half*)a3, wsc, sc_out); \
     break;                                                                                                           \
   }
   switch (C) {
