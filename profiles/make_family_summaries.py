@@ -19,7 +19,7 @@ import sys
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 OWN = ("stg_tcn_ln_kernel", "stg_gated_aggregate_kernel", "stg_posterior_kernel", "gauss_fill_kernel",
        "dts_fourier_topk_fwd_kernel", "dts_fourier_topk_bwd_kernel", "dts_ddim_step_kernel", "dts_adagrad_kernel",
-       "dts_infill_kernel", "dts_attn_fwd_kernel", "dts_attn_bwd_kernel")
+       "dts_infill_kernel", "dts_attn_fwd_kernel", "dts_attn_bwd_kernel", "fx_split_kernel")
 lines = [l for l in open("gpurun_out/%s_families_launches.csv" % tag) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 # split the launch list at the first DiffusionTS-only kernel: everything before belongs to DiffSTG

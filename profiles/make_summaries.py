@@ -17,7 +17,7 @@ import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 OWN = ("sampler_tc_kernel", "sampler_simt_kernel", "welford_over_samples", "window_means", "sigma_estimation_kernel",
-       "fx_attention_kernel", "fx_add_ln_split_kernel", "fx_split_kernel")
+       "fx_attention_kernel", "fx_add_ln_split_kernel", "fx_split_kernel", "fx_embed_split_kernel")
 
 # ---- launch list -> shares ----
 lines = [l for l in open("gpurun_out/launches.csv") if not l.startswith("==")]
@@ -33,7 +33,7 @@ for row in csv.DictReader(lines):
 with open("profiles/%s_bench_launches_summary.txt" % tag, "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 9000   python bench.py --steps 1 --warmup 1\n")
     f.write("# (UPD_BENCH_SKIP_CPU=1: the CPU baseline leg is skipped under the profiler).  Per-launch times are\n")
-    f.write("# cold-cache and serialised: compare SHARES.  The command runs 2 resident sweeps + 2 end-to-end sweeps.\n")
+    f.write("# cold-cache and serialised: compare SHARES.  The command runs 2 resident sweeps + 2 end-to-end sweeps\n# + the one sweep of the wall-time measurement (5 sampler launches).\n")
     f.write("# total GPU time %.1f ms over %d launches\n" % (tot / 1e6, sum(a[0] for a in agg.values())))
     f.write("%12s %8s %7s  %s\n" % ("time_ms", "share", "n", "kernel"))
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
