@@ -208,6 +208,16 @@ int upd_dts_fourier_topk(const float* spec_dev, long long spec_row_stride, long 
 int upd_dts_fourier_topk_bwd(const float* gseason_dev, const int* idx_dev, long long gspec_row_stride, long long rows,
                              int NF, int low, int seq, int D, int top_k, float* gspec_dev, void* stream);
 
+/* upd_dts_layernorm / _bwd -- replaces AdaLayerNorm (diffusionts_model_utils.py:187-202) and the blocks' nn.LayerNorm
+ *   (diffusionts_transformer.py:215, 287) forward and input-gradient backward: y = LayerNorm(x) * gamma + beta over the
+ *   last axis (eps 1e-5); gamma_dev / beta_dev [D] (AdaLN: 1 + scale[t] and shift[t], the step is shared by all rows).
+ *   stats_dev [rows, 2] = (mean, rstd), written by the forward (may be NULL) and read by the backward, which returns
+ *   dx only (the weights are constants during sampling).  D in {32,64,96,128,192,256,384,512,1024}. */
+int upd_dts_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, long long rows, int D,
+                      float* y_dev, float* stats_dev, void* stream);
+int upd_dts_layernorm_bwd(const float* x_dev, const float* dy_dev, const float* gamma_dev, const float* stats_dev,
+                          long long rows, int D, float* dx_dev, void* stream);
+
 /* upd_dts_attention / _bwd -- replaces FullAttention / CrossAttention (diffusionts_transformer.py:126-203; head size 16)
  *   and their autograd backward (the refinement gradient of langevin_fn, DiffusionTS.py:384-399):
  *   o = softmax(scale * q k^T) v per (row r, head h), heads merged in o_dev [R*Lq, H*16].  q_dev: position (r*Lq + i) at

@@ -164,3 +164,17 @@ def test_fused_attention_forward_backward_against_autograd(Lq, S, cross):
     refs = torch.autograd.grad((ref * w.double()).sum(), [qb] if not cross else [qb, kvb])
     for g, r in zip(grads, refs):
         assert _rel(g, r) < 2e-5, _rel(g, r)
+
+
+def test_fused_layernorm_forward_backward():
+    from updgm_b200.diffusionts import FusedLayerNorm
+    torch.manual_seed(4)
+    x = torch.randn(3, 50, 64, device=DEV, requires_grad=True)
+    gam, bet = torch.rand(64, device=DEV) + 0.5, torch.randn(64, device=DEV)
+    y = FusedLayerNorm.apply(x, gam, bet)
+    ref = torch.nn.functional.layer_norm(x.double(), (64,), gam.double(), bet.double())
+    assert _rel(y.detach(), ref.detach()) < 1e-5
+    w = torch.randn_like(y)
+    (g,) = torch.autograd.grad((y * w).sum(), x)
+    (gr,) = torch.autograd.grad((ref * w.double()).sum(), x)
+    assert _rel(g, gr) < 1e-5

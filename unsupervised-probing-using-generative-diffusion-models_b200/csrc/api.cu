@@ -54,6 +54,10 @@ cudaError_t upd_launch_dts_attention_bwd(const float* q, long long q_stride, con
                                          float* dv, long long dkv_stride, cudaStream_t stream);
 cudaError_t upd_launch_fx_embed_split(const float* x, const float* w, const float* pe, long long rows, int L, int NF, int K,
                                       float* y, void* a3, cudaStream_t stream);
+cudaError_t upd_launch_dts_layernorm(const float* x, const float* gamma, const float* beta, long long rows, int D, float* y,
+                                     float* stats, cudaStream_t stream);
+cudaError_t upd_launch_dts_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* stats,
+                                         long long rows, int D, float* dx, cudaStream_t stream);
 
 namespace {
 
@@ -426,6 +430,20 @@ int upd_fx_embed_split(const float* x_dev, const float* w_dev, const float* pe_d
   if (!x_dev || !w_dev || !pe_dev || !y_dev || !a3_dev || rows <= 0) return UPD_ERR_BAD_ARG;
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_fx_embed_split(x_dev, w_dev, pe_dev, rows, L, NF, K, y_dev, a3_dev, (cudaStream_t)stream));
+}
+
+int upd_dts_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, long long rows, int D,
+                      float* y_dev, float* stats_dev, void* stream) {
+  if (!x_dev || !gamma_dev || !beta_dev || !y_dev || rows <= 0) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_layernorm(x_dev, gamma_dev, beta_dev, rows, D, y_dev, stats_dev, (cudaStream_t)stream));
+}
+
+int upd_dts_layernorm_bwd(const float* x_dev, const float* dy_dev, const float* gamma_dev, const float* stats_dev,
+                          long long rows, int D, float* dx_dev, void* stream) {
+  if (!x_dev || !dy_dev || !gamma_dev || !stats_dev || !dx_dev || rows <= 0) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_layernorm_bwd(x_dev, dy_dev, gamma_dev, stats_dev, rows, D, dx_dev, (cudaStream_t)stream));
 }
 
 }  // extern "C"

@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import _lib, kernels
+from .fx_encoder import _W3Cache, a3_split, gemm3
 
 P = "model."            # Transformer lives at Diffusion_TS.model (DiffusionTS.py:69)
 ROWS_PER_LAUNCH = 2048
@@ -214,6 +215,54 @@ class FusedAttention(torch.autograd.Function):
         return dqbuf, (None if same else dkvbuf), None, None, None, None, None
 
 
+class FusedLayerNorm(torch.autograd.Function):
+    """y = LayerNorm(x) * gamma + beta over the last axis (upd_dts_layernorm / _bwd); gamma, beta: constant [d] vectors."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta):
+        x = x.contiguous()
+        d = x.shape[-1]
+        rows = x.numel() // d
+        y = torch.empty_like(x)
+        need = ctx.needs_input_grad[0]
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if need else None
+        rc = _lib.lib().upd_dts_layernorm(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), rows, d, _lib.ptr(y), _lib.ptr(stats),
+                                          _lib.stream_ptr(x.device))
+        _lib.check(rc, "upd_dts_layernorm")
+        if need:
+            ctx.save_for_backward(x, gamma, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, stats = ctx.saved_tensors
+        g = g.contiguous()
+        d = x.shape[-1]
+        dx = torch.empty_like(x)
+        rc = _lib.lib().upd_dts_layernorm_bwd(_lib.ptr(x), _lib.ptr(g), _lib.ptr(gamma), _lib.ptr(stats), x.numel() // d, d,
+                                              _lib.ptr(dx), _lib.stream_ptr(x.device))
+        _lib.check(rc, "upd_dts_layernorm_bwd")
+        return dx, None, None
+
+
+class ConstLinear(torch.autograd.Function):
+    """y = x W^T + b with constant weights.  Forward: ONE error-compensated fp16 tensor-core GEMM (fx_encoder.gemm3 on the
+    split operand [x_hi | x_lo | x_hi | 1 1 0..], 3e-6 accuracy; the activations are O(1)).  Backward: dx = dy W as a plain
+    fp32 GEMM -- the refinement gradients are ~1e-6 and smaller, inside fp16's subnormal range, and are not split."""
+
+    @staticmethod
+    def forward(ctx, x, w3, w, n_out):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        y = gemm3(a3_split(x2), w3, n_out)
+        ctx.w, ctx.shp = w, shp
+        return y.reshape(*shp[:-1], n_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.reshape(-1, g.shape[-1]) @ ctx.w).reshape(ctx.shp), None, None, None
+
+
 def _sinusoidal(t, dim):
     half = dim // 2
     e = math.log(10000) / (half - 1)
@@ -247,7 +296,8 @@ class PreparedTransformer:
         emb_t = F.silu(_sinusoidal(torch.arange(T, device=dev), d))          # AdaLayerNorm input for every step
 
         def ada(pre):
-            return F.linear(emb_t, sd[pre + "linear.weight"], sd[pre + "linear.bias"])      # [T, 2d] = (scale | shift)
+            mod = F.linear(emb_t, sd[pre + "linear.weight"], sd[pre + "linear.bias"])       # [T, 2d] = (scale | shift)
+            return (1.0 + mod[:, :d]).contiguous(), mod[:, d:].contiguous()                 # LayerNorm gain / bias per step
 
         def conv3_cols(w):      # Conv1d weight [out, in, 3] -> per-tap matrices [3, in, out]
             return w.permute(2, 1, 0).contiguous()
@@ -269,15 +319,20 @@ class PreparedTransformer:
         self.poly = torch.stack([lin ** float(p + 1) for p in range(3)], dim=0).to(dev)   # [3, seq]
         self.enc, self.dec = [], []
 
+        def lin(w, b):
+            """(split-operand weights, fp32 weights for the backward, n_out) of a constant dense layer (ConstLinear)."""
+            w, b = w.contiguous(), b.contiguous()
+            return (_W3Cache().get([(w, b)]), w, w.shape[0])
+
         def attn_self(pre):
-            return dict(wqkv=torch.cat([sd[pre + "query.weight"], sd[pre + "key.weight"], sd[pre + "value.weight"]], 0),
-                        bqkv=torch.cat([sd[pre + "query.bias"], sd[pre + "key.bias"], sd[pre + "value.bias"]], 0),
-                        wo=sd[pre + "proj.weight"], bo=sd[pre + "proj.bias"])
+            return dict(qkv=lin(torch.cat([sd[pre + "query.weight"], sd[pre + "key.weight"], sd[pre + "value.weight"]], 0),
+                                torch.cat([sd[pre + "query.bias"], sd[pre + "key.bias"], sd[pre + "value.bias"]], 0)),
+                        o=lin(sd[pre + "proj.weight"], sd[pre + "proj.bias"]))
 
         def common(pre):
-            return dict(ada1=ada(pre + "ln1."), ln2_w=sd[pre + "ln2.weight"], ln2_b=sd[pre + "ln2.bias"],
-                        w1=sd[pre + "mlp.0.weight"], b1=sd[pre + "mlp.0.bias"], w2=sd[pre + "mlp.2.weight"],
-                        b2=sd[pre + "mlp.2.bias"])
+            return dict(ada1=ada(pre + "ln1."), ln2_w=sd[pre + "ln2.weight"].contiguous(), ln2_b=sd[pre + "ln2.bias"].contiguous(),
+                        fc1=lin(sd[pre + "mlp.0.weight"], sd[pre + "mlp.0.bias"]),
+                        fc2=lin(sd[pre + "mlp.2.weight"], sd[pre + "mlp.2.bias"]))
 
         for i in range(self.n_enc):
             pre = "encoder.blocks.%d." % i
@@ -289,10 +344,10 @@ class PreparedTransformer:
             blk = common(pre)
             blk["attn1"] = attn_self(pre + "attn1.")
             a2 = pre + "attn2."
-            blk["attn2"] = dict(wq=sd[a2 + "query.weight"], bq=sd[a2 + "query.bias"],
-                                wkv=torch.cat([sd[a2 + "key.weight"], sd[a2 + "value.weight"]], 0),
-                                bkv=torch.cat([sd[a2 + "key.bias"], sd[a2 + "value.bias"]], 0),
-                                wo=sd[a2 + "proj.weight"], bo=sd[a2 + "proj.bias"])
+            blk["attn2"] = dict(q=lin(sd[a2 + "query.weight"], sd[a2 + "query.bias"]),
+                                kv=lin(torch.cat([sd[a2 + "key.weight"], sd[a2 + "value.weight"]], 0),
+                                       torch.cat([sd[a2 + "key.bias"], sd[a2 + "value.bias"]], 0)),
+                                o=lin(sd[a2 + "proj.weight"], sd[a2 + "proj.bias"]))
             blk["ada1_1"] = ada(pre + "ln1_1.")
             # fold proj (Conv1d seq -> 2*seq, k=1) with the rfft of its seasonal half and the first trend conv
             wp = sd[pre + "proj.weight"][:, :, 0].double()
@@ -311,9 +366,7 @@ class PreparedTransformer:
 
     # ---- blocks ----
     def _ada_ln(self, x, tab, t):
-        d = self.d
-        mod = tab[t]
-        return F.layer_norm(x, (d,)) * (1 + mod[:d]) + mod[d:]
+        return FusedLayerNorm.apply(x, tab[0][t], tab[1][t])
 
     def _heads(self, x):
         R, c, _ = x.shape
@@ -326,25 +379,25 @@ class PreparedTransformer:
         return (att @ v).transpose(1, 2).reshape(q.shape[0], q.shape[2], self.d)
 
     def _self_attn(self, a, w):
-        qkv = F.linear(a, w["wqkv"], w["bqkv"])                                   # [R, c, 3d] = (q | k | v)
+        qkv = ConstLinear.apply(a, *w["qkv"])                                     # [R, c, 3d] = (q | k | v)
         if self.d // self.nh == 16:
             y = FusedAttention.apply(qkv, qkv, 0, self.d, 2 * self.d, self.nh, self.d)
         else:
             y = self._attend(*qkv.split(self.d, dim=-1))
-        return F.linear(y, w["wo"], w["bo"])
+        return ConstLinear.apply(y, *w["o"])
 
     def _cross_attn(self, a, enc, w):
-        q = F.linear(a, w["wq"], w["bq"])
-        kv = F.linear(enc, w["wkv"], w["bkv"])                                    # [R, c_enc, 2d] = (k | v)
+        q = ConstLinear.apply(a, *w["q"])
+        kv = ConstLinear.apply(enc, *w["kv"])                                     # [R, c_enc, 2d] = (k | v)
         if self.d // self.nh == 16:
             y = FusedAttention.apply(q, kv, 0, 0, self.d, self.nh, self.d)
         else:
             y = self._attend(q, *kv.split(self.d, dim=-1))
-        return F.linear(y, w["wo"], w["bo"])
+        return ConstLinear.apply(y, *w["o"])
 
     def _mlp(self, x, w):
-        h = F.layer_norm(x, (self.d,), w["ln2_w"], w["ln2_b"])
-        return F.linear(F.gelu(F.linear(h, w["w1"], w["b1"])), w["w2"], w["b2"])
+        h = FusedLayerNorm.apply(x, w["ln2_w"], w["ln2_b"])
+        return ConstLinear.apply(F.gelu(ConstLinear.apply(h, *w["fc1"])), *w["fc2"])
 
     @staticmethod
     def _conv3(x, w, b):
