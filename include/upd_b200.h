@@ -280,10 +280,17 @@ int upd_fx_split(const float* x_dev, long long rows, int K, int H, int L, int ac
 
 /* upd_fx_add_ln_split -- y = LayerNorm_2(LayerNorm_1(x + res)) (eps 1e-5; res, the second norm, y_dev or a3_dev may be
  *   NULL): the `norm(x + sublayer(x))` of every encoder/decoder layer, with the stack's final norm folded into the
- *   last one; writes y [rows,K] fp32 and A3(y).  K multiple of 128, K <= 1024. */
+ *   last one; writes y [rows,K] fp32 and A3(y).  K in {32, 64, 96} or a multiple of 128, K <= 1024. */
 int upd_fx_add_ln_split(const float* x_dev, const float* res_dev, const float* g1_dev, const float* b1_dev,
                         const float* g2_dev, const float* b2_dev, long long rows, int K, float* y_dev, void* a3_dev,
                         void* stream);
+
+/* upd_fx_attention_hs16 -- the same de-stationary attention for head size 16 (TMDM's condition encoder: d_model 64, 4
+ *   heads; tmdm_ns_transformer.py:53-91): fp32 FFMA kernel shared with DiffusionTS (dts_attention.cu), output o_dev
+ *   [B*Lq, H*16] fp32 with the heads merged.  Same addressing, tau / delta / causal conventions as upd_fx_attention. */
+int upd_fx_attention_hs16(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                          long long kv_row_stride, const float* tau_dev, const float* delta_dev, int delta_pitch, int B, int H,
+                          int Lq, int S, int causal, float scale, float* o_dev, void* stream);
 
 /* upd_fx_embed_split -- DataEmbedding (circular token Conv1d(k=3, no bias) + positional table; torch-timeseries block used
  *   at mu_backbone.py:66-69): x_dev [rows/L, L, NF], w_dev [K, NF, 3], pe_dev [>= L, K] -> y_dev [rows, K] fp32 and its

@@ -345,7 +345,7 @@ def test_fx_split_operand(K, act):
     assert float((val - o.transpose(1, 2).reshape(B * L, K)).abs().max()) < 2e-6 * float(o.abs().max())
 
 
-@pytest.mark.parametrize("K", [128, 512])
+@pytest.mark.parametrize("K", [64, 128, 512])
 def test_fx_add_layernorm_split(K):
     from updgm_b200 import fx_encoder
     torch.manual_seed(K)
@@ -439,3 +439,39 @@ def test_three_tile_kernels_full_bench_shape_against_two_tile(impl):
     rms = float(a.pow(2).mean().sqrt())
     assert torch.isfinite(b).all()
     assert float((a - b).abs().max()) / rms < 2e-5
+
+
+@pytest.mark.parametrize("Lq,S,causal,use_delta", [(100, 100, False, True), (150, 150, True, False), (150, 100, False, True)])
+def test_fx_attention_head_size_16_against_fp64(Lq, S, causal, use_delta):
+    """upd_fx_attention_hs16 (TMDM's condition encoder: 4 heads of 16) == softmax(scale*(tau*QK^T + delta)) V in float64."""
+    import ctypes
+    import math
+    from updgm_b200 import _lib
+    torch.manual_seed(Lq + 7 * S)
+    dev = _dev()
+    B, H, dk = 5, 4, 16
+    d = H * dk
+    qkv = torch.randn(B * max(Lq, S), 3 * d, device=dev)
+    tau = torch.rand(B, device=dev) * 1.5 + 0.5
+    scale = 1.0 / math.sqrt(dk)
+    pitch = (S + 15) // 16 * 16
+    dbuf = torch.zeros(B, pitch, device=dev)
+    delta = torch.randn(B, S, device=dev)
+    dbuf[:, :S] = delta * scale
+    o = torch.empty(B * Lq, d, device=dev)
+    rc = _lib.lib().upd_fx_attention_hs16(
+        _lib.ptr(qkv), 3 * d, ctypes.c_void_p(qkv.data_ptr() + 4 * d), ctypes.c_void_p(qkv.data_ptr() + 8 * d), 3 * d,
+        _lib.ptr(tau), ctypes.c_void_p(dbuf.data_ptr()) if use_delta else None, pitch, B, H, Lq, S, int(causal), scale,
+        _lib.ptr(o), _lib.stream_ptr(dev))
+    _lib.check(rc, "upd_fx_attention_hs16")
+    q = qkv[: B * Lq, :d].double().view(B, Lq, H, dk).transpose(1, 2)
+    k = qkv[: B * S, d:2 * d].double().view(B, S, H, dk).transpose(1, 2)
+    v = qkv[: B * S, 2 * d:].double().view(B, S, H, dk).transpose(1, 2)
+    sc = (q @ k.transpose(-1, -2)) * tau.double().view(B, 1, 1, 1)
+    if use_delta:
+        sc = sc + delta.double().view(B, 1, 1, S)
+    sc = sc * scale
+    if causal:
+        sc = sc.masked_fill(torch.ones(Lq, S, dtype=torch.bool, device=dev).triu(1), float("-inf"))
+    ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * Lq, d)
+    assert float((o.double() - ref).abs().max() / ref.abs().max()) < 2e-5

@@ -47,7 +47,8 @@ cudaError_t upd_launch_fx_attention(const float* q, long long q_stride, const fl
                                     const float* tau, const float* delta, int delta_pitch, int B, int H, int Lq, int S,
                                     int causal, float scale, void* a3, cudaStream_t stream);
 cudaError_t upd_launch_dts_attention(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
-                                     int R, int H, int Lq, int S, float scale, float* o, float* lse, cudaStream_t stream);
+                                     int R, int H, int Lq, int S, float scale, float* o, float* lse, const float* tau,
+                                     const float* delta, int delta_pitch, int causal, cudaStream_t stream);
 cudaError_t upd_launch_dts_attention_bwd(const float* q, long long q_stride, const float* k, const float* v,
                                          long long kv_stride, int R, int H, int Lq, int S, float scale, const float* o,
                                          const float* lse, const float* d_o, float* dq, long long dq_stride, float* dk,
@@ -408,7 +409,17 @@ int upd_dts_attention(const float* q_dev, long long q_row_stride, const float* k
   if (head_dim != 16 || (long long)R * H > 0x7fffffffLL) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_dts_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev, lse_dev,
-                                      (cudaStream_t)stream));
+                                      nullptr, nullptr, 0, 0, (cudaStream_t)stream));
+}
+
+int upd_fx_attention_hs16(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
+                          long long kv_row_stride, const float* tau_dev, const float* delta_dev, int delta_pitch, int B, int H,
+                          int Lq, int S, int causal, float scale, float* o_dev, void* stream) {
+  if (!q_dev || !k_dev || !v_dev || !o_dev || B <= 0 || H <= 0 || Lq <= 0 || S <= 0) return UPD_ERR_BAD_ARG;
+  if (delta_dev && delta_pitch < S) return UPD_ERR_BAD_ARG;
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_dts_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, B, H, Lq, S, scale, o_dev, nullptr,
+                                      tau_dev, delta_dev, delta_pitch, causal, (cudaStream_t)stream));
 }
 
 int upd_dts_attention_bwd(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,

@@ -27,6 +27,10 @@ struct DtsAttnParams {
   const float* d_o;                         // [R*Lq, H*16]
   float* dq; long long dq_stride;           // same addressing as q
   float* dk; float* dv; long long dkv_stride;
+  // forward only, de-stationary attention of the TMDM / NsDiff condition encoder at head size 16:
+  const float* tau;                         // [R] or null: scores *= tau[r]
+  const float* delta; int delta_pitch;      // [R, pitch] ALREADY multiplied by scale, or null: added to the scaled scores
+  int causal;                               // keys j > i masked
 };
 
 __device__ __forceinline__ float ex2f(float x) {
@@ -77,15 +81,18 @@ __global__ void dts_attn_fwd_kernel(const DtsAttnParams p) {
   stage_rows(p.k + (long long)r * p.S * p.kv_stride + h * HS, p.kv_stride, p.S, sk);
   stage_rows(p.v + (long long)r * p.S * p.kv_stride + h * HS, p.kv_stride, p.S, sv);
   __syncthreads();
-  const float qs = p.scale * LOG2E;
+  const float qs = p.scale * LOG2E * (p.tau ? p.tau[r] : 1.0f);
+  const float* dl = p.delta ? p.delta + (long long)r * p.delta_pitch : nullptr;
   for (int i = threadIdx.x; i < p.Lq; i += blockDim.x) {
     float q[HS], o[HS];
     load16(p.q + ((long long)r * p.Lq + i) * p.q_stride + h * HS, q);
 #pragma unroll
     for (int c = 0; c < HS; ++c) { q[c] *= qs; o[c] = 0.f; }
     float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < p.S; ++j) {
-      const float s = dot16(q, sk + j * HS);
+    const int s_end = p.causal ? min(p.S, i + 1) : p.S;
+    for (int j = 0; j < s_end; ++j) {
+      float s = dot16(q, sk + j * HS);
+      if (dl) s = fmaf(dl[j], LOG2E, s);
       if (s > m) {                           // rare after the first few keys
         const float f = ex2f(m - s);
         l *= f;
@@ -177,14 +184,15 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 }  // namespace
 
 cudaError_t upd_launch_dts_attention(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
-                                     int R, int H, int Lq, int S, float scale, float* o, float* lse, cudaStream_t stream) {
+                                     int R, int H, int Lq, int S, float scale, float* o, float* lse, const float* tau,
+                                     const float* delta, int delta_pitch, int causal, cudaStream_t stream) {
   if ((q_stride & 3) || (kv_stride & 3) || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o))
     return cudaErrorInvalidValue;
   const size_t smem = sizeof(float) * 2 * (size_t)S * HS;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   DtsAttnParams p = {};
   p.q = q; p.q_stride = q_stride; p.k = k; p.v = v; p.kv_stride = kv_stride; p.R = R; p.H = H; p.Lq = Lq; p.S = S;
-  p.scale = scale; p.o = o; p.lse = lse;
+  p.scale = scale; p.o = o; p.lse = lse; p.tau = tau; p.delta = delta; p.delta_pitch = delta_pitch; p.causal = causal;
   cudaError_t e = cudaFuncSetAttribute(dts_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int threads = Lq >= 256 ? 256 : ((Lq + 31) / 32) * 32;

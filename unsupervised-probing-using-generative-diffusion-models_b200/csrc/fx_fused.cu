@@ -125,6 +125,57 @@ __global__ void fx_add_ln_split_kernel(const float* __restrict__ x, const float*
   }
 }
 
+// Narrow rows (K = 32 * NS, e.g. TMDM's d_model = 64): the same residual + LayerNorm (+ final norm) -> fp32 and split
+// operand, one warp per row with NS scalars per lane.
+template <int NS>
+__global__ void fx_add_ln_split_small_kernel(const float* __restrict__ x, const float* __restrict__ res,
+                                             const float* __restrict__ g1, const float* __restrict__ b1,
+                                             const float* __restrict__ g2, const float* __restrict__ b2, long long rows,
+                                             float* __restrict__ y, __half* __restrict__ a3) {
+  constexpr int K = NS * 32;
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float v[NS];
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    v[i] = x[r * K + lane + 32 * i];
+    if (res) v[i] += res[r * K + lane + 32 * i];
+  }
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    const float* g = pass == 0 ? g1 : g2;
+    const float* bb = pass == 0 ? b1 : b2;
+    if (!g) break;
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s += v[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / K);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) { const float d = v[i] - mean; q += d * d; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / K) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) v[i] = (v[i] - mean) * rstd * g[lane + 32 * i] + bb[lane + 32 * i];
+  }
+#pragma unroll
+  for (int i = 0; i < NS; ++i) {
+    const int c = lane + 32 * i;
+    if (y) y[r * K + c] = v[i];
+    if (a3) {
+      __half* out = a3 + r * (3 * K + 8);
+      const __half h = __float2half_rn(v[i]);
+      const __half l = __float2half_rn(v[i] - __half2float(h));
+      out[c] = h; out[K + c] = l; out[2 * K + c] = h;
+    }
+  }
+  if (a3 && lane == 0) fx_store_tail(a3 + r * (3 * K + 8), K);
+}
+
 // DataEmbedding of the condition encoder: circular Conv1d(c_in -> d, k=3, no bias) over the sequence + sinusoidal
 // positional table, written as fp32 AND as the split operand of the first projection GEMM in one pass
 // (TokenEmbedding / PositionalEmbedding of torch-timeseries as used at mu_backbone.py:66-69; three einsum + roll + add
@@ -171,9 +222,15 @@ cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, in
 cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const float* g1, const float* b1,
                                        const float* g2, const float* b2, long long rows, int K, float* y, void* a3,
                                        cudaStream_t stream) {
-  if (K < 128 || K > FX_MAX_K || (K % 128)) return cudaErrorInvalidValue;
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  if (K == 32 || K == 64 || K == 96) {
+    if (K == 32) fx_add_ln_split_small_kernel<1><<<grid, wpb * 32, 0, stream>>>(x, res, g1, b1, g2, b2, rows, y, (__half*)a3);
+    else if (K == 64) fx_add_ln_split_small_kernel<2><<<grid, wpb * 32, 0, stream>>>(x, res, g1, b1, g2, b2, rows, y, (__half*)a3);
+    else fx_add_ln_split_small_kernel<3><<<grid, wpb * 32, 0, stream>>>(x, res, g1, b1, g2, b2, rows, y, (__half*)a3);
+    return cudaGetLastError();
+  }
+  if (K < 128 || K > FX_MAX_K || (K % 128)) return cudaErrorInvalidValue;
 #define UPD_LN_CASE(NV)                                                                                    \
   case NV:                                                                                                 \
     fx_add_ln_split_kernel<NV><<<grid, wpb * 32, 0, stream>>>(x, res, g1, b1, g2, b2, rows, y, (__half*)a3); \

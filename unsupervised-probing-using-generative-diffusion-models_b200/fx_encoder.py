@@ -18,7 +18,8 @@ tensor-core GEMM with fp32 accumulation on an error-compensated operand, [x_hi |
 C ABI (csrc/fx_fused.cu): ``upd_fx_split`` (operand split fused with the activation or with the attention output's head
 merge) and ``upd_fx_add_ln_split`` (residual + LayerNorm (+ the stack's final norm) -> fp32 + split operand).
 The GEMMs themselves and the de-stationary attention are library calls (cuBLAS, fp32 memory-efficient SDPA).
-Other widths (TMDM's d_model = 64) and CPU tensors take the module-by-module path below (TF32x3 / plain fp32).
+Head size 16 (TMDM's d_model = 64) uses the fp32 FFMA attention kernel shared with DiffusionTS (upd_fx_attention_hs16);
+other widths and CPU tensors take the module-by-module path below (TF32x3 / plain fp32).
 """
 import ctypes
 import math
@@ -314,6 +315,17 @@ class AttentionLayer(nn.Module):
                 B, H, Lq, S, dk, 1 if self.causal else 0, scale, _lib.ptr(a3_o), _lib.stream_ptr(q_buf.device))
             _lib.check(rc, "upd_fx_attention")
             return gemm3(a3_o, self.out_projection.w3(), d)
+        if dk == 16 and not (self.causal and (delta is not None or Lq != S)):
+            # head size 16 (TMDM's condition encoder): fp32 FFMA attention kernel shared with DiffusionTS
+            o = torch.empty((B * Lq, d), dtype=torch.float32, device=q_buf.device)
+            base = kv_buf.data_ptr()
+            rc = _lib.lib().upd_fx_attention_hs16(
+                _lib.ptr(q_buf), q_stride, ctypes.c_void_p(base + 4 * k_off), ctypes.c_void_p(base + 4 * v_off), kv_stride,
+                None if tau is None else _lib.ptr(tau.reshape(-1).contiguous()),
+                None if delta is None else ctypes.c_void_p(delta.data_ptr()), 0 if delta is None else delta.stride(0),
+                B, H, Lq, S, 1 if self.causal else 0, scale, _lib.ptr(o), _lib.stream_ptr(q_buf.device))
+            _lib.check(rc, "upd_fx_attention_hs16")
+            return gemm3(a3_split(o), self.out_projection.w3(), d)
         # other head sizes / longer sequences: library attention on strided views of the projection buffers
         q = q_buf.view(B, Lq, -1)[:, :, :d].reshape(B, Lq, H, dk).transpose(1, 2) if a3_kv is not None else \
             q_buf.view(B, Lq, 3, H, dk)[:, :, 0].transpose(1, 2)
@@ -446,8 +458,8 @@ class NsTransformer(nn.Module):
             def mlp():
                 return nn.Sequential(nn.Linear(d, d), nn.ReLU(), nn.Linear(d, d))
             self.z_mean, self.z_logvar, self.z_out = mlp(), mlp(), mlp()
-        # limits of the fused kernels (csrc/fx_fused.cu): LayerNorm width a multiple of 128, 16-byte aligned heads
-        self.fused_ok = (d % 128 == 0 and d <= 1024 and configs.d_ff % 4 == 0 and configs.d_ff <= 1024
+        # limits of the fused kernels (csrc/fx_fused.cu): LayerNorm width 32/64/96 or a multiple of 128, 16-byte aligned heads
+        self.fused_ok = ((d % 128 == 0 or d in (32, 64, 96)) and d <= 1024 and configs.d_ff % 4 == 0 and configs.d_ff <= 1024
                          and (d // configs.n_heads) % 4 == 0 and len(self.encoder.attn_layers) > 0
                          and len(self.decoder.layers) > 0)
 
