@@ -12,7 +12,7 @@ G = os.path.join("tests", "golden")
 def timed(fn, n=2):
     fn(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(n): r = fn()
+    for _ in range(n): r = fn()   # the previous result is still alive: every call pins a fresh cache
     torch.cuda.synchronize()
     return (time.perf_counter() - t0) / n, r
 
