@@ -11,7 +11,6 @@ import json
 import os
 import sys
 
-import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import _lib, kernels
+from . import _lib
 from .fx_encoder import _W3Cache, a3_split, gemm3
 
 P = "model."            # Transformer lives at Diffusion_TS.model (DiffusionTS.py:69)
