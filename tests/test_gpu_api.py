@@ -230,3 +230,35 @@ def test_state_dict_roundtrip_and_repack(model8):
     m.load_state_dict(sd, strict=True)
     c, _ = m.evaluation_step(g["window_scaled"].cuda(), noise=g["noise"])
     assert torch.equal(a, c)
+
+
+def test_real_data_gx_uncertainty_batched(tmp_path):
+    """SURVEY 8f row 3 (real_data_analysis.run_model_uncertainty): all windows' g(x) in one launch == the per-window oracle."""
+    from updgm_b200.nsdiff import NsDiff_model_variants
+    U = _U()
+    net_param, _ = load_wo_fx_checkpoint()
+    net = dict(net_param, device=torch.device("cuda:0"), dataset_nf=1, windows=100, seq_len=100, pred_len=100,
+               rolling_length=50, scaler_type="StandardScaler")
+    torch.manual_seed(77)
+    m = NsDiff_model_variants(net, "cond_var").eval()
+    m.scaler_mean.fill_(0.4)
+    m.scaler_std.fill_(1.7)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(21)
+    series = (torch.randn(3, 3000, 1, generator=g) * 0.1).cumsum(dim=1) * 1.7 + 0.4
+    tdata = torch.arange(3000) * 0.1
+    times, values = U.real_data_gx_uncertainty(m, series, tdata, windows=100, sampling_t=1.0, sample_window_step=20,
+                                               pred_dim=2, cache_path=tmp_path / "gx.pt")
+    sub = series[:, ::10, :]
+    W = (300 - 100) // 20 + 1
+    assert len(values) == W and len(times) == W and float(times[0]) == pytest.approx(float(tdata[::10][99]))
+    cached = U._load_tensor_list(tmp_path / "gx.pt")
+    assert len(cached) == W and tuple(cached[0].shape) == (3, 100)
+    for w in (0, W - 1):
+        x = (sub[:, 20 * w: 20 * w + 100, :] - 0.4) / 1.7
+        ref = sigma_oracle.sigma_estimation(sd, x, 50, 100).squeeze(-1)          # [Node, O]
+        _close(cached[w], ref, tol=2e-5)
+        assert values[w] == pytest.approx(float(ref.mean(dim=-1)[2]), rel=1e-4)
+    m2, _ = U.load_model_from_dir(CKPT_DIR, device=torch.device("cuda:0"))         # F = 2: not a scalar per window
+    with pytest.raises(TypeError):
+        U.real_data_gx_uncertainty(m2, torch.zeros(1, 4000, 2), torch.arange(4000) * 0.1, 200, 1.0, 50, 0, tmp_path / "x.pt")

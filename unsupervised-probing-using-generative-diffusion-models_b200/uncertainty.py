@@ -609,6 +609,38 @@ def run_slbp_gx_cache_for_fig6(model, input_datas, cache_path, device, pred_dim=
     return gx_list
 
 
+def real_data_gx_uncertainty(model, torch_model_time_series, time_data, windows, sampling_t, sample_window_step,
+                             pred_dim, cache_path, device=None):
+    """The model part of ``run_model_uncertainty`` (evaluation_and_analysis/real_data_analysis.py:331-348; SURVEY 8f
+    row 3): sub-sample the prepared series [Node, T, F] (torch_data_preprocessing, :200-205), cut rolling windows
+    ``unfold(1, windows, step)``, evaluate g(x) on every window -- here ALL windows in one ``upd_sigma_estimation`` launch
+    instead of a Python loop -- and reduce ``gx.squeeze(-1).mean(-1)[pred_dim]`` per window.  As in that function the
+    scaler is applied only when ``model.scaler == "StandardScaler"`` (:338, unlike run_evaluation_cache).  Writes the
+    cache ``list[Tensor [Node, O]]`` to ``cache_path`` and returns (model_times[:n], values float64 [n])."""
+    device = device or _model_device(model)
+    if not hasattr(model, "cond_pred_model_g") or model.cond_pred_model_g is None:
+        raise ValueError("model does not provide cond_pred_model_g for gx generation.")
+    sampling_interval = int(sampling_t / 0.1) if sampling_t > 0.1 else 1          # :201-202
+    sampled_series = torch.as_tensor(torch_model_time_series)[:, ::sampling_interval, :]
+    sampled_time = torch.as_tensor(time_data)[::sampling_interval].detach().cpu().numpy()
+    stacked = sampled_series.unfold(1, windows, sample_window_step).permute(1, 0, 3, 2).contiguous()   # [W, Node, L, F]
+    model_times = sampled_time[windows - 1:: sample_window_step]
+    W, B = stacked.shape[0], stacked.shape[1]
+    x = stacked.to(device, torch.float32)
+    if getattr(model, "scaler", None) == "StandardScaler":
+        x = model.scaler_transform(x)
+    with torch.no_grad():
+        gx = model.cond_pred_model_g(x.reshape(W * B, x.shape[2], x.shape[3])[:, :model.windows, :].contiguous())
+    gx = gx.view(W, B, gx.shape[1], gx.shape[2]).squeeze(-1)                      # [W, Node, O] for F = 1
+    if gx.dim() != 3:
+        # the reference does float(gx.mean(-1)[pred_dim]) per window, which only works for a single feature
+        raise TypeError("only length-1 arrays can be converted to Python scalars")
+    values = gx.mean(dim=-1)[:, pred_dim].double().cpu().numpy()
+    data_save_list = list(gx.cpu().unbind(0))
+    _save_tensor_list(data_save_list, Path(cache_path))
+    return model_times[: len(values)], np.asarray(values, dtype=float)
+
+
 def load_diffstg_graph(graph_file):
     """:342-351: graphml -> graph object with ``edge_index`` [2,E] int64 and ``num_nodes``.  The reference goes through
     networkx + torch_geometric.utils.from_networkx; the same edge order is produced here without torch_geometric:
