@@ -332,3 +332,16 @@ def test_background_cache_writer_roundtrip(tmp_path, monkeypatch):
     U._save_tensor_list(data, bad)
     with pytest.raises(OSError):
         U.flush_cache_writes()
+
+
+def test_feature_inverse_transform_helper():
+    """:267-283: feature axis is -2 for cache elements [.., O, F, K], -1 otherwise; identity without a model / scaler."""
+    class M:
+        scaler = "StandardScaler"
+        scaler_mean, scaler_std = torch.tensor([1.0, -2.0]), torch.tensor([2.0, 0.5])
+    x = torch.arange(24.).view(3, 2, 4)                       # [O, F, K]
+    y = U._feature_inverse_transform(x, M())
+    assert torch.equal(y[:, 0], x[:, 0] * 2.0 + 1.0) and torch.equal(y[:, 1], x[:, 1] * 0.5 - 2.0)
+    z = torch.arange(6.).view(3, 2)                           # [.., F]
+    assert torch.equal(U._feature_inverse_transform(z, M()), z * M.scaler_std + M.scaler_mean)
+    assert U._feature_inverse_transform(x, None) is x and U._as_path(None) is None and str(U._as_path("a/b")) == "a/b"

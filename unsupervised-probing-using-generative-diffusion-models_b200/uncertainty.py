@@ -35,6 +35,11 @@ def set_project_root(path):
     PROJECT_ROOT = Path(path).resolve()
 
 
+def _as_path(path):
+    """:39-42."""
+    return None if path is None else Path(path)
+
+
 def _resolve_project_path(path):
     if path is None:
         return None
@@ -724,6 +729,27 @@ def _scaler_table(model):
     return torch.stack([model.scaler_mean.detach().float().cpu(), model.scaler_std.detach().float().cpu()]).cuda().contiguous()
 
 
+def _feature_inverse_transform(pred_future, model=None):
+    """:267-283, for callers that post-process a cache element themselves (the summaries above apply the same
+    (mean, std) table inside the reduction kernel): back to raw units along the feature axis, when a model with a
+    scaler is present."""
+    if model is None or getattr(model, "scaler", None) is None:
+        return pred_future
+    if not hasattr(model, "scaler_mean") or not hasattr(model, "scaler_std"):
+        if hasattr(model, "scaler_inverse_transform"):
+            return model.scaler_inverse_transform(pred_future)
+        return pred_future
+    mean = model.scaler_mean.detach().to(pred_future.device, pred_future.dtype)
+    std = model.scaler_std.detach().to(pred_future.device, pred_future.dtype)
+    if pred_future.ndim >= 3 and pred_future.shape[-2] == mean.numel():
+        shape = [1] * pred_future.ndim
+        shape[-2] = mean.numel()
+        return pred_future * std.view(*shape) + mean.view(*shape)
+    if pred_future.shape[-1] == mean.numel():
+        return pred_future * std + mean
+    return pred_future
+
+
 def _np_scalars(t):
     return [np.asarray(v, dtype=np.float32).reshape(()) for v in t.tolist()]
 
@@ -1245,3 +1271,24 @@ def distributed_sweep(model, stacked_windows, device=None, group=None, graph_dat
         local = local.to(device)
     full = gather_window_stats(local, W, group=group).cpu()
     return cache, (w0, w1), {"mpv": full[:, 0], "pred_mean": full[:, 1], "mpv_f": full[:, 2:]}
+
+
+def main():
+    """:1591-1625 without the figure (plotting is outside this package): the reference's default run."""
+    run_config = {
+        "model_save_file": "ews_results/model_compare/NsDiff/SIS",
+        "data_file": "dataset/spdata_sde_SIS/barabasi_albert_30_0/SIS_dynamic_eta0.0001d0.5_increase.pt",
+        "dynamic_type": "SIS", "task_model": None, "graph_file": "dataset/test_graph/barabasi_albert_30_0.graphml",
+        "cache_path": None, "sample_window_step": None, "sampling_t": None, "pred_dim": 0, "force_recompute": False,
+        "uncertainty_method": "gx", "device": None,
+        "infer_params": {"parallel_sampling": 50, "sequential_sampling": 1, "n_z_samples": 100, "diffusion_steps": 20},
+    }
+    result = uncertainty_ews(**run_config)
+    flush_cache_writes()
+    print("cache_path:", result["cache_path"])
+    print("figure_path:", result["figure_path"])
+    print("num_windows:", len(result["ews"]))
+
+
+if __name__ == "__main__":
+    main()
