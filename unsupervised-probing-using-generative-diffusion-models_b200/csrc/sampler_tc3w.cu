@@ -6,7 +6,9 @@
 // of MMA m-1, once that MMA has completed).  24 warps = 768 threads at 80 registers, no MUFU turn-taking: with three tiles
 // free-running there are always softplus epilogues of other tiles to fill the MUFU pipe while one tile waits for its
 // MMAs, and up to six warps per scheduler to hide the dependency chains (the X3 measurements: the more warps share the
-// MUFU pipe, the better).  Arithmetic, operand encodings, weight image: identical to sampler_tc.cu.
+// MUFU pipe, the better).  Arithmetic, operand encodings, weight image: identical to sampler_tc.cu, except that the NsDiff
+// heads always take the two-pass form (pass 1 leaves L3 in TMEM, pass 2 evaluates the heads outside the MUFU-heavy part):
+// at 80 registers the single-pass power sums cost more in spills than the second TMEM read (3.63 -> 3.74 G row-steps/s).
 #include "sampler_params.cuh"
 #include "tc_helpers.cuh"
 #include "upd_common.cuh"
@@ -159,7 +161,7 @@ sampler_tc3w_kernel(const UpdSamplerParams p) {
   const uint32_t xch_off = upd_align128(steps_off + STEP_BYTES * p.T);
   // exchange area per tile: ssx[2 layers][2 halves][128 rows]; headx[1 + 7F][128 rows] = layer-3 sum of squares,
   // F eps sums, F noise draws, 5F sigma-head sums handed from the half-1 warp to the row's owner
-  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0 && F > 1) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
+  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
   const uint32_t sync_off = upd_align128(xch_off + 3 * XCH_TILE_FLOATS * 4);
   TcSync* sync = reinterpret_cast<TcSync*>(smem + sync_off);
 
@@ -215,7 +217,7 @@ sampler_tc3w_kernel(const UpdSamplerParams p) {
   const uint32_t bar = tc::smem_u32(&sync->mma_bar[tile_id]);
   const uint32_t img = tc::smem_u32(smem);
   float* ssx = sf(xch_off) + tile_id * XCH_TILE_FLOATS;     // [2][2][128]
-  float* headx = ssx + ((NS && F > 1) ? 3 : 2) * 2 * 128;   // [1 + 7F][128] (single-pass heads) or [3F][128]
+  float* headx = ssx + (NS ? 3 : 2) * 2 * 128;   // [1 + 7F][128] (single-pass heads) or [3F][128]
   // named barriers: 1,2 = all 256 threads of a tile (precede every MMA issue); 5..12 = the two warps that share
   // a TMEM lane quadrant (64 threads), for the half<->half exchanges that need no tile-wide rendezvous
   const int full_bar = 1 + tile_id, pair_bar = 4 + tile_id * 4 + quad;    // ids 1..3 and 4..15
@@ -362,7 +364,7 @@ sampler_tc3w_kernel(const UpdSamplerParams p) {
       tc::fence_after_sync();
       UPD_STAMP(8);
 
-      if constexpr (!(NS && F > 1)) {
+      if constexpr (!NS) {
       // ---------------- layer 3 epilogue + heads (denoise.py:50 / tmdm_model.py:63) ----------------
       // NsDiff heads read hn = h/||h|| (= L/||L||): eps = lin4(hn), sigma = softplus(sigma_lin(softplus(hn))).
       // ||L|| is only known once the whole row is done, so instead of a second pass over the row the layer-3
@@ -560,7 +562,7 @@ template <int KIND, int F>
 cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
   constexpr uint32_t STEP_BYTES = (KIND == 0) ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
-  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0 && F > 1) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
+  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
   size_t smem = upd_align128(upd_align128(upd_align128(L.tc_image_bytes) + STEP_BYTES * p.T) + 3 * XCH_TILE_FLOATS * 4) +
                 sizeof(TcSync) + 128;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
