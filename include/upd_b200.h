@@ -244,6 +244,18 @@ int upd_dts_attention_bwd(const float* q_dev, long long q_row_stride, const floa
 int upd_stg_posterior(const float* xt_dev, const float* pred_dev, const float* z_dev, long long n,
                       float a, float b, float c, float* out_dev, void* stream);
 
+/* upd_nsx_step -- NsDiff_spatial (models/Diffusion_model/NsDiff/NsDiff_model.py:695-790): replaces the two heads of the
+ *   graph denoiser (models/Diffusion_model/NsDiff/ugnet.py:290-292: eps = lin4(e), sigma = softplus(sigma_lin(
+ *   softplus(e)))) and the posterior step that consumes them (p_sample, models/Diffusion_model/NsDiff/nsdiff_utils.py:
+ *   111-158; t == 0: p_sample_t_1to0, :209-239, no noise).  e_dev [N, DH, T] is UGnet's out block, channel-major;
+ *   w4/ws [F, DH], b4/bs [F]; y/yT/gx/z/out [N, T, F]; sched_dev [10, n_steps] rows in the order of upd_nsdiff_sample.
+ *   z_dev must be NULL exactly when t == 0.  y_dev NULL: heads only, written to eps_out_dev / sig_out_dev (either may
+ *   be NULL otherwise). */
+int upd_nsx_step(const float* e_dev, const float* w4_dev, const float* b4_dev, const float* ws_dev, const float* bs_dev,
+                 const float* y_dev, const float* yT_dev, const float* gx_dev, const float* z_dev, const float* sched_dev,
+                 int n_steps, int t, long long N, int DH, int T, int F, float* out_dev, float* eps_out_dev,
+                 float* sig_out_dev, void* stream);
+
 /* upd_stg_gated_aggregate -- replaces SpatialBlock's relu(ResGatedGraphConv(x, edge_index))
  *   (models/Diffusion_model/DiffSTG/ugnet.py:36-45; torch_geometric 2.5.3 layer, bias=True, root_weight=True) after
  *   its four projections, and duplicate_edge_index (graph_diffusion_model.py:77-84):

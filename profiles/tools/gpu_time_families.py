@@ -73,3 +73,27 @@ if which in ("stg", "both"):
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
             m.sample_windows(win, ei, 100, seed=1, window_base=0); torch.cuda.synchronize()
         print(p.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+
+if which in ("nsx", "both"):
+    from updgm_b200.nsdiff_spatial import NsDiff_model_spatial
+    import networkx as nx
+    g = np.load("tests/golden/nsx_yaml_evalstep.npz"); cfg = json.loads(str(g["cfg"]))
+    cfg = dict(cfg, n_z_samples=100, parallel_sample=10)            # the biomass YAML's K / S on the spatial class
+    torch.manual_seed(123)
+    m = NsDiff_model_spatial(dict(cfg, device=DEV), "NsDiff_model").eval()
+    with torch.no_grad():
+        m.scaler_std.fill_(1.0)
+    G = nx.barabasi_albert_graph(100, 12, seed=0)
+    ei = torch.tensor(list(G.to_directed().edges)).t().contiguous()
+    W = 4
+    torch.manual_seed(0)
+    win = 5.0 + (torch.randn(W, 100, 100, 1, device=DEV).cumsum(2) * 0.05)
+    m.sample_windows(win[:1], ei, 100, seed=1, window_base=0)
+    t, out = timed(lambda: m.sample_windows(win, ei, 100, seed=1, window_base=0))
+    n_traj = out.shape[0] * out.shape[1]
+    print("NSX sample: %d node-trajectories (%d windows x 100 nodes x 100 samples) in %.2f s -> %.1f traj/s; finite frac %.3f; peak mem %.1f GB" % (n_traj, W, t, n_traj / t, float(torch.isfinite(out).float().mean()), torch.cuda.max_memory_allocated() / 2**30))
+    if prof:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
+            m.sample_windows(win[:1], ei, 100, seed=1, window_base=0); torch.cuda.synchronize()
+        print(p.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))

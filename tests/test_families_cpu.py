@@ -163,3 +163,67 @@ def test_factory_builds_the_new_families():
     assert type(loader.diffusion_models("DiffusionTS", dict(cfg, device="cpu"))).__name__ == "DiffusionTS_model"
     g, cfg, shapes, seed = _load("stg_small_evalstep.npz")
     assert type(loader.diffusion_models("DiffSTG", dict(cfg, device="cpu"))).__name__ == "DiffSTG"
+
+
+# ------------------------------------------------------------------------------------------ NsDiff_spatial
+def _nsx_weights(g, shapes, seed):
+    from oracle import nsdiff_spatial_oracle as nsx
+    from updgm_b200.fx_encoder import PositionalEmbedding
+    cfg = json.loads(str(g["cfg"]))
+    sd = _stg_weights(shapes, seed)
+    fshapes = json.loads(str(g["fx_keys"]))
+    fx_sd = {nsx.FX + k: v for k, v in dto.synth_state_dict(fshapes, seed + 1).items()}
+    pe = PositionalEmbedding(cfg["d_model"]).pe
+    for k in fx_sd:
+        if k.endswith("position_embedding.pe"):
+            fx_sd[k] = pe.clone()
+    sd.update(fx_sd)
+    return sd
+
+
+@pytest.mark.parametrize("name", ["nsx_small_evalstep.npz", "nsx_yaml_evalstep.npz"])
+def test_nsx_oracle_matches_reference_run(name):
+    from oracle import nsdiff_spatial_oracle as nsx, nsdiff_oracle as nso
+    g, cfg, shapes, seed = _load(name)
+    sd = _nsx_weights(g, shapes, seed)
+    x, ei = torch.from_numpy(g["x"]), torch.from_numpy(g["edge_index"])
+    V, S = x.shape[0], cfg["parallel_sample"]
+    sched = nso.nsdiff_schedule(cfg["diffusion_schedule"], cfg["diffusion_steps"], cfg["beta_start"], cfg["beta_end"])
+    for k in ("alphas", "betas_tilde", "betas_bar", "betas_tilde_m_1", "betas_bar_m_1", "one_minus_alphas_bar_sqrt",
+              "alphas_cumprod_prev"):
+        assert torch.equal(sched[k], torch.from_numpy(g["sched:" + k])), k
+    par = so.duplicate_edge_index(S, ei, V)
+    for t in (0, 1, cfg["diffusion_steps"] - 1):
+        with torch.no_grad():
+            eps, sig = nsx.ugnet_forward(sd, cfg, *[torch.from_numpy(g["den%d:%s" % (t, n)]) for n in ("y", "y0", "gx")],
+                                         t, par)
+        assert torch.equal(eps, torch.from_numpy(g["den%d:eps" % t])) and torch.equal(sig, torch.from_numpy(g["den%d:sig" % t]))
+    draws = iter([torch.from_numpy(g["z%03d" % i]) for i in range(int(g["n_draws"]))])
+    outs, by = nsx.evaluation_step(sd, cfg, x, ei, V, lambda like: next(draws).clone())
+    assert by is None and torch.equal(outs.contiguous(), torch.from_numpy(g["outs"]))
+    assert next(draws, None) is None and int(g["n_draws"]) == cfg["diffusion_steps"] * (cfg["n_z_samples"] // S)
+
+
+def test_nsx_product_keys_and_loader(tmp_path):
+    from updgm_b200.nsdiff_spatial import NsDiff_model_spatial
+    from updgm_b200 import loader
+    g, cfg, shapes, seed = _load("nsx_yaml_evalstep.npz")
+    m = NsDiff_model_spatial(dict(cfg, device="cpu"), "NsDiff_model")
+    own = m.state_dict()
+    assert {k: list(v.shape) for k, v in own.items()
+            if k.startswith("model.") or k.startswith("cond_pred_model_g.")} == shapes
+    fshapes = json.loads(str(g["fx_keys"]))
+    assert {k[len("cond_pred_model."):]: list(v.shape) for k, v in own.items() if k.startswith("cond_pred_model.")} == fshapes
+    sd = _nsx_weights(g, shapes, seed)
+    sd.update(scaler_mean=torch.zeros(1), scaler_std=torch.ones(1))
+    m.load_state_dict(sd, strict=True)
+    for k in ("alphas", "betas_tilde", "betas_bar_m_1", "one_minus_alphas_bar_sqrt"):
+        assert torch.equal(getattr(m.model, k), torch.from_numpy(g["sched:" + k])), k
+    ei = torch.from_numpy(g["edge_index"])
+    assert torch.equal(m.duplicate_edge_index(3, ei, 6, "cpu"), so.duplicate_edge_index(3, ei, 6))
+    assert loader.NOT_YET == {}
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        from updgm_b200.diffstg import GraphData
+        m.evaluation_step(GraphData(x=torch.from_numpy(g["x"]), edge_index=ei, num_nodes=6))
+    with pytest.raises(ValueError, match="divisible"):
+        NsDiff_model_spatial(dict(cfg, device="cpu", pred_len=101), "NsDiff_model")

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_build.build_library())
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.lib().upd_abi_version() == 3
+    assert _lib.lib().upd_abi_version() == 4
     assert _lib.lib().upd_error_string(2) == b"unsupported shape"
 
 
@@ -252,8 +252,8 @@ def test_factory_names():
     from updgm_b200 import loader
     with pytest.raises(ValueError, match="don't exit"):
         loader.diffusion_models("Nope", {})
-    with pytest.raises(NotImplementedError):
-        loader.diffusion_models("NsDiff_spatial", {})
+    with pytest.raises(KeyError):                     # every task_model of models/models.py:5-32 is built; this one
+        loader.diffusion_models("NsDiff_spatial", {})   # needs train_model_select like the reference's factory
 
 
 # ------------------------------------------------------------------------------------------ N > 1 host path (gloo)

@@ -32,6 +32,10 @@ cudaError_t upd_launch_dts_fourier_fwd(const float* spec, long long spec_row_str
                                        cudaStream_t stream);
 cudaError_t upd_launch_dts_fourier_bwd(const float* gseason, const int* idx, long long gspec_row_stride, long long rows,
                                        int NF, int low, int seq, int D, int top_k, float* gspec, cudaStream_t stream);
+cudaError_t upd_launch_nsx_step(const float* e, const float* w4, const float* b4, const float* ws, const float* bs,
+                                const float* y, const float* yT, const float* gx, const float* z, const float* sched,
+                                int n_steps, int t, long long N, int DH, int T, int F, float* out, float* eps_out,
+                                float* sig_out, int sms, cudaStream_t stream);
 cudaError_t upd_launch_stg_posterior(const float* xt, const float* pred, const float* z, long long n, float a, float b,
                                      float c, float* out, int sms, cudaStream_t stream);
 cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr, const int* col, const float* bias,
@@ -352,6 +356,22 @@ int upd_stg_posterior(const float* xt_dev, const float* pred_dev, const float* z
   if (!xt_dev || !pred_dev || !out_dev || n <= 0) return UPD_ERR_BAD_ARG;
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_posterior(xt_dev, pred_dev, z_dev, n, a, b, c, out_dev, sms, (cudaStream_t)stream));
+}
+
+int upd_nsx_step(const float* e_dev, const float* w4_dev, const float* b4_dev, const float* ws_dev, const float* bs_dev,
+                 const float* y_dev, const float* yT_dev, const float* gx_dev, const float* z_dev, const float* sched_dev,
+                 int n_steps, int t, long long N, int DH, int T, int F, float* out_dev, float* eps_out_dev,
+                 float* sig_out_dev, void* stream) {
+  if (!e_dev || !w4_dev || !b4_dev || !ws_dev || !bs_dev || !sched_dev || N <= 0 || DH <= 0 || T <= 0 || F <= 0 ||
+      n_steps <= 0 || t < 0 || t >= n_steps) return UPD_ERR_BAD_ARG;
+  if (y_dev) {
+    if (!yT_dev || !gx_dev || !out_dev || (t > 0) != (z_dev != nullptr)) return UPD_ERR_BAD_ARG;
+  } else if (!eps_out_dev && !sig_out_dev) {
+    return UPD_ERR_BAD_ARG;
+  }
+  UPD_DEVICE_OR_RETURN();
+  UPD_FINISH(upd_launch_nsx_step(e_dev, w4_dev, b4_dev, ws_dev, bs_dev, y_dev, yT_dev, gx_dev, z_dev, sched_dev, n_steps, t,
+                                 N, DH, T, F, out_dev, eps_out_dev, sig_out_dev, sms, (cudaStream_t)stream));
 }
 
 int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const int* col_dev, const float* bias_dev,

@@ -231,6 +231,37 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
   }
 }
 
+// NsDiff_spatial: the two heads of the graph denoiser and one NsDiff posterior step, fused.
+//   e [N, DH, T] = UGnet's out block, channel-major -> eps = lin4(e^T), sigma = softplus(sigma_lin(softplus(e^T)))
+//   (models/Diffusion_model/NsDiff/ugnet.py:290-292), then p_sample / p_sample_t_1to0
+//   (models/Diffusion_model/NsDiff/nsdiff_utils.py:111-158, 209-239) on [N, T, F].  y == nullptr: heads only.
+__global__ void nsx_step_kernel(const float* __restrict__ e, const float* __restrict__ w4, const float* __restrict__ b4,
+                                const float* __restrict__ ws, const float* __restrict__ bs, const float* __restrict__ y,
+                                const float* __restrict__ yT, const float* __restrict__ gx, const float* __restrict__ z,
+                                const float* __restrict__ sched, int n_steps, int t, long long N, int DH, int T, int F,
+                                float* __restrict__ out, float* __restrict__ eps_out, float* __restrict__ sig_out) {
+  const UpdNsStep st = upd_ns_step(sched, n_steps, t);
+  const long long total = N * T * F;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % F);
+    const long long np = i / F;
+    const int p = (int)(np % T);
+    const long long n = np / T;
+    const float* er = e + n * DH * T + p;
+    float ae = 0.0f, as = 0.0f;
+    for (int c = 0; c < DH; ++c) {
+      const float v = er[(long long)c * T];
+      ae = fmaf(v, w4[f * DH + c], ae);
+      as = fmaf(upd_softplus_accurate(v), ws[f * DH + c], as);
+    }
+    const float eps = __fadd_rn(ae, b4[f]);
+    const float sig = upd_softplus_accurate(__fadd_rn(as, bs[f]));
+    if (eps_out) eps_out[i] = eps;
+    if (sig_out) sig_out[i] = sig;
+    if (y) out[i] = upd_ns_update(st, y[i], yT[i], gx[i], eps, sig, z ? z[i] : 0.0f, t == 0);
+  }
+}
+
 inline unsigned stream_grid(long long n, int block, int sms) {
   long long g = (n + block - 1) / block;
   long long cap = (long long)sms * 16;
@@ -242,6 +273,15 @@ inline unsigned stream_grid(long long n, int block, int sms) {
 cudaError_t upd_launch_stg_posterior(const float* xt, const float* pred, const float* z, long long n, float a, float b,
                                      float c, float* out, int sms, cudaStream_t stream) {
   stg_posterior_kernel<<<stream_grid(n, 256, sms), 256, 0, stream>>>(xt, pred, z, n, a, b, c, out);
+  return cudaGetLastError();
+}
+
+cudaError_t upd_launch_nsx_step(const float* e, const float* w4, const float* b4, const float* ws, const float* bs,
+                                const float* y, const float* yT, const float* gx, const float* z, const float* sched,
+                                int n_steps, int t, long long N, int DH, int T, int F, float* out, float* eps_out,
+                                float* sig_out, int sms, cudaStream_t stream) {
+  nsx_step_kernel<<<stream_grid(N * T * F, 256, sms), 256, 0, stream>>>(e, w4, b4, ws, bs, y, yT, gx, z, sched, n_steps, t, N,
+                                                                        DH, T, F, out, eps_out, sig_out);
   return cudaGetLastError();
 }
 

@@ -44,10 +44,13 @@ class GraphData:
         return GraphData(None if self.x is None else self.x.clone(), self.edge_index.clone(), self.num_nodes)
 
 
-def block_plan(net_param):
-    """Execution-ordered (key prefix, kind, c_in, c_out, T_in) of UGnet (ugnet.py:190-239)."""
+def block_plan(net_param, T_total=None):
+    """Execution-ordered (key prefix, kind, c_in, c_out, T_in) of UGnet (ugnet.py:190-239).  ``T_total``: length of the
+    time axis the U-Net works on (DiffSTG: 2*(T_h+T_p), the default; NsDiff_spatial's UGnet: pred_len)."""
     d_h, mults, n_blocks = net_param["d_h"], net_param["channel_multipliers"], net_param["n_blocks"]
-    T_in = 2 * (net_param["T_p"] + net_param["T_h"])
+    if T_total is None:
+        T_total = 2 * (net_param["T_p"] + net_param["T_h"])
+    T_in = T_total
     n_res = len(mults)
     down, up = [], []
     out_c = in_c = d_h
@@ -75,18 +78,18 @@ def block_plan(net_param):
             up.append(("up.%d." % idx, "upsample", in_c, in_c, T_in))
             idx += 1
             T_in = T_in * 2
-    assert T_in == 2 * (net_param["T_p"] + net_param["T_h"]), "T_in should be equal to 2*T"
+    assert T_in == T_total, "T_in should be equal to T"
     return down, middle, up
 
 
-def ugnet_shapes(net_param):
-    F_, d_h, Td_h = net_param["F"], net_param["d_h"], net_param["Td_h"]
-    T = net_param["T_p"] + net_param["T_h"]
+def block_shapes(net_param, T_total=None):
+    """Key -> shape of every U-Net block (without the input / output projections)."""
+    d_h, Td_h = net_param["d_h"], net_param["Td_h"]
     if net_param["gnn_name"] != "ResGatedGraphConv":
         raise NotImplementedError("only gnn_name='ResGatedGraphConv' (every shipped DiffSTG YAML) is built")
     gp = net_param.get("gnn_param") or {}
     sh = {}
-    down, middle, up = block_plan(net_param)
+    down, middle, up = block_plan(net_param, T_total)
     for pre, kind, c_in, c_out, T_in in down + middle + up:
         if kind == "res":
             for tcn, ci in (("tcn1.", c_in), ("tcn2.", c_out)):
@@ -111,10 +114,51 @@ def ugnet_shapes(net_param):
             sh[pre + "conv.weight"], sh[pre + "conv.bias"] = (c_in, c_in, 1, 3), (c_in,)
         else:
             sh[pre + "conv.weight"], sh[pre + "conv.bias"] = (c_in, c_in, 1, 4), (c_in,)
+    return sh
+
+
+def ugnet_shapes(net_param):
+    F_, d_h = net_param["F"], net_param["d_h"]
+    T = net_param["T_p"] + net_param["T_h"]
+    sh = block_shapes(net_param)
     sh["x_proj.weight"], sh["x_proj.bias"] = (d_h, F_, 1, 1), (d_h,)
     sh["out.0.weight"], sh["out.0.bias"] = (F_, d_h, 1, 1), (F_,)
     sh["out.1.weight"], sh["out.1.bias"] = (T, 2 * T), (T,)
     return sh
+
+
+def populate_ugnet(tree, shapes, alias):
+    """Register UGnet's parameters on ``tree`` (a ParamTree) under the reference's key names, default-style init;
+    TcnBlock registers its conv twice (``conv`` and ``net.0``: the same Parameter) -- ``alias(key, param)`` adds those."""
+    gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 63))
+    for key, shp in shapes.items():
+        if ".net.0." in key:
+            continue
+        if ".norm." in key:
+            w = torch.ones(shp) if key.endswith("weight") else torch.zeros(shp)
+        elif key.endswith("spatial.gnn.bias"):
+            w = torch.zeros(shp)
+        else:
+            fan_in = shp[0] if len(shp) == 1 else int(np.prod(shp[1:]))
+            bound = 1.0 / math.sqrt(max(fan_in, 1))
+            w = torch.empty(shp).uniform_(-bound, bound, generator=gen)
+        tree.add(key, w)
+    for key in shapes:
+        if ".net.0." in key:
+            node = tree
+            for part in key.replace(".net.0.", ".conv.").split("."):
+                node = getattr(node, part) if not part.isdigit() else node._modules[part]
+            alias(key, node)
+
+
+def alias_parameter(tree, key, param):
+    node = tree
+    parts = key.split(".")
+    for part in parts[:-1]:
+        if part not in node._modules:
+            node.add_module(part, ParamTree())
+        node = node._modules[part]
+    node.register_parameter(parts[-1], param)
 
 
 class GaussianDiffusion:
@@ -182,11 +226,11 @@ def gated_aggregate(kqvs, rowptr, col, bias, V, C, relu=True):
 class PreparedUGnet:
     """Inference-time weight layout of UGnet (fp32 on the device, built once per model load)."""
 
-    def __init__(self, model, net_param, diffusion_T):
+    def __init__(self, model, net_param, diffusion_T, T_total=None):
         sd = {k: v.detach().to(torch.float32) for k, v in model.state_dict().items()}
         dev = sd["x_proj.weight"].device
         self.device, self.Td_h, self.d_h = dev, net_param["Td_h"], net_param["d_h"]
-        self.down, self.middle, self.up = block_plan(net_param)
+        self.down, self.middle, self.up = block_plan(net_param, T_total)
         d_h, Td = self.d_h, self.Td_h
         # TimeEmbedding (ugnet.py:15-33) for every diffusion step 0..T
         half = d_h // 2
@@ -304,9 +348,15 @@ class PreparedUGnet:
 
     def forward(self, xt, x_masked, t, rowptr, col, V):
         """xt, x_masked [N, T, F]; t: int diffusion step shared by all rows -> eps prediction [N, T, F]."""
+        x = torch.cat((xt.transpose(1, 2), x_masked.transpose(1, 2)), dim=-1)                # [N, F, 2T]
+        return self.trunk(x, t, rowptr, col, V).transpose(1, 2).contiguous()
+
+    def trunk(self, x, t, rowptr, col, V):
+        """x [N, C_in, T_total] -> the out block's result [N, C_out, T_out]; t: index into the step-embedding table."""
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            x = torch.cat((xt.transpose(1, 2), x_masked.transpose(1, 2)), dim=-1)            # [N, F, 2T]
-            x = F.conv1d(x, self.xproj_w, self.xproj_b)
+            # the 1x1 projections are plain matmuls (cuDNN's heuristic picks an FFT algorithm for some of these shapes:
+            # 30 ms per call at [10^4, 3, 100])
+            x = torch.matmul(self.xproj_w[:, :, 0], x) + self.xproj_b[None, :, None]
             hs = [x]
 
             def run(blk, x):
@@ -327,9 +377,8 @@ class PreparedUGnet:
                 if blk[1] != "upsample":
                     x = torch.cat((x, hs.pop()), dim=1)
                 x = run(blk, x)
-            e = F.conv1d(x, self.out0_w, self.out0_b)
-            e = F.linear(e, self.out1_w, self.out1_b)
-            return e.transpose(1, 2).contiguous()
+            e = torch.matmul(self.out0_w[:, :, 0], x) + self.out0_b[None, :, None]
+            return F.linear(e, self.out1_w, self.out1_b)
 
 
 class DiffSTG(nn.Module):
@@ -353,26 +402,7 @@ class DiffSTG(nn.Module):
         self.mask_ratio = net_param["mask_ratio"]
         self.net_param = net_param
         self.model = ParamTree()
-        gen = torch.Generator().manual_seed(torch.initial_seed() % (2 ** 63))
-        shapes = ugnet_shapes(net_param)
-        for key, shp in shapes.items():
-            if ".net.0." in key:
-                continue
-            if ".norm." in key:
-                w = torch.ones(shp) if key.endswith("weight") else torch.zeros(shp)
-            elif key.endswith("spatial.gnn.bias"):
-                w = torch.zeros(shp)
-            else:
-                fan_in = shp[0] if len(shp) == 1 else int(np.prod(shp[1:]))
-                bound = 1.0 / math.sqrt(max(fan_in, 1))
-                w = torch.empty(shp).uniform_(-bound, bound, generator=gen)
-            self.model.add(key, w)
-        for key in shapes:                     # TcnBlock: self.net = Sequential(self.conv, ...) -> the same Parameter twice
-            if ".net.0." in key:
-                node = self.model
-                for part in key.replace(".net.0.", ".conv.").split("."):
-                    node = getattr(node, part) if not part.isdigit() else node._modules[part]
-                self._alias(key, node)
+        populate_ugnet(self.model, ugnet_shapes(net_param), self._alias)
         self.scaler = net_param["scaler_type"]
         self.register_buffer("scaler_mean", torch.zeros(self.F))
         self.register_buffer("scaler_std", torch.zeros(self.F))
@@ -384,13 +414,7 @@ class DiffSTG(nn.Module):
         self.to(self.device)
 
     def _alias(self, key, param):
-        node = self.model
-        parts = key.split(".")
-        for part in parts[:-1]:
-            if part not in node._modules:
-                node.add_module(part, ParamTree())
-            node = node._modules[part]
-        node.register_parameter(parts[-1], param)
+        alias_parameter(self.model, key, param)
 
     def scaler_fit(self, data):
         data_std = data.std(axis=(0, 1))

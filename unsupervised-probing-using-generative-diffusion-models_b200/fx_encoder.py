@@ -439,6 +439,8 @@ class NsTransformer(nn.Module):
     (pred [B,O,F], dec_out); ``vae=True``: TMDM condition model (tmdm_ns_transformer.py:40-174), eval
     path (z = posterior mean), returning (pred, dec_out [B,label+O,F], None, None)."""
 
+    bridge = None      # subclasses may define bridge(enc_out [B, L, d]) -> [B, L, d], applied before the decoder reads it
+
     def __init__(self, configs, vae=False):
         super().__init__()
         self.pred_len, self.seq_len, self.label_len = configs.pred_len, configs.seq_len, configs.label_len
@@ -481,6 +483,9 @@ class NsTransformer(nn.Module):
         if self.vae:
             x = self.z_out(self.z_mean(x))                    # eval: z = posterior mean (:133-134)
             a3 = a3_split(x.contiguous())
+        if self.bridge is not None:                           # Model_spatial: graph block between encoder and decoder
+            x = self.bridge(x.view(B, L, -1)).reshape(B * L, -1)
+            a3 = a3_split(x.contiguous())
         a3_enc = a3
         xd, a3 = self.dec_embedding.fused(x_dec_new)
         layers = self.decoder.layers
@@ -510,6 +515,8 @@ class NsTransformer(nn.Module):
         enc_out = self.encoder(self.enc_embedding(x_enc), tau, delta)
         if self.vae:
             enc_out = self.z_out(self.z_mean(enc_out))        # eval: z = posterior mean (:133-134)
+        if self.bridge is not None:
+            enc_out = self.bridge(enc_out)
         dec_out = self.decoder(self.dec_embedding(x_dec_new), enc_out, tau, delta)
         dec_out = dec_out * std_enc + mean_enc
         if self.vae:

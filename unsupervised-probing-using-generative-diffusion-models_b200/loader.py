@@ -5,9 +5,7 @@ import torch
 
 from . import _lib
 
-NOT_YET = {
-    "NsDiff_spatial": "NsDiff_spatial is not referenced by any shipped configuration (SURVEY 8a11)",
-}
+NOT_YET = {}
 
 
 def diffusion_models(task_model, net_param, **kwargs):
@@ -17,6 +15,11 @@ def diffusion_models(task_model, net_param, **kwargs):
         return NsDiff_model(net_param=net_param, train_model_select=kwargs["train_model_select"],
                             pretrain_f_path=net_param["pretrain_f_path"] if net_param.get("pretrain_f_path") else None,
                             pretrain_g_path=net_param["pretrain_g_path"] if net_param.get("pretrain_g_path") else None)
+    if task_model == "NsDiff_spatial":
+        from .nsdiff_spatial import NsDiff_model_spatial
+        return NsDiff_model_spatial(net_param=net_param, train_model_select=kwargs["train_model_select"],
+                                    pretrain_f_path=net_param["pretrain_f_path"] if net_param.get("pretrain_f_path") else None,
+                                    pretrain_g_path=net_param["pretrain_g_path"] if net_param.get("pretrain_g_path") else None)
     if task_model == "NsDiff_model_variants":
         from .nsdiff import NsDiff_model_variants
         return NsDiff_model_variants(net_param=net_param, train_model_select=kwargs["train_model_select"])

@@ -1,0 +1,377 @@
+"""NsDiff_spatial model object with the reference's surface, backed by the GPU sampler (third class).
+
+Mirrors models/Diffusion_model/NsDiff/NsDiff_model.py:496-801 (``NsDiff_model_spatial``: constructor keys, ``scaler_*``,
+``cond_pred_model_g``, ``evaluation_step(gdata)`` with ``gdata.x [Node, L(+O), F]``, ``gdata.edge_index [2,E]``,
+``gdata.num_nodes``) and keeps every parameter name of ``NsDiff_net_spatial`` / ``UGnet`` (NsDiff_net.py:175-264,
+NsDiff/ugnet.py:194-293) and ``Model_spatial`` (mu_backbone.py:186-345) so reference checkpoints load ``strict=True``.
+
+The sampler is the NsDiff posterior (nsdiff_utils.py:111-284) around a graph U-Net denoiser.  It reuses the DiffSTG build:
+``diffstg.PreparedUGnet`` (fused causal-TCN + LayerNorm kernel, split-operand tensor-core GEMMs, gated graph aggregation
+on one CSR for every replica) with a 3F-channel input and a [d_h, T] output, followed by ``upd_nsx_step`` -- the eps /
+sigma heads and the posterior update in one kernel.  Chunks, windows and parallel samples are batched as graph replicas.
+
+Row order: a chunk's rows are ``b*S + s`` (NsDiff_model.py:749-757) while the reference's duplicated edge list addresses
+rows as ``s*V + b`` (:792-801).  Both are kept: rows are laid out ``b*S + s`` and the graph conv treats every V consecutive
+rows as one replica of the graph, exactly what the reference computes.  There is no CPU path.
+"""
+from types import SimpleNamespace
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import _lib, schedules
+from .diffstg import (PreparedUGnet, alias_parameter, block_shapes, gated_aggregate, graph_csr, populate_ugnet)
+from .diffusionts import ParamTree
+from .fx_encoder import NsTransformer
+from .nsdiff import EPS, SigmaEstimation
+
+ROWS_PER_LAUNCH = 32768
+
+
+def ugnet_shapes(cfg):
+    """Key -> shape of the NsDiff UGnet (NsDiff/ugnet.py:194-255): 3F input channels, T = pred_len, eps / sigma heads."""
+    nf, d_h, T = cfg["dataset_nf"], cfg["d_h"], cfg["pred_len"]
+    sh = block_shapes(cfg, T_total=T)
+    sh["x_proj.weight"], sh["x_proj.bias"] = (d_h, 3 * nf, 1, 1), (d_h,)
+    sh["out.0.weight"], sh["out.0.bias"] = (d_h, d_h, 1, 1), (d_h,)
+    sh["out.1.weight"], sh["out.1.bias"] = (T, T), (T,)
+    sh["lin4.weight"], sh["lin4.bias"] = (nf, d_h), (nf,)
+    sh["sigma_lin.weight"], sh["sigma_lin.bias"] = (nf, d_h), (nf,)
+    return sh
+
+
+class GatedGraphConvParams(nn.Module):
+    """Parameters of torch_geometric.nn.ResGatedGraphConv under PyG's names (models/layer/gnn_conv.py:18-19)."""
+
+    def __init__(self, channels, gnn_param):
+        super().__init__()
+        gp = gnn_param or {}
+        self.lin_key = nn.Linear(channels, channels)
+        self.lin_query = nn.Linear(channels, channels)
+        self.lin_value = nn.Linear(channels, channels)
+        if gp.get("root_weight", True):
+            self.lin_skip = nn.Linear(channels, channels, bias=False)
+        else:
+            self.register_parameter("lin_skip", None)
+        if gp.get("bias", True):
+            self.bias = nn.Parameter(torch.zeros(channels))
+        else:
+            self.register_parameter("bias", None)
+
+    def fused_weights(self):
+        """(K|Q|V|skip weight [4C, C], its bias [4C]) for one GEMM in front of upd_stg_gated_aggregate."""
+        C = self.lin_key.in_features
+        dev = self.lin_key.weight.device
+        skip = self.lin_skip.weight if self.lin_skip is not None else torch.zeros(C, C, device=dev)
+        w = torch.cat([self.lin_key.weight, self.lin_query.weight, self.lin_value.weight, skip], 0).detach().contiguous()
+        b = torch.cat([self.lin_key.bias, self.lin_query.bias, self.lin_value.bias,
+                       torch.zeros(C, device=dev)], 0).detach().contiguous()
+        return w, b
+
+
+class SpatialBlockParams(nn.Module):
+    """SpatialBlock (mu_backbone.py:43-51): relu(gnn(x, edge_index)); the arithmetic is in NsTransformerSpatial.bridge."""
+
+    def __init__(self, channels, gnn_name, gnn_param):
+        super().__init__()
+        if gnn_name != "ResGatedGraphConv":
+            raise NotImplementedError("only f_gnn_name='ResGatedGraphConv' is built")
+        self.gnn = GatedGraphConvParams(channels, gnn_param)
+
+
+class NsTransformerSpatial(NsTransformer):
+    """ns_Transformer.Model_spatial (mu_backbone.py:186-345): f(x) with a (1, T+1) convolution down to ``fT_h`` steps,
+    ``spatial_layers`` gated graph blocks on [rows, fT_h*d_model] and a transposed convolution back, between the encoder
+    and the decoder.  forward(x_enc, x_dec, edge_index) -> (pred [B,O,F], dec_out); B rows = replicas of the graph."""
+
+    def __init__(self, configs):
+        super().__init__(configs)
+        d = configs.d_model
+        self.T, self.fT_h, self.spatial_layers = configs.windows, configs.fT_h, configs.spatial_layers
+        self.d_model = d
+        self.spatial_encoder = nn.ModuleList([SpatialBlockParams(self.fT_h * d, configs.f_gnn_name, configs.f_gnn_param)
+                                              for _ in range(self.spatial_layers)])
+        self.downsampling = nn.Conv2d(d, d, (1, self.T + 1), (1, 1), (0, self.fT_h // 2))
+        self.upsampling = nn.ConvTranspose2d(d, d, (1, self.T + 1), (1, 1), (0, self.fT_h // 2))
+        self._graph = None
+
+    def set_graph(self, rowptr, col, num_nodes):
+        self._graph = (rowptr, col, int(num_nodes))
+
+    def bridge(self, enc_out):
+        if self._graph is None:
+            raise RuntimeError("edge_index must be set before the forward pass")
+        rowptr, col, V = self._graph
+        B, L, d = enc_out.shape
+        if B % V != 0:
+            raise ValueError("{} rows are not whole replicas of the {}-node graph".format(B, V))
+        fT, pad = self.fT_h, self.fT_h // 2
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            h = F.conv1d(enc_out.transpose(1, 2), self.downsampling.weight[:, :, 0, :], self.downsampling.bias, padding=pad)
+            s = h.transpose(1, 2).reshape(B, fT * d)
+            for blk in self.spatial_encoder:
+                w, b = blk.gnn.fused_weights()
+                kqvs = torch.addmm(b, s, w.t())
+                s = gated_aggregate(kqvs, rowptr, col, blk.gnn.bias, V, fT * d)
+            h = s.reshape(B, fT, d).transpose(1, 2)
+            h = F.conv_transpose1d(h, self.upsampling.weight[:, :, 0, :], self.upsampling.bias, padding=pad)
+        return h.transpose(1, 2).contiguous()
+
+    def forward(self, x_enc, x_dec, edge_index=None, *unused):
+        if edge_index is not None:
+            V = self._graph[2] if self._graph is not None else x_enc.shape[0]
+            rowptr, col = graph_csr(edge_index, V)
+            self.set_graph(rowptr.to(x_enc.device), col.to(x_enc.device), V)
+        return super().forward(x_enc, x_dec)
+
+
+class NsDiffNetSpatial(nn.Module):
+    """NsDiff_net_spatial (NsDiff_net.py:175-264): schedule tables as plain attributes + the UGnet denoiser under the
+    reference's attribute name ``diffussion_model``."""
+
+    def __init__(self, configs, device):
+        super().__init__()
+        self.args = configs
+        self.device = device
+        self.num_timesteps = configs.diffusion_steps
+        tab = schedules.nsdiff_tables(configs.diffusion_schedule, configs.diffusion_steps, configs.beta_start,
+                                      configs.beta_end)
+        self.tables = tab
+        for k, v in tab.items():
+            setattr(self, k, v.to(device))
+        self.alphas_tilde = self.alphas_cumprod_sum
+        self.diffussion_model = ParamTree()
+        populate_ugnet(self.diffussion_model, ugnet_shapes(vars(configs)),
+                       lambda key, param: alias_parameter(self.diffussion_model, key, param))
+        self.edge_index = None
+
+    def set_edge_index(self, edge_index):
+        self.edge_index = edge_index
+
+
+class NsDiff_model_spatial(nn.Module):
+    """NsDiff_model.py:496-801.  ``train_model_select`` in {'NsDiff_model', 'pretrain_f', 'pretrain_g'}."""
+
+    def __init__(self, net_param, train_model_select, pretrain_f_path="results/pre_model_F",
+                 pretrain_g_path="results/pre_model_G"):
+        super().__init__()
+        self.scaler = net_param["scaler_type"]
+        self.device = net_param["device"]
+        self.dataset_nf = net_param["dataset_nf"]
+        self.windows = net_param["windows"]
+        self.pred_len = net_param["pred_len"]
+        self.rolling_length = net_param["rolling_length"]
+        self.diffusion_steps = net_param["diffusion_steps"]
+        self.load_pretrain = net_param["load_pretrain"]
+        self.seq_len = net_param["seq_len"] = self.windows
+        self.label_len = net_param["label_len"] = self.windows // 2
+        self.freeze_pretrain = net_param["freeze_pretrain"] if "freeze_pretrain" in net_param else False
+        self.EPS = EPS
+        self.configs = SimpleNamespace(**net_param)
+        self.register_buffer("scaler_mean", torch.zeros(self.dataset_nf))
+        self.register_buffer("scaler_std", torch.zeros(self.dataset_nf))
+        self.train_model_select = train_model_select
+        if train_model_select == "NsDiff_model":
+            if self.pred_len % (2 ** (len(net_param["channel_multipliers"]) - 1)) != 0:
+                raise ValueError("pred_len must be divisible by 2^(resolutions-1): the reference's UGnet asserts it")
+            self.model = NsDiffNetSpatial(self.configs, self.device)
+            if self.load_pretrain:
+                pre_f = torch.load(pretrain_f_path + "/model_trained", map_location="cpu", weights_only=True)
+                pre_g = torch.load(pretrain_g_path + "/model_trained", map_location="cpu", weights_only=True)
+                self.cond_pred_model = NsTransformerSpatial(SimpleNamespace(**pre_f["net_param"]))
+                self.cond_pred_model_g = SigmaEstimation(self.windows, self.pred_len, self.dataset_nf, 512,
+                                                         pre_g["net_param"]["rolling_length"])
+                self.cond_pred_model.load_state_dict({k.replace("module.", ""): v for k, v in pre_f["state_dict"].items()},
+                                                     strict=True)
+                self.cond_pred_model_g.load_state_dict({k.replace("module.", ""): v for k, v in pre_g["state_dict"].items()},
+                                                       strict=True)
+            else:
+                self.cond_pred_model = NsTransformerSpatial(self.configs)
+                self.cond_pred_model_g = SigmaEstimation(self.windows, self.pred_len, self.dataset_nf, 512,
+                                                         self.rolling_length)
+        elif train_model_select == "pretrain_f":
+            self.cond_pred_model = NsTransformerSpatial(self.configs)
+        elif train_model_select == "pretrain_g":
+            self.cond_pred_model_g = SigmaEstimation(self.windows, self.pred_len, self.dataset_nf, 512,
+                                                     self.rolling_length)
+        else:
+            raise ValueError("train_model_select should be in ['NsDiff_model', 'pretrain_f', 'pretrain_g']")
+        self.rows_per_launch = ROWS_PER_LAUNCH
+        self._prepared = None
+        self._prepared_key = None
+        self._csr_cache = None
+        self._windows_drawn = 0
+        self.to(self.device)
+
+    # ---- reference helpers (NsDiff_model.py:587-598) ----
+    def scaler_fit(self, data):
+        data_std = data.std(axis=(0, 1))
+        data_std[data_std == 0] = 1
+        self.scaler_mean = data.mean(axis=(0, 1))
+        self.scaler_std = data_std
+
+    def scaler_transform(self, data):
+        return (data - self.scaler_mean) / self.scaler_std
+
+    def scaler_inverse_transform(self, data):
+        return (data * self.scaler_std) + self.scaler_mean
+
+    def forward(self, gdatalist):
+        raise NotImplementedError("training is outside the accelerated hot path (SURVEY section 8: out of scope)")
+
+    training_step = pretrain_f = pretrain_g = forward
+
+    def duplicate_edge_index(self, parallel_sampling, edge_index, num_nodes, device):
+        """NsDiff_model.py:792-801 (integer, bit-exact).  Kept for callers; the sampler shares one CSR across replicas."""
+        edge_index = edge_index.reshape((2, 1, -1))
+        indent = torch.arange(0, parallel_sampling).view(1, -1, 1).to(device) * num_nodes
+        return (edge_index + indent).reshape((2, -1))
+
+    # ---- device-side state ----
+    def _apply(self, fn, *a, **k):
+        self._prepared = None
+        return super()._apply(fn, *a, **k)
+
+    def prepared(self):
+        """(PreparedUGnet, head weights, schedule rows [10, T]) on the model's device; rebuilt if parameters changed."""
+        params = list(self.model.diffussion_model.parameters())
+        key = (params[0].device,) + tuple(p._version for p in params)
+        if self._prepared is None or self._prepared_key != key:
+            dev = _lib.require_cuda(params[0].device)
+            with torch.no_grad():
+                net = PreparedUGnet(self.model.diffussion_model, vars(self.configs), self.diffusion_steps,
+                                    T_total=self.pred_len)
+                sd = self.model.diffussion_model.state_dict()
+                heads = [sd[k].detach().to(dev, torch.float32).contiguous()
+                         for k in ("lin4.weight", "lin4.bias", "sigma_lin.weight", "sigma_lin.bias")]
+                rows = schedules.stack_rows(self.model.tables, schedules.NSDIFF_ROWS)
+                sched = torch.as_tensor(rows, dtype=torch.float32).to(dev).contiguous()
+            self._prepared = (net, heads, sched)
+            self._prepared_key = key
+        return self._prepared
+
+    def _csr(self, edge_index, num_nodes, dev):
+        key = (id(edge_index), tuple(edge_index.shape), num_nodes, str(dev))
+        if self._csr_cache is None or self._csr_cache[0] != key:
+            rowptr, col = graph_csr(edge_index, num_nodes)
+            if col.numel() == 0:
+                col = torch.zeros(1, dtype=torch.int32)
+            self._csr_cache = (key, rowptr.to(dev), col.to(dev), edge_index)
+        return self._csr_cache[1], self._csr_cache[2]
+
+    def condition(self, batch_x, rowptr, col, num_nodes):
+        """f(x) (graph-coupled, whole replicas per call) and g(x): rows [R, L, F] -> (y_0_hat, gx), both [R, O, F]."""
+        dev = batch_x.device
+        V = num_nodes
+        self.cond_pred_model.set_graph(rowptr, col, V)
+        per = max(1, 4096 // V) * V
+        parts = []
+        for r0 in range(0, batch_x.size(0), per):
+            xb = batch_x[r0:r0 + per]
+            dec_inp = torch.cat([xb[:, -self.label_len:, :],
+                                 torch.zeros(xb.size(0), self.pred_len, self.dataset_nf, device=dev)], dim=1)
+            parts.append(self.cond_pred_model(xb, dec_inp)[0])
+        gx = self.cond_pred_model_g(batch_x)                       # no EPS at inference (NsDiff_model.py:744)
+        return torch.cat(parts).contiguous(), gx.contiguous()
+
+    def denoise(self, y, y_0_hat, gx, t, edge_index, num_nodes):
+        """NsDiff_net_spatial.forward for rows that share step ``t`` -> (eps_theta, sigma_theta), both [N, O, F]."""
+        dev = _lib.require_cuda(y.device)
+        rowptr, col = self._csr(edge_index, num_nodes, dev)
+        net, heads, sched = self.prepared()
+        N, O, nf = y.shape
+        with torch.no_grad(), torch.cuda.device(dev):
+            x = torch.cat((y, y_0_hat, gx), dim=-1).transpose(1, 2).contiguous()
+            e = net.trunk(x, int(t), rowptr, col, num_nodes).contiguous()
+            eps, sig = torch.empty_like(y), torch.empty_like(y)
+            rc = _lib.lib().upd_nsx_step(_lib.ptr(e), *[_lib.ptr(h) for h in heads], None, None, None, None,
+                                         _lib.ptr(sched), self.diffusion_steps, int(t), N, e.shape[1], O, nf, None,
+                                         _lib.ptr(eps), _lib.ptr(sig), _lib.stream_ptr(dev))
+            _lib.check(rc, "upd_nsx_step")
+        return eps, sig
+
+    def sample_windows(self, windows, edge_index, num_nodes, noise=None, seed=None, window_base=None, y_0_hat=None):
+        """windows [W, Node, L(+O), F] scaled -> trajectories [W*Node, K, O, F] on the device, K = (n_z_samples //
+        parallel_sample) * parallel_sample.  noise: validation mode, noise[w][c] = that chunk's T draws ([Node*S, O, F]
+        each) in reference order.  ``y_0_hat`` [W*Node, O, F] overrides f(x) (validation of the sampler alone)."""
+        dev = _lib.require_cuda(self.scaler_mean.device)
+        W, V = windows.shape[0], windows.shape[1]
+        if V != num_nodes:
+            raise ValueError("windows hold {} nodes, graph has {}".format(V, num_nodes))
+        S = int(self.configs.parallel_sample)
+        n_chunks = int(self.configs.n_z_samples) // S
+        K = n_chunks * S
+        if K <= 0:
+            raise ValueError("n_z_samples // parallel_sample is zero")
+        O, nf, T = self.pred_len, self.dataset_nf, self.diffusion_steps
+        if seed is None:
+            seed = torch.initial_seed()
+        if window_base is None:
+            window_base = self._windows_drawn
+            self._windows_drawn += W
+        rowptr, col = self._csr(edge_index, num_nodes, dev)
+        net, heads, sched = self.prepared()
+        lib = _lib.lib()
+        x = windows.reshape(W * V, windows.shape[2], windows.shape[3])[:, :self.windows, :].to(dev, torch.float32).contiguous()
+        out = torch.empty((W, V, K, O, nf), dtype=torch.float32, device=dev)
+        with torch.no_grad(), torch.cuda.device(dev):
+            st = _lib.stream_ptr(dev)
+            y0_all, gx_all = self.condition(x, rowptr, col, V)
+            if y_0_hat is not None:
+                y0_all = y_0_hat.to(dev, torch.float32).contiguous()
+            y0_all, gx_all = y0_all.view(W, V, O, nf), gx_all.view(W, V, O, nf)
+            units = [(w, c) for w in range(W) for c in range(n_chunks)]          # unit = one chunk of one window
+            per = max(1, self.rows_per_launch // (V * S))
+            for u0 in range(0, len(units), per):
+                group = units[u0:u0 + per]
+                N = len(group) * V * S
+                wi = torch.tensor([w for (w, c) in group], device=dev)
+                # rows of a unit in the reference's tile order b*S + s
+                y0 = y0_all[wi].repeat_interleave(S, dim=1).reshape(N, O, nf).contiguous()
+                gx = gx_all[wi].repeat_interleave(S, dim=1).reshape(N, O, nf).contiguous()
+
+                def draw(i):
+                    if noise is not None:
+                        return torch.cat([noise[w][c][i] for (w, c) in group], 0).to(dev, torch.float32).contiguous()
+                    z = torch.empty((N, O, nf), dtype=torch.float32, device=dev)
+                    for gi, (w, c) in enumerate(group):
+                        base = ((window_base + w) * n_chunks + c) * (V * S)
+                        _lib.check(lib.upd_gauss_fill(_lib.ptr(z[gi * V * S:(gi + 1) * V * S]), V * S, O * nf,
+                                                      seed & (2 ** 64 - 1), base, i, st), "upd_gauss_fill")
+                    return z
+
+                y = torch.sqrt(gx) * draw(0) + y0                                   # nsdiff_utils.py:273-274
+                nxt = torch.empty_like(y)
+                for i, t in enumerate(reversed(range(T))):
+                    xin = torch.cat((y, y0, gx), dim=-1).transpose(1, 2).contiguous()
+                    e = net.trunk(xin, t, rowptr, col, V).contiguous()
+                    z = draw(i + 1) if t > 0 else None
+                    rc = lib.upd_nsx_step(_lib.ptr(e), *[_lib.ptr(h) for h in heads], _lib.ptr(y), _lib.ptr(y0),
+                                          _lib.ptr(gx), _lib.ptr(z), _lib.ptr(sched), T, t, N, e.shape[1], O, nf,
+                                          _lib.ptr(nxt), None, None, st)
+                    _lib.check(rc, "upd_nsx_step")
+                    y, nxt = nxt, y
+                res = y.view(len(group), V, S, O, nf)
+                for gi, (w, c) in enumerate(group):
+                    out[w, :, c * S:(c + 1) * S] = res[gi]
+        return out.reshape(W * V, K, O, nf)
+
+    def evaluation_step(self, gdata, noise=None, y_0_hat=None):
+        """NsDiff_model.py:695-790 for a single graph -> (outs [Node, O, F, K] on the CPU, a permuted view of contiguous
+        [Node, K, O, F]; batch_y or None)."""
+        batch = gdata.x
+        if batch.shape[1] - self.windows >= self.pred_len:
+            batch_y = batch[:, self.windows:, :].to(self.device)
+            assert batch_y.size(1) == self.pred_len, "pred_len is not equal to the length of the prediction"
+        else:
+            batch_y = None
+        edge_index = gdata.edge_index.reshape(2, -1)
+        traj = self.sample_windows(batch.unsqueeze(0), edge_index, int(gdata.num_nodes),
+                                   noise=None if noise is None else [noise], y_0_hat=y_0_hat)
+        outs = traj.cpu().permute(0, 2, 3, 1)
+        assert (outs.shape[1], outs.shape[2], outs.shape[3]) == (self.pred_len, self.dataset_nf,
+                                                                 (int(self.configs.n_z_samples) //
+                                                                  int(self.configs.parallel_sample)) *
+                                                                 int(self.configs.parallel_sample))
+        return outs, batch_y

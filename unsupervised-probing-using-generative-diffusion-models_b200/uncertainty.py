@@ -447,14 +447,14 @@ def sample_sweep(model, stacked_windows, device=None, pin=True, reduce=True, win
     With ``reduce`` the per-window MPV / mean statistics are computed on the device in the same pass
     (both in scaled units and, when the model has a scaler, in raw units) and remembered for the
     summarize_* functions; they are also returned as ``cache.upd_stats`` (dict of CPU tensors).
-    ``graph_data`` (DiffSTG only): object with ``edge_index`` / ``num_nodes``; every window, sampling round and
-    parallel replica is then a replica of that graph inside one launch (:369-391)."""
+    ``graph_data`` (DiffSTG, NsDiff_spatial): object with ``edge_index`` / ``num_nodes``; every window, sampling round
+    and parallel replica is then a replica of that graph inside one launch (:369-391)."""
     device = device or _model_device(model)
     W, B = stacked_windows.shape[0], stacked_windows.shape[1]
-    if graph_data is not None:
+    if graph_data is not None and hasattr(model, "parallel_sampling"):
         probe_k = int(model.parallel_sampling) * int(model.sequential_sampling)
         O, F = model.T_p, model.F
-    else:
+    else:                       # NsDiff / TMDM / DiffusionTS, and NsDiff_spatial when ``graph_data`` is given
         probe_k = _samples_per_row(model)
         O, F = model.pred_len, model.dataset_nf
     per_window = B * probe_k * O * F * 4
@@ -1256,7 +1256,7 @@ def distributed_sweep(model, stacked_windows, device=None, group=None, graph_dat
     W = stacked_windows.shape[0]
     w0, w1 = partition_windows(W, world, rank)
     device = device or _model_device(model)
-    F = model.F if graph_data is not None else model.dataset_nf
+    F = model.F if hasattr(model, "parallel_sampling") else model.dataset_nf
     start = getattr(model, "_windows_drawn", 0)
     if w1 > w0:
         cache = sample_sweep(model, stacked_windows[w0:w1], device=device, window_offset=w0, graph_data=graph_data)
