@@ -271,7 +271,8 @@ int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const 
  *   kernels (the image height is 1) with the shortcut (or identity) folded into tap 2; b1_dev [C] = conv bias +
  *   shortcut bias + t_conv(emb(step)); b2_dev [C]; gamma/beta [C].  Exactly one of hn_dev (fp32) and a3_dev (the row as the
  *   fp16 split operand [N, 3*C*T+8] of the down-sampling GEMM, see the f(x) section) is written; the other is NULL.  wsc_dev [C, CI] / sc_dev [N, C, T] (both or neither): the block's 1x1 shortcut W_sc x
- *   (ugnet.py:129) evaluated in the same pass.  Limits: C in {4, 8, 16}, T <= 512 and a multiple of 4. */
+ *   (ugnet.py:129) evaluated in the same pass.  Limits: C in {4, 8, 16}, T even (any length: a row is walked in
+ *   segments of 512 positions; T % 4 != 0 takes scalar global accesses). */
 int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
                    const float* gamma_dev, const float* beta_dev, long long N, int CI, int C, int T, float* hn_dev,
                    void* a3_dev, const float* wsc_dev, float* sc_dev, void* stream);
@@ -287,7 +288,7 @@ int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev,
 /* upd_fx_split -- A3(act(x)).  act: 0 none, 1 ReLU, 2 GELU (erf) = the feed-forward activation between conv1 and conv2
  *   (EncoderLayer/DecoderLayer of torch-timeseries as called at mu_backbone.py:70-104).  H > 1: x_dev is an attention
  *   output [B, H, L, K/H] and the row (b,l) gathers its heads (the `out.transpose(1,2).reshape(B, L, -1)` of
- *   AttentionLayer) -- rows = B*L.  K multiple of 4 (K/H too), K <= 1024. */
+ *   AttentionLayer) -- rows = B*L.  K multiple of 4 (K/H too), K <= 2^20. */
 int upd_fx_split(const float* x_dev, long long rows, int K, int H, int L, int act, void* a3_dev, void* stream);
 
 /* upd_fx_add_ln_split -- y = LayerNorm_2(LayerNorm_1(x + res)) (eps 1e-5; res, the second norm, y_dev or a3_dev may be

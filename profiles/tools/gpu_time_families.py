@@ -64,8 +64,10 @@ if which in ("stg", "both"):
     torch.manual_seed(0)
     win = (torch.randn(W, 100, 100, 1, device=DEV).cumsum(2) * 0.1)
     m.sample_windows(win[:1], ei, 100, seed=1, window_base=0)
+    t_first, _ = timed(lambda: m.sample_windows(win, ei, 100, seed=1, window_base=0))
     t, out = timed(lambda: m.sample_windows(win, ei, 100, seed=1, window_base=0))
     n_traj = out.shape[0] * out.shape[1]
+    print("STG first call at this shape: %.2f s (library heuristics for the new GEMM shapes)" % t_first)
     print("STG sample: %d node-trajectories (%d windows x 100 nodes x 100 samples) in %.2f s -> %.1f traj/s; finite %s; peak mem %.1f GB" % (n_traj, W, t, n_traj / t, bool(torch.isfinite(out).all()), torch.cuda.max_memory_allocated() / 2**30))
     if prof:
         from torch.profiler import profile, ProfilerActivity
@@ -89,11 +91,14 @@ if which in ("nsx", "both"):
     torch.manual_seed(0)
     win = 5.0 + (torch.randn(W, 100, 100, 1, device=DEV).cumsum(2) * 0.05)
     m.sample_windows(win[:1], ei, 100, seed=1, window_base=0)
+    t_first, _ = timed(lambda: m.sample_windows(win, ei, 100, seed=1, window_base=0))
     t, out = timed(lambda: m.sample_windows(win, ei, 100, seed=1, window_base=0))
     n_traj = out.shape[0] * out.shape[1]
+    print("NSX first call at this shape: %.2f s" % t_first)
     print("NSX sample: %d node-trajectories (%d windows x 100 nodes x 100 samples) in %.2f s -> %.1f traj/s; finite frac %.3f; peak mem %.1f GB" % (n_traj, W, t, n_traj / t, float(torch.isfinite(out).float().mean()), torch.cuda.max_memory_allocated() / 2**30))
     if prof:
         from torch.profiler import profile, ProfilerActivity
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as p:
             m.sample_windows(win[:1], ei, 100, seed=1, window_base=0); torch.cuda.synchronize()
         print(p.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+        print(p.key_averages().table(sort_by="self_cpu_time_total", row_limit=12, max_name_column_width=60))

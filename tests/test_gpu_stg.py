@@ -115,7 +115,8 @@ def test_gated_aggregate_kernel_against_oracle():
     assert _rel(out, ref) < 1e-5
 
 
-@pytest.mark.parametrize("C,CI,T", [(8, 4, 400), (16, 32, 200), (4, 12, 40), (16, 16, 20)])
+@pytest.mark.parametrize("C,CI,T", [(8, 4, 400), (16, 32, 200), (4, 12, 40), (16, 16, 20), (8, 4, 2000), (16, 32, 1200),
+                                    (16, 32, 50), (8, 16, 514), (4, 4, 6)])
 def test_fused_tcn_layernorm_kernel_against_library_ops(C, CI, T):
     """upd_stg_tcn_ln == causal conv -> causal conv -> LayerNorm over channels (torch fp32, TF32 off)."""
     import torch.nn.functional as F

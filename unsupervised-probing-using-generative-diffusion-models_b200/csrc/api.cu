@@ -389,7 +389,7 @@ int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev,
   if (!x_dev || !w1_dev || !b1_dev || !w2_dev || !b2_dev || !gamma_dev || !beta_dev || (!hn_dev && !a3_dev) || N <= 0 ||
       T <= 0)
     return UPD_ERR_BAD_ARG;
-  if ((C != 4 && C != 8 && C != 16) || CI < 1 || T > 512 || (T & 3) != 0) return UPD_ERR_UNSUPPORTED;
+  if ((C != 4 && C != 8 && C != 16) || CI < 1 || (T & 1) != 0) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_tcn_ln(x_dev, w1_dev, b1_dev, w2_dev, b2_dev, gamma_dev, beta_dev, N, CI, C, T, hn_dev, a3_dev,
                                    wsc_dev, sc_dev, (cudaStream_t)stream));

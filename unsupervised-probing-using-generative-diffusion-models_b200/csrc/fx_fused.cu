@@ -15,7 +15,8 @@
 
 namespace {
 
-constexpr int FX_MAX_K = 1024;
+constexpr int FX_MAX_K = 1024;            // widths with a LayerNorm or an embedding row held in registers
+constexpr int FX_SPLIT_MAX_K = 1 << 20;   // the plain split streams its row
 
 __device__ __forceinline__ float fx_act(float v, int act) {
   if (act == 1) return fmaxf(v, 0.0f);
@@ -211,7 +212,7 @@ __global__ void fx_embed_split_kernel(const float* __restrict__ x, const float* 
 
 cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, int L, int act, void* a3,
                                 cudaStream_t stream) {
-  if (K < 4 || K > FX_MAX_K || (K & 3) || H < 1 || (K % H) || ((K / H) & 3) || (H > 1 && (L < 1 || rows % L)))
+  if (K < 4 || K > FX_SPLIT_MAX_K || (K & 3) || H < 1 || (K % H) || ((K / H) & 3) || (H > 1 && (L < 1 || rows % L)))
     return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(a3) & 15)) return cudaErrorInvalidValue;
   const int wpb = 8;

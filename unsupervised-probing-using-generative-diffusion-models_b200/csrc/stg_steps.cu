@@ -56,9 +56,11 @@ __global__ void stg_gated_aggregate_kernel(const float* __restrict__ kqvs, const
 //     h1 = causal_conv3(x) + b1[step]     (TcnBlock 1: conv + 1x1 shortcut folded into tap 2, + t_conv(time emb))
 //     h2 = causal_conv3(h1) + b2          (TcnBlock 2, identity shortcut folded)
 //     hn = LayerNorm_c(h2) * g + beta     (nn.LayerNorm([1, c]) over the channel axis, eps 1e-5)
-// x [N, CI, T] -> hn [N, C, T].  One CTA per row; x and h1 live in shared memory with a 2-column zero halo on the
-// left (both convolutions are causal and zero-padded); each thread owns 4 consecutive positions x all C channels in
-// registers, so the LayerNorm needs no cross-thread reduction and the store is one float4 per channel.
+// x [N, CI, T] -> hn [N, C, T].  One CTA per row (or 8 rows); the row is walked in segments of TT = 4*blockDim positions:
+// x and h1 of a segment live in shared memory behind 4 halo columns -- zero at the start of a row (both convolutions
+// are causal and zero-padded), else the last 4 columns of the previous segment.  Each thread owns 4 consecutive
+// positions x all C channels in registers, so the LayerNorm needs no cross-thread reduction and the store is one
+// float4 per channel (scalar loads / stores when T is not a multiple of 4: the global rows are then only 8-byte aligned).
 // fp32 FFMA: C <= 16 channels is far below a tensor-core tile, and the pass is 3 B/FLOP away from HBM-bound.
 // ------------------------------------------------------------------------------------------------------
 template <int C>
@@ -70,8 +72,9 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
                                                          __half* __restrict__ a3, const float* __restrict__ wsc,
                                                          float* __restrict__ sc_out) {
   extern __shared__ __align__(16) float smem[];
-  const int TP = T + 4;                              // row pitch: data starts at column 4 (16-byte aligned, T % 4 == 0),
-                                                     // columns 0..3 are zero: the halo of the causal convolutions
+  const int TT = (T <= 4 * (int)blockDim.x) ? ((T + 3) & ~3) : 4 * (int)blockDim.x;   // positions per segment
+  const int TP = TT + 4;                             // row pitch: data starts at column 4 (16-byte aligned),
+                                                     // columns 0..3 are the halo of the causal convolutions
   float* sx = smem;                                  // [CI][TP]
   float* sh = sx + CI * TP;                          // [C][TP]
   float* sw1 = sh + C * TP;                          // [CI][3][C]  (tap-major inside a channel, channels contiguous)
@@ -88,18 +91,34 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
   }
   if (wsc)
     for (int i = threadIdx.x; i < CI * C; i += blockDim.x) swsc[i] = wsc[(i % C) * CI + i / C];       // [C][CI] -> [CI][C]
-  for (int i = threadIdx.x; i < (CI + C) * 4; i += blockDim.x) sx[(i >> 2) * TP + (i & 3)] = 0.0f;   // halos of sx and sh
-  const int t0 = threadIdx.x * 4;                    // first of this thread's 4 positions
-  const bool active = t0 < T;
-  const int T4 = T >> 2;
+  const int t0 = threadIdx.x * 4;                    // first of this thread's 4 positions inside a segment
+  const bool vec = (T & 3) == 0;
+  const int Q = TT >> 2;
   for (int rr = 0; rr < rows_per_cta; ++rr) {
     const long long n = (long long)blockIdx.x * rows_per_cta + rr;
     if (n >= N) break;
-    __syncthreads();                                 // previous row's readers of sx / sh are done
     const float* xr = x + n * (long long)CI * T;
-    for (int i = threadIdx.x; i < CI * T4; i += blockDim.x) {
-      const int ci = i / T4, q = i - ci * T4;
-      *reinterpret_cast<float4*>(sx + ci * TP + 4 + 4 * q) = *reinterpret_cast<const float4*>(xr + ci * T + 4 * q);
+   for (int tb = 0; tb < T; tb += TT) {
+    const bool active = tb + t0 < T;
+    __syncthreads();                                 // previous segment's / row's readers of sx / sh are done
+    for (int i = threadIdx.x; i < (CI + C) * 4; i += blockDim.x) {   // halos of sx and sh (contiguous: CI + C rows)
+      float* r = sx + (i >> 2) * TP + (i & 3);
+      *r = tb == 0 ? 0.0f : r[TT];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < CI * Q; i += blockDim.x) {
+      const int ci = i / Q, q = i - ci * Q, t = tb + 4 * q;
+      float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      const float* src = xr + (long long)ci * T + t;
+      if (vec) {
+        if (t < T) v = *reinterpret_cast<const float4*>(src);
+      } else {
+        if (t < T) v.x = src[0];
+        if (t + 1 < T) v.y = src[1];
+        if (t + 2 < T) v.z = src[2];
+        if (t + 3 < T) v.w = src[3];
+      }
+      *reinterpret_cast<float4*>(sx + ci * TP + 4 + 4 * q) = v;
     }
     __syncthreads();
     float acc[4][C];
@@ -162,6 +181,7 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
           }
         }
     }
+    const int tg = tb + t0;                          // global position of this thread's quad
     float* out = hn + n * (long long)C * T;
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
@@ -178,8 +198,15 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
     }
     if (a3 == nullptr) {
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        *reinterpret_cast<float4*>(out + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      for (int c = 0; c < C; ++c) {
+        if (vec) {
+          *reinterpret_cast<float4*>(out + c * T + tg) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (tg + p < T) out[c * T + tg + p] = acc[p][c];
+        }
+      }
     } else {
       // the row as the split operand [hi | lo | hi | 1 1 0..] (K = C*T) of the fp16 tensor-core GEMM that follows
       const int K = C * T;
@@ -193,12 +220,24 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
         uint2 hi, lo;
         hi.x = *reinterpret_cast<uint32_t*>(&h01); hi.y = *reinterpret_cast<uint32_t*>(&h23);
         lo.x = *reinterpret_cast<uint32_t*>(&l01); lo.y = *reinterpret_cast<uint32_t*>(&l23);
-        const int col = c * T + t0;
-        *reinterpret_cast<uint2*>(row + col) = hi;
-        *reinterpret_cast<uint2*>(row + K + col) = lo;
-        *reinterpret_cast<uint2*>(row + 2 * K + col) = hi;
+        const int col = c * T + tg;
+        if (vec) {
+          *reinterpret_cast<uint2*>(row + col) = hi;
+          *reinterpret_cast<uint2*>(row + K + col) = lo;
+          *reinterpret_cast<uint2*>(row + 2 * K + col) = hi;
+        } else {
+          const __half hv4[4] = {__low2half(h01), __high2half(h01), __low2half(h23), __high2half(h23)};
+          const __half lv4[4] = {__low2half(l01), __high2half(l01), __low2half(l23), __high2half(l23)};
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (tg + p < T) {
+              row[col + p] = hv4[p];
+              row[K + col + p] = lv4[p];
+              row[2 * K + col + p] = hv4[p];
+            }
+        }
       }
-      if (threadIdx.x == 0) *reinterpret_cast<uint4*>(row + 3 * K) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+      if (threadIdx.x == 0 && tb == 0) *reinterpret_cast<uint4*>(row + 3 * K) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
     }
     if (wsc) {
       // the block's 1x1 shortcut W_sc x (ugnet.py:129, c_in != c_out) while x is still in shared memory: it becomes the
@@ -225,9 +264,17 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
       }
       float* so = sc_out + n * (long long)C * T;
 #pragma unroll
-      for (int c = 0; c < C; ++c)
-        *reinterpret_cast<float4*>(so + c * T + t0) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+      for (int c = 0; c < C; ++c) {
+        if (vec) {
+          *reinterpret_cast<float4*>(so + c * T + tg) = make_float4(acc[0][c], acc[1][c], acc[2][c], acc[3][c]);
+        } else {
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+            if (tg + p < T) so[c * T + tg + p] = acc[p][c];
+        }
+      }
     }
+   }
   }
 }
 
@@ -294,11 +341,13 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
 cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
                                   void* a3, const float* wsc, float* sc_out, cudaStream_t stream) {
-  const int threads = ((T / 4) + 31) / 32 * 32;
-  if ((T & 3) != 0 || threads > 128 || CI < 1 || N > 0x7fffffffLL) return cudaErrorInvalidValue;
+  int threads = ((T + 3) / 4 + 31) / 32 * 32;          // one segment of 4*threads positions at a time
+  if (threads > 128) threads = 128;
+  if ((T & 1) != 0 || T < 2 || CI < 1 || N > 0x7fffffffLL) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(hn) & 15) != 0 || (reinterpret_cast<uintptr_t>(a3) & 15) != 0) return cudaErrorInvalidValue;
   if (hn == nullptr && a3 == nullptr) return cudaErrorInvalidValue;
-  const size_t smem = sizeof(float) * ((size_t)(CI + C) * (T + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C + (size_t)CI * C);
+  const int seg = T <= 4 * threads ? ((T + 3) & ~3) : 4 * threads;
+  const size_t smem = sizeof(float) * ((size_t)(CI + C) * (seg + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C + (size_t)CI * C);
   if ((wsc == nullptr) != (sc_out == nullptr) || (reinterpret_cast<uintptr_t>(sc_out) & 15) != 0) return cudaErrorInvalidValue;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorInvalidValue;

@@ -301,7 +301,7 @@ class PreparedUGnet:
         """tcn1 (+ step embedding) -> tcn2 -> LayerNorm over channels: x [N, c_in, T] -> hn [N, c_out*T] fp32, or -- when
         ``as_operand`` -- directly the fp16 split operand [N, 3*c_out*T+8] of the down-sampling GEMM."""
         N = x.shape[0]
-        if c_out in (4, 8, 16) and T_in % 4 == 0 and T_in <= 512:
+        if c_out in (4, 8, 16) and T_in % 2 == 0:
             K = c_out * T_in
             hn = None if as_operand else torch.empty((N, K), dtype=torch.float32, device=x.device)
             a3 = torch.empty((N, 3 * K + 8), dtype=torch.float16, device=x.device) if as_operand else None
