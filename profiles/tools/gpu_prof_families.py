@@ -1,5 +1,6 @@
-"""Short DiffSTG / DiffusionTS step for ncu: 2 DiffSTG denoise steps on 16384 replica rows, one DiffusionTS loop
-iteration (t = 99 -> 98: x0 prediction, DDIM mean, 3 Langevin iterations, infill) on 1000 rows."""
+"""Short DiffSTG / DiffusionTS / NsDiff_spatial steps for ncu: 2 DiffSTG denoise steps on 16384 replica rows, one DiffusionTS
+loop iteration (t = 99 -> 98: x0 prediction, DDIM mean, 3 Langevin iterations, infill) on 1000 rows, then f(x) + g(x) and a
+2-step NsDiff_spatial chain on 16000 replica rows."""
 import json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -34,3 +35,16 @@ gen = torch.Generator(device=DEV).manual_seed(0)
 img = d._sample_rows(tgt, 1000, lambda i, shape: torch.randn(shape, device=DEV, generator=gen))
 torch.cuda.synchronize()
 print("dts ok", tuple(img.shape), bool(torch.isfinite(img).all()))
+
+from updgm_b200.nsdiff_spatial import NsDiff_model_spatial
+g = np.load("tests/golden/nsx_yaml_evalstep.npz"); cfg = json.loads(str(g["cfg"]))
+cfg = dict(cfg, n_z_samples=80, parallel_sample=10, diffusion_steps=2)
+torch.manual_seed(123)
+x = NsDiff_model_spatial(dict(cfg, device=DEV), "NsDiff_model").eval()
+with torch.no_grad():
+    x.scaler_std.fill_(1.0)
+x.rows_per_launch = 16000
+win = 5.0 + torch.randn(2, 100, 100, 1, device=DEV).cumsum(2) * 0.05
+out = x.sample_windows(win, ei, 100, seed=1, window_base=0)
+torch.cuda.synchronize()
+print("nsx ok", tuple(out.shape), bool(torch.isfinite(out).all()))

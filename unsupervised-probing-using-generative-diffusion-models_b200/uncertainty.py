@@ -1248,7 +1248,7 @@ def distributed_sweep(model, stacked_windows, device=None, group=None, graph_dat
     """Sweep sharded over the ranks of ``group``: rank r samples its contiguous block of windows (Philox
     keys use the global window index, so the union equals the single-GPU sweep), reduces it on its GPU,
     and the ranks exchange only [W, 2+F] floats.  Returns (local_cache [w1-w0,B,K,O,F], (w0,w1), stats) with
-    stats = dict(mpv [W], pred_mean [W], mpv_f [W,F]) identical on every rank.  ``graph_data``: DiffSTG only (windows and
+    stats = dict(mpv [W], pred_mean [W], mpv_f [W,F]) identical on every rank.  ``graph_data``: DiffSTG / NsDiff_spatial (windows and
     sample replicas shard; nodes are coupled by the graph conv and do not)."""
     import torch.distributed as dist
 
