@@ -147,3 +147,37 @@ def test_fused_tcn_layernorm_kernel_against_library_ops(C, CI, T):
     assert _rel(val, ref.reshape(N, K)) < 2e-5
     assert _lib.lib().upd_stg_tcn_ln(_lib.ptr(x), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), _lib.ptr(g),
                                      _lib.ptr(be), N, CI, 5, T, _lib.ptr(out), None, None, None, None) == 2      # UPD_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("C,CI,T,N", [(16, 32, 50, 9), (8, 16, 514, 5), (4, 4, 6, 3), (8, 4, 2000, 4), (16, 16, 1028, 8200)])
+def test_fused_tcn_kernel_writes_stay_inside_their_buffers(C, CI, T, N):
+    """Own bounds check (no sanitizer on this pool): every output sits between sentinel guard bands that must survive, for the
+    scalar (T % 4 != 0), segmented (T > 512) and 8-rows-per-CTA (N >= 8192) paths."""
+    from updgm_b200 import _lib
+    torch.manual_seed(T)
+    G = 256
+    x = torch.randn(N, CI, T, device=DEV)
+    w1, b1 = torch.randn(C, CI, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
+    w2, b2 = torch.randn(C, C, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
+    g, be, wsc = torch.randn(C, device=DEV), torch.randn(C, device=DEV), torch.randn(C, CI, device=DEV)
+    K = C * T
+
+    def guarded(n, dtype):
+        buf = torch.full((n + 2 * G,), 777.0, dtype=dtype, device=DEV)
+        return buf, buf[G:G + n]
+
+    hn_buf, hn = guarded(N * K, torch.float32)
+    sc_buf, sc = guarded(N * K, torch.float32)
+    a3_buf, a3 = guarded(N * (3 * K + 8), torch.float16)
+    st = _lib.stream_ptr(torch.device(DEV))
+    args = [_lib.ptr(v) for v in (x, w1, b1, w2, b2, g, be)]
+    _lib.check(_lib.lib().upd_stg_tcn_ln(*args, N, CI, C, T, _lib.ptr(hn), None, _lib.ptr(wsc), _lib.ptr(sc), st), "tcn")
+    _lib.check(_lib.lib().upd_stg_tcn_ln(*args, N, CI, C, T, None, _lib.ptr(a3), None, None, st), "tcn")
+    torch.cuda.synchronize()
+    for buf in (hn_buf, sc_buf, a3_buf):
+        assert bool((buf[:G] == 777.0).all()) and bool((buf[-G:] == 777.0).all())
+    assert not bool((hn == 777.0).any()) and torch.isfinite(hn).all() and torch.isfinite(sc).all()
+    row = a3.view(N, 3 * K + 8)
+    assert _rel(row[:, :K].float() + row[:, K:2 * K].float(), hn.view(N, K)) < 2e-5
+    assert float(row[:, 3 * K].min()) == 1.0 and float(row[:, 3 * K + 2:].abs().max()) == 0.0
+    assert _rel(sc.view(N, C, T), torch.matmul(wsc, x)) < 1e-5
