@@ -277,6 +277,13 @@ int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev,
                    const float* gamma_dev, const float* beta_dev, long long N, int CI, int C, int T, float* hn_dev,
                    void* a3_dev, const float* wsc_dev, float* sc_dev, void* stream);
 
+/* upd_stg_tcn_ln_cat -- upd_stg_tcn_ln on the channel concatenation cat(x_dev [N, CI1, T], x2_dev [N, CI2, T]) of the
+ *   U-Net's up path (`x = torch.cat((x, s), dim=1)`, models/Diffusion_model/DiffSTG/ugnet.py:288-289), read from the two
+ *   tensors in place; w1_dev [C, CI1+CI2, 3], wsc_dev [C, CI1+CI2].  Same limits. */
+int upd_stg_tcn_ln_cat(const float* x_dev, int CI1, const float* x2_dev, int CI2, const float* w1_dev, const float* b1_dev,
+                       const float* w2_dev, const float* b2_dev, const float* gamma_dev, const float* beta_dev, long long N,
+                       int C, int T, float* hn_dev, void* a3_dev, const float* wsc_dev, float* sc_dev, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * f(x) condition encoder (ns-Transformer; models/Diffusion_model/NsDiff/mu_backbone.py:53-183,
  * TMDM/tmdm_ns_transformer.py:40-174; blocks from torch-timeseries 0.1.10 -- parity unpinned).

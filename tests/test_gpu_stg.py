@@ -181,3 +181,29 @@ def test_fused_tcn_kernel_writes_stay_inside_their_buffers(C, CI, T, N):
     assert _rel(row[:, :K].float() + row[:, K:2 * K].float(), hn.view(N, K)) < 2e-5
     assert float(row[:, 3 * K].min()) == 1.0 and float(row[:, 3 * K + 2:].abs().max()) == 0.0
     assert _rel(sc.view(N, C, T), torch.matmul(wsc, x)) < 1e-5
+
+
+@pytest.mark.parametrize("C,CI1,CI2,T,N", [(16, 16, 16, 200, 33), (8, 16, 8, 50, 7), (4, 8, 4, 1200, 5)])
+def test_fused_tcn_kernel_reads_a_skip_concatenation_in_place(C, CI1, CI2, T, N):
+    """upd_stg_tcn_ln_cat(x1, x2) == upd_stg_tcn_ln(cat(x1, x2)) bit for bit (same arithmetic, two source tensors)."""
+    from updgm_b200 import _lib
+    torch.manual_seed(CI1 * 100 + T)
+    CI = CI1 + CI2
+    x1, x2 = torch.randn(N, CI1, T, device=DEV), torch.randn(N, CI2, T, device=DEV)
+    w1, b1 = torch.randn(C, CI, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
+    w2, b2 = torch.randn(C, C, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
+    g, be, wsc = torch.randn(C, device=DEV), torch.randn(C, device=DEV), torch.randn(C, CI, device=DEV)
+    st = _lib.stream_ptr(torch.device(DEV))
+    tail = [_lib.ptr(v) for v in (w1, b1, w2, b2, g, be)]
+    K = C * T
+    ref_hn, ref_sc, hn, sc = (torch.empty(N, K, device=DEV) for _ in range(4))
+    ref_a3, a3 = (torch.empty(N, 3 * K + 8, dtype=torch.float16, device=DEV) for _ in range(2))
+    xc = torch.cat((x1, x2), dim=1).contiguous()
+    L = _lib.lib()
+    _lib.check(L.upd_stg_tcn_ln(_lib.ptr(xc), *tail, N, CI, C, T, _lib.ptr(ref_hn), None, _lib.ptr(wsc), _lib.ptr(ref_sc), st), "a")
+    _lib.check(L.upd_stg_tcn_ln(_lib.ptr(xc), *tail, N, CI, C, T, None, _lib.ptr(ref_a3), None, None, st), "b")
+    _lib.check(L.upd_stg_tcn_ln_cat(_lib.ptr(x1), CI1, _lib.ptr(x2), CI2, *tail, N, C, T, _lib.ptr(hn), None, _lib.ptr(wsc),
+                                    _lib.ptr(sc), st), "c")
+    _lib.check(L.upd_stg_tcn_ln_cat(_lib.ptr(x1), CI1, _lib.ptr(x2), CI2, *tail, N, C, T, None, _lib.ptr(a3), None, None, st), "d")
+    assert torch.equal(hn, ref_hn) and torch.equal(sc, ref_sc) and torch.equal(a3, ref_a3)
+    assert L.upd_stg_tcn_ln_cat(_lib.ptr(x1), CI1, None, CI2, *tail, N, C, T, _lib.ptr(hn), None, None, None, st) == 1   # bad arg

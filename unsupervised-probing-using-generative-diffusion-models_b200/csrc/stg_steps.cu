@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
                                                          const float* __restrict__ beta, long long N, int CI, int T,
                                                          int rows_per_cta, float* __restrict__ hn,
                                                          __half* __restrict__ a3, const float* __restrict__ wsc,
-                                                         float* __restrict__ sc_out) {
+                                                         float* __restrict__ sc_out, const float* __restrict__ x2, int CI1) {
+  // x2 != nullptr: the input is the channel concatenation of x [N, CI1, T] and x2 [N, CI - CI1, T] (U-Net skip connection,
+  // ugnet.py:288-289) read from the two tensors in place
   extern __shared__ __align__(16) float smem[];
   const int TT = (T <= 4 * (int)blockDim.x) ? ((T + 3) & ~3) : 4 * (int)blockDim.x;   // positions per segment
   const int TP = TT + 4;                             // row pitch: data starts at column 4 (16-byte aligned),
@@ -97,7 +99,8 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
   for (int rr = 0; rr < rows_per_cta; ++rr) {
     const long long n = (long long)blockIdx.x * rows_per_cta + rr;
     if (n >= N) break;
-    const float* xr = x + n * (long long)CI * T;
+    const float* xr = x + n * (long long)CI1 * T;
+    const float* xr2 = x2 ? x2 + n * (long long)(CI - CI1) * T : nullptr;
    for (int tb = 0; tb < T; tb += TT) {
     const bool active = tb + t0 < T;
     __syncthreads();                                 // previous segment's / row's readers of sx / sh are done
@@ -109,7 +112,7 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
     for (int i = threadIdx.x; i < CI * Q; i += blockDim.x) {
       const int ci = i / Q, q = i - ci * Q, t = tb + 4 * q;
       float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      const float* src = xr + (long long)ci * T + t;
+      const float* src = (ci < CI1 ? xr + (long long)ci * T : xr2 + (long long)(ci - CI1) * T) + t;
       if (vec) {
         if (t < T) v = *reinterpret_cast<const float4*>(src);
       } else {
@@ -340,7 +343,8 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
 
 cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
-                                  void* a3, const float* wsc, float* sc_out, cudaStream_t stream) {
+                                  void* a3, const float* wsc, float* sc_out, const float* x2, int CI2, cudaStream_t stream) {
+  if ((x2 == nullptr) != (CI2 == 0) || CI2 < 0 || CI2 >= CI || (reinterpret_cast<uintptr_t>(x2) & 15) != 0) return cudaErrorInvalidValue;
   int threads = ((T + 3) / 4 + 31) / 32 * 32;          // one segment of 4*threads positions at a time
   if (threads > 128) threads = 128;
   if ((T & 1) != 0 || T < 2 || CI < 1 || N > 0x7fffffffLL) return cudaErrorInvalidValue;
@@ -357,7 +361,7 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
   case CC: {                                                                                                         \
     cudaError_t e = cudaFuncSetAttribute(stg_tcn_ln_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
     if (e != cudaSuccess) return e;                                                                                  \
-    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn, (__half*)a3, wsc, sc_out); \
+    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn, (__half*)a3, wsc, sc_out, x2, CI - CI2); \
     break;                                                                                                           \
   }
   switch (C) {

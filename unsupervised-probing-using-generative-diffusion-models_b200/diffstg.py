@@ -299,21 +299,33 @@ class PreparedUGnet:
 
     def _front(self, b, x, t, c_in, c_out, T_in, as_operand):
         """tcn1 (+ step embedding) -> tcn2 -> LayerNorm over channels: x [N, c_in, T] -> hn [N, c_out*T] fp32, or -- when
-        ``as_operand`` -- directly the fp16 split operand [N, 3*c_out*T+8] of the down-sampling GEMM."""
+        ``as_operand`` -- directly the fp16 split operand [N, 3*c_out*T+8] of the down-sampling GEMM.  ``x`` may be a pair
+        (x, skip): the up path's channel concatenation, which the kernel reads from the two tensors in place."""
+        pair = x if isinstance(x, tuple) else None
+        if pair is not None:
+            x = pair[0]
         N = x.shape[0]
         if c_out in (4, 8, 16) and T_in % 2 == 0:
             K = c_out * T_in
             hn = None if as_operand else torch.empty((N, K), dtype=torch.float32, device=x.device)
             a3 = torch.empty((N, 3 * K + 8), dtype=torch.float16, device=x.device) if as_operand else None
             sc = torch.empty((N, K), dtype=torch.float32, device=x.device) if c_in != c_out else None
-            rc = _lib.lib().upd_stg_tcn_ln(_lib.ptr(x.contiguous()), _lib.ptr(b["tcn1.w"]), _lib.ptr(b["tcn1.b_step"][t]),
-                                           _lib.ptr(b["tcn2.w"]), _lib.ptr(b["tcn2.b"]), _lib.ptr(b["norm_w"]),
-                                           _lib.ptr(b["norm_b"]), N, c_in, c_out, T_in, _lib.ptr(hn), _lib.ptr(a3),
-                                           None if sc is None else _lib.ptr(b["sc_w2"]), _lib.ptr(sc),
-                                           _lib.stream_ptr(x.device))
-            _lib.check(rc, "upd_stg_tcn_ln")
+            tail = (_lib.ptr(b["tcn1.w"]), _lib.ptr(b["tcn1.b_step"][t]), _lib.ptr(b["tcn2.w"]), _lib.ptr(b["tcn2.b"]),
+                    _lib.ptr(b["norm_w"]), _lib.ptr(b["norm_b"]))
+            outs = (_lib.ptr(hn), _lib.ptr(a3), None if sc is None else _lib.ptr(b["sc_w2"]), _lib.ptr(sc),
+                    _lib.stream_ptr(x.device))
+            if pair is None:
+                rc = _lib.lib().upd_stg_tcn_ln(_lib.ptr(x.contiguous()), *tail, N, c_in, c_out, T_in, *outs)
+                _lib.check(rc, "upd_stg_tcn_ln")
+            else:
+                x1, x2 = pair[0].contiguous(), pair[1].contiguous()
+                rc = _lib.lib().upd_stg_tcn_ln_cat(_lib.ptr(x1), x1.shape[1], _lib.ptr(x2), x2.shape[1], *tail, N, c_out, T_in,
+                                                   *outs)
+                _lib.check(rc, "upd_stg_tcn_ln_cat")
             return (a3 if as_operand else hn), sc
         # shapes outside the fused kernel's limits: the same arithmetic as library ops
+        if pair is not None:
+            x = torch.cat(pair, dim=1)
         h = F.conv1d(F.pad(x, (2, 0)), b["tcn1.w"], b["tcn1.b_step"][t])
         h = F.conv1d(F.pad(h, (2, 0)), b["tcn2.w"], b["tcn2.b"])
         var, mu = torch.var_mean(h, dim=1, unbiased=False, keepdim=True)
@@ -326,12 +338,12 @@ class PreparedUGnet:
         fp16 tensor-core GEMMs (fx_encoder.gemm3: [x_hi | x_lo | x_hi | 1 1 0..] x [W_hi | W_hi | W_lo | b..]^T, 3e-6
         accuracy) when their widths allow it, else as fp32 library GEMMs."""
         b, Td = self.blocks[pre], self.Td_h
-        N = x.shape[0]
+        N = x[0].shape[0] if isinstance(x, tuple) else x.shape[0]
         C = Td * c_out
         tc_ok = b["down_w3"] is not None
         front, sc = self._front(b, x, t, c_in, c_out, T_in, tc_ok)
-        if sc is None:
-            sc = x.reshape(N, c_out * T_in)                                                     # identity shortcut
+        if sc is None:                                                                          # identity shortcut
+            sc = (torch.cat(x, dim=1) if isinstance(x, tuple) else x).reshape(N, c_out * T_in)
         if tc_ok:
             sp = gemm3(front, b["down_w3"], C)                                                  # [N, Td*c]
             kqvs = gemm3(a3_split(sp.contiguous()), b["kqvs_w3"], 4 * C)                        # [N, 4C]
@@ -351,12 +363,14 @@ class PreparedUGnet:
         x = torch.cat((xt.transpose(1, 2), x_masked.transpose(1, 2)), dim=-1)                # [N, F, 2T]
         return self.trunk(x, t, rowptr, col, V).transpose(1, 2).contiguous()
 
-    def trunk(self, x, t, rowptr, col, V):
-        """x [N, C_in, T_total] -> the out block's result [N, C_out, T_out]; t: index into the step-embedding table."""
+    def trunk(self, x, t, rowptr, col, V, projected=False):
+        """x [N, C_in, T_total] (or, with ``projected``, already x_proj(x) [N, d_h, T_total]) -> the out block's result
+        [N, C_out, T_out]; t: index into the step-embedding table."""
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             # the 1x1 projections are plain matmuls (cuDNN's heuristic picks an FFT algorithm for some of these shapes:
             # 30 ms per call at [10^4, 3, 100])
-            x = torch.matmul(self.xproj_w[:, :, 0], x) + self.xproj_b[None, :, None]
+            if not projected:
+                x = torch.matmul(self.xproj_w[:, :, 0], x) + self.xproj_b[None, :, None]
             hs = [x]
 
             def run(blk, x):
@@ -374,9 +388,7 @@ class PreparedUGnet:
             for blk in self.middle:
                 x = run(blk, x)
             for blk in self.up:
-                if blk[1] != "upsample":
-                    x = torch.cat((x, hs.pop()), dim=1)
-                x = run(blk, x)
+                x = run(blk, x if blk[1] == "upsample" else (x, hs.pop()))      # (x, skip): concatenated inside the kernel
             e = torch.matmul(self.out0_w[:, :, 0], x) + self.out0_b[None, :, None]
             return F.linear(e, self.out1_w, self.out1_b)
 
@@ -529,11 +541,12 @@ class DiffSTG(nn.Module):
                     if noise is not None:
                         parts = [noise[w][k // P_][i][(k % P_) * V:(k % P_ + 1) * V] for (w, k) in group]
                         return torch.cat(parts, 0).to(dev, torch.float32).contiguous()
+                    # replicas of a group are consecutive (window, sample) pairs, so their Philox row keys
+                    # ((window_base + w)*K + k)*V + v are one contiguous range: one launch fills the whole group
                     z = torch.empty((N, T, nf), dtype=torch.float32, device=dev)
-                    for gi, (w, k) in enumerate(group):
-                        base = ((window_base + w) * K + k) * V
-                        _lib.check(lib.upd_gauss_fill(_lib.ptr(z[gi * V:(gi + 1) * V]), V, T * nf,
-                                                      seed & (2 ** 64 - 1), base, i, st), "upd_gauss_fill")
+                    w_first, k_first = group[0]
+                    base = ((window_base + w_first) * K + k_first) * V
+                    _lib.check(lib.upd_gauss_fill(_lib.ptr(z), N, T * nf, seed & (2 ** 64 - 1), base, i, st), "upd_gauss_fill")
                     return z
 
                 i_draw = 0

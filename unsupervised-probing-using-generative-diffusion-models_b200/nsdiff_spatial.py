@@ -119,8 +119,8 @@ class NsTransformerSpatial(NsTransformer):
         return h.transpose(1, 2).contiguous()
 
     def forward(self, x_enc, x_dec, edge_index=None, *unused):
-        if edge_index is not None:
-            V = self._graph[2] if self._graph is not None else x_enc.shape[0]
+        if edge_index is not None:              # the reference's call: the rows of x_enc are the nodes of this graph
+            V = x_enc.shape[0]
             rowptr, col = graph_csr(edge_index, V)
             self.set_graph(rowptr.to(x_enc.device), col.to(x_enc.device), V)
         return super().forward(x_enc, x_dec)
@@ -317,9 +317,10 @@ class NsDiff_model_spatial(nn.Module):
         out = torch.empty((W, V, K, O, nf), dtype=torch.float32, device=dev)
         with torch.no_grad(), torch.cuda.device(dev):
             st = _lib.stream_ptr(dev)
-            y0_all, gx_all = self.condition(x, rowptr, col, V)
-            if y_0_hat is not None:
-                y0_all = y_0_hat.to(dev, torch.float32).contiguous()
+            if y_0_hat is None:
+                y0_all, gx_all = self.condition(x, rowptr, col, V)
+            else:
+                y0_all, gx_all = y_0_hat.to(dev, torch.float32).contiguous(), self.cond_pred_model_g(x).contiguous()
             y0_all, gx_all = y0_all.view(W, V, O, nf), gx_all.view(W, V, O, nf)
             units = [(w, c) for w in range(W) for c in range(n_chunks)]          # unit = one chunk of one window
             per = max(1, self.rows_per_launch // (V * S))
@@ -334,18 +335,23 @@ class NsDiff_model_spatial(nn.Module):
                 def draw(i):
                     if noise is not None:
                         return torch.cat([noise[w][c][i] for (w, c) in group], 0).to(dev, torch.float32).contiguous()
+                    # units of a group are consecutive (window, chunk) pairs, so their Philox row keys
+                    # ((window_base + w)*n_chunks + c)*(V*S) + row are one contiguous range: one launch per draw
                     z = torch.empty((N, O, nf), dtype=torch.float32, device=dev)
-                    for gi, (w, c) in enumerate(group):
-                        base = ((window_base + w) * n_chunks + c) * (V * S)
-                        _lib.check(lib.upd_gauss_fill(_lib.ptr(z[gi * V * S:(gi + 1) * V * S]), V * S, O * nf,
-                                                      seed & (2 ** 64 - 1), base, i, st), "upd_gauss_fill")
+                    w_first, c_first = group[0]
+                    base = ((window_base + w_first) * n_chunks + c_first) * (V * S)
+                    _lib.check(lib.upd_gauss_fill(_lib.ptr(z), N, O * nf, seed & (2 ** 64 - 1), base, i, st), "upd_gauss_fill")
                     return z
 
                 y = torch.sqrt(gx) * draw(0) + y0                                   # nsdiff_utils.py:273-274
                 nxt = torch.empty_like(y)
+                # x_proj(cat(y_t, f(x), g(x))): the f(x) / g(x) columns do not change along the chain
+                wp = net.xproj_w[:, :, 0]
+                p_cond = torch.matmul(wp[:, nf:], torch.cat((y0, gx), dim=-1).transpose(1, 2)) + net.xproj_b[None, :, None]
+                wy = wp[:, :nf].contiguous()
                 for i, t in enumerate(reversed(range(T))):
-                    xin = torch.cat((y, y0, gx), dim=-1).transpose(1, 2).contiguous()
-                    e = net.trunk(xin, t, rowptr, col, V).contiguous()
+                    xin = p_cond + torch.matmul(wy, y.transpose(1, 2))
+                    e = net.trunk(xin, t, rowptr, col, V, projected=True).contiguous()
                     z = draw(i + 1) if t > 0 else None
                     rc = lib.upd_nsx_step(_lib.ptr(e), *[_lib.ptr(h) for h in heads], _lib.ptr(y), _lib.ptr(y0),
                                           _lib.ptr(gx), _lib.ptr(z), _lib.ptr(sched), T, t, N, e.shape[1], O, nf,
