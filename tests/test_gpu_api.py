@@ -262,3 +262,33 @@ def test_real_data_gx_uncertainty_batched(tmp_path):
     m2, _ = U.load_model_from_dir(CKPT_DIR, device=torch.device("cuda:0"))         # F = 2: not a scalar per window
     with pytest.raises(TypeError):
         U.real_data_gx_uncertainty(m2, torch.zeros(1, 4000, 2), torch.arange(4000) * 0.1, 200, 1.0, 50, 0, tmp_path / "x.pt")
+
+
+def test_distributed_sweep_single_rank_group_equals_plain_sweep(model8):
+    """The N > 1 driver (bench.py under torchrun) on a one-rank gloo group: same cache and MPV list as sample_sweep, and the
+    Philox window counter advances by the whole sweep."""
+    import socket
+    import torch.distributed as dist
+    U = _U()
+    m, _ = model8
+    g = torch.Generator().manual_seed(6)
+    stacked = (torch.randn(5, 1, 200, 2, generator=g) * 0.1).cumsum(dim=2)
+    torch.manual_seed(78)
+    m._windows_drawn = 0
+    ref = U.sample_sweep(m, stacked)
+    ref_stats = {k: v.clone() for k, v in ref.upd_stats.get("raw", ref.upd_stats["scaled"]).items()}
+    ref = ref.clone()
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1)
+    try:
+        m._windows_drawn = 0
+        cache, (w0, w1), stats = U.distributed_sweep(m, stacked, device=torch.device("cuda:0"))
+    finally:
+        dist.destroy_process_group()
+    assert (w0, w1) == (0, 5) and m._windows_drawn == 5
+    assert torch.equal(cache, ref)
+    assert torch.equal(stats["mpv"], ref_stats["mpv"]) and torch.equal(stats["pred_mean"], ref_stats["pred_mean"])
+    assert tuple(stats["mpv_f"].shape) == (5, 2)
