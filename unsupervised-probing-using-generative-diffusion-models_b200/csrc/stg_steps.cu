@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "upd_common.cuh"
 
@@ -63,7 +64,7 @@ __global__ void stg_gated_aggregate_kernel(const float* __restrict__ kqvs, const
 // float4 per channel (scalar loads / stores when T is not a multiple of 4: the global rows are then only 8-byte aligned).
 // fp32 FFMA: C <= 16 channels is far below a tensor-core tile, and the pass is 3 B/FLOP away from HBM-bound.
 // ------------------------------------------------------------------------------------------------------
-template <int C>
+template <int C, bool XG>   // XG: x is read through L1 straight from global memory instead of being staged (T % 4 == 0 only)
 __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict__ x, const float* __restrict__ w1,
                                                          const float* __restrict__ b1, const float* __restrict__ w2,
                                                          const float* __restrict__ b2, const float* __restrict__ gamma,
@@ -77,8 +78,8 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
   const int TT = (T <= 4 * (int)blockDim.x) ? ((T + 3) & ~3) : 4 * (int)blockDim.x;   // positions per segment
   const int TP = TT + 4;                             // row pitch: data starts at column 4 (16-byte aligned),
                                                      // columns 0..3 are the halo of the causal convolutions
-  float* sx = smem;                                  // [CI][TP]
-  float* sh = sx + CI * TP;                          // [C][TP]
+  float* sx = smem;                                  // [CI][TP]   (absent when XG)
+  float* sh = XG ? smem : sx + CI * TP;              // [C][TP]
   float* sw1 = sh + C * TP;                          // [CI][3][C]  (tap-major inside a channel, channels contiguous)
   float* sw2 = sw1 + CI * 3 * C;                     // [C][3][C]
   float* swsc = sw2 + C * 3 * C;                     // [CI][C]   1x1 block shortcut (optional)
@@ -104,12 +105,12 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
    for (int tb = 0; tb < T; tb += TT) {
     const bool active = tb + t0 < T;
     __syncthreads();                                 // previous segment's / row's readers of sx / sh are done
-    for (int i = threadIdx.x; i < (CI + C) * 4; i += blockDim.x) {   // halos of sx and sh (contiguous: CI + C rows)
-      float* r = sx + (i >> 2) * TP + (i & 3);
+    for (int i = threadIdx.x; i < ((XG ? 0 : CI) + C) * 4; i += blockDim.x) {   // halos of sx and sh (contiguous rows)
+      float* r = smem + (i >> 2) * TP + (i & 3);
       *r = tb == 0 ? 0.0f : r[TT];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < CI * Q; i += blockDim.x) {
+    for (int i = threadIdx.x; i < (XG ? 0 : CI * Q); i += blockDim.x) {
       const int ci = i / Q, q = i - ci * Q, t = tb + 4 * q;
       float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       const float* src = (ci < CI1 ? xr + (long long)ci * T : xr2 + (long long)(ci - CI1) * T) + t;
@@ -132,7 +133,13 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
         for (int c = 0; c < C; ++c) acc[p][c] = b1[c];
       for (int ci = 0; ci < CI; ++ci) {
         float xv[6];                                                                    // x[t0-2 .. t0+3]
-        {
+        if (XG) {
+          const float* xc = (ci < CI1 ? xr + (long long)ci * T : xr2 + (long long)(ci - CI1) * T) + tb + t0;
+          const float4 b = __ldg(reinterpret_cast<const float4*>(xc));
+          float4 a = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (tb + t0 >= 4) a = __ldg(reinterpret_cast<const float4*>(xc - 4));        // the neighbour's quad: an L1 hit
+          xv[0] = a.z; xv[1] = a.w; xv[2] = b.x; xv[3] = b.y; xv[4] = b.z; xv[5] = b.w;
+        } else {
           const float4 a = *reinterpret_cast<const float4*>(sx + ci * TP + t0);        // columns t0..t0+3 = x[t0-4..t0-1]
           const float4 b = *reinterpret_cast<const float4*>(sx + ci * TP + t0 + 4);
           xv[0] = a.z; xv[1] = a.w; xv[2] = b.x; xv[3] = b.y; xv[4] = b.z; xv[5] = b.w;
@@ -250,7 +257,8 @@ __global__ void __launch_bounds__(128) stg_tcn_ln_kernel(const float* __restrict
 #pragma unroll
         for (int c = 0; c < C; ++c) acc[p][c] = 0.0f;
       for (int ci = 0; ci < CI; ++ci) {
-        const float4 xb = *reinterpret_cast<const float4*>(sx + ci * TP + t0 + 4);
+        const float4 xb = XG ? __ldg(reinterpret_cast<const float4*>((ci < CI1 ? xr + (long long)ci * T : xr2 + (long long)(ci - CI1) * T) + tb + t0))
+                             : *reinterpret_cast<const float4*>(sx + ci * TP + t0 + 4);
         const float* w = swsc + ci * C;
 #pragma unroll
         for (int c = 0; c < C; c += 4) {
@@ -351,25 +359,34 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
   if ((reinterpret_cast<uintptr_t>(hn) & 15) != 0 || (reinterpret_cast<uintptr_t>(a3) & 15) != 0) return cudaErrorInvalidValue;
   if (hn == nullptr && a3 == nullptr) return cudaErrorInvalidValue;
   const int seg = T <= 4 * threads ? ((T + 3) & ~3) : 4 * threads;
-  const size_t smem = sizeof(float) * ((size_t)(CI + C) * (seg + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C + (size_t)CI * C);
+  // 16-channel blocks and segmented rows: x is read through L1 instead of being staged (measured: 16->16 ch x T=200
+  // 0.98 -> 0.91 ms, 32->16 ch 1.77 -> 1.41 ms, 8 ch x T=2000 0.83 -> 0.75 ms; 8 ch x T=400 is faster staged, 0.46 vs
+  // 0.54 ms).  UPD_TCN_XG=0/1 forces one path (measurement only).
+  static const int xg_env = getenv("UPD_TCN_XG") ? atoi(getenv("UPD_TCN_XG")) : -1;
+  const bool xg = (T & 3) == 0 && (xg_env >= 0 ? xg_env != 0 : (C == 16 || T > 4 * threads));
+  const size_t smem = sizeof(float) * ((size_t)((xg ? 0 : CI) + C) * (seg + 4) + (size_t)CI * 3 * C + (size_t)C * 3 * C + (size_t)CI * C);
   if ((wsc == nullptr) != (sc_out == nullptr) || (reinterpret_cast<uintptr_t>(sc_out) & 15) != 0) return cudaErrorInvalidValue;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorInvalidValue;
   const int rpc = N >= 8192 ? 8 : 1;                   // rows per CTA: amortises the weight staging on big launches
   const unsigned grid = (unsigned)((N + rpc - 1) / rpc);
-#define UPD_TCN_CASE(CC)                                                                                             \
-  case CC: {                                                                                                         \
-    cudaError_t e = cudaFuncSetAttribute(stg_tcn_ln_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return e;                                                                                  \
-    stg_tcn_ln_kernel<CC><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn, (__half*)a3, wsc, sc_out, x2, CI - CI2); \
-    break;                                                                                                           \
+#define UPD_TCN_LAUNCH(CC, XX)                                                                                         \
+  {                                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(stg_tcn_ln_kernel<CC, XX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return e;                                                                                    \
+    stg_tcn_ln_kernel<CC, XX><<<grid, threads, smem, stream>>>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, rpc, hn, (__half*)a3, wsc, sc_out, x2, CI - CI2); \
   }
+#define UPD_TCN_CASE(CC)                                                                                               \
+  case CC:                                                                                                             \
+    if (xg) UPD_TCN_LAUNCH(CC, true) else UPD_TCN_LAUNCH(CC, false)                                                    \
+    break;
   switch (C) {
     UPD_TCN_CASE(4)
     UPD_TCN_CASE(8)
     UPD_TCN_CASE(16)
     default: return cudaErrorInvalidValue;
   }
+#undef UPD_TCN_LAUNCH
 #undef UPD_TCN_CASE
   return cudaGetLastError();
 }
