@@ -3,7 +3,7 @@
  * (conditional reverse-diffusion sampling + MPV / gx reduction).
  *
  * The reference has no FFI layer: its boundary is the Python surface between
- * evaluation_and_analysis/diffusion_model_uncertainy.py and models/Diffusion_model/*.
+ * evaluation_and_analysis/diffusion_model_uncertainy.py and models/Diffusion_model/ (every file).
  * Each entry point below replaces one reference function at that surface; the reference
  * file:line it stands in for is cited per function.  INTEGRATION.md shows the ctypes stub a
  * reference maintainer would add.

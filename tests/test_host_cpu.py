@@ -345,3 +345,17 @@ def test_feature_inverse_transform_helper():
     z = torch.arange(6.).view(3, 2)                           # [.., F]
     assert torch.equal(U._feature_inverse_transform(z, M()), z * M.scaler_std + M.scaler_mean)
     assert U._feature_inverse_transform(x, None) is x and U._as_path(None) is None and str(U._as_path("a/b")) == "a/b"
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/upd_b200.h is the drop-in boundary: it must compile as C (no C++ / CUDA / torch types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "use.c"
+    src.write_text('#include "upd_b200.h"\nint main(void) { return upd_abi_version() < 0; }\n')
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
