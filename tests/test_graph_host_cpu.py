@@ -1,4 +1,4 @@
-"""Host-side orchestration of NsDiff_spatial on the CPU: the C-ABI kernels are replaced by oracle-based stand-ins INSIDE THIS
+"""Host-side orchestration of the graph samplers (NsDiff_spatial, DiffSTG) on the CPU: the C-ABI kernels are replaced by oracle-based stand-ins INSIDE THIS
 TEST (monkeypatched, restored afterwards), so tile order, chunk / window batching, the shared-CSR replica convention, draw
 order and Philox row keys are checked against the reference-made fixture without a GPU.  The kernels themselves are
 checked on the GPU (tests/test_gpu_nsx.py, tests/test_gpu_stg.py); the product has no CPU path."""
@@ -47,6 +47,11 @@ class _StandInLib:
                 g0, g1, g2 = nso._gammas(sc, t, gx, sy0)
                 y0 = g0 * y0 + g1 * y + g2 * yT + torch.sqrt(sig) * z
             out.copy_(y0)
+        return 0
+
+    def upd_stg_posterior(self, xt, pred, z, n, a, b, c, out, st):
+        a, b, c = (torch.tensor(v, dtype=torch.float32) for v in (a, b, c))
+        out.copy_(a * (xt - b * pred) + c * (z if z is not None else pred))
         return 0
 
     def upd_gauss_fill(self, z, rows, elems, seed, base, draw, st):      # keyed per (seed, row_base + row, draw) like the kernel
@@ -137,3 +142,31 @@ def test_spatial_sampler_orchestration_matches_reference_fixture(cpu_stand_ins):
     m._windows_drawn = 0
     m.sample_windows(wins[:2], ei, V, seed=5)
     assert m._windows_drawn == 2
+
+
+def test_diffstg_sampler_orchestration_matches_reference_fixture(cpu_stand_ins):
+    """DiffSTG.sample_windows: (window, round, parallel sample) -> graph replicas, step plan, draw order, output layout."""
+    ns, diffstg = cpu_stand_ins
+    g = np.load("{}/stg_small_evalstep.npz".format(GOLDEN))
+    cfg, shapes, seed = json.loads(str(g["cfg"])), json.loads(str(g["keys"])), int(g["seed"])
+    sd = dto.synth_state_dict(shapes, seed)
+    for k in shapes:
+        if ".net.0." in k:
+            sd[k] = sd[k.replace(".net.0.", ".conv.")]
+    sd["scaler_mean"], sd["scaler_std"] = torch.zeros(cfg["F"]), torch.ones(cfg["F"])
+    m = diffstg.DiffSTG(dict(cfg, device="cpu")).eval()
+    m.load_state_dict(sd, strict=True)
+    x, ei = torch.from_numpy(g["x"]), torch.from_numpy(g["edge_index"])
+    V = x.shape[0]
+    draws = [torch.from_numpy(g["z%03d" % i]) for i in range(int(g["n_draws"]))]
+    per = m.draws_per_round()
+    noise = [draws[r * per:(r + 1) * per] for r in range(cfg["sequential_sampling"])]
+    outs, truth = m.evaluation_step(diffstg.GraphData(x=x, edge_index=ei, num_nodes=V), noise=noise)
+    ref = torch.from_numpy(g["outs"])
+    assert truth is None and tuple(outs.shape) == tuple(ref.shape) and _rel(outs, ref) < 1e-5
+    wins = torch.stack([x, x.flip(0), x * 0.5], 0)
+    a = m.sample_windows(wins, ei, V, seed=5, window_base=7)
+    m.rows_per_launch = V
+    b = m.sample_windows(wins, ei, V, seed=5, window_base=7)
+    c = m.sample_windows(wins[1:], ei, V, seed=5, window_base=8)
+    assert _rel(b, a) < 1e-5 and _rel(c, a[V:]) < 1e-5 and float(a.var(dim=1).mean()) > 0
