@@ -60,14 +60,18 @@ class GatedGraphConvParams(nn.Module):
             self.register_parameter("bias", None)
 
     def fused_weights(self):
-        """(K|Q|V|skip weight [4C, C], its bias [4C]) for one GEMM in front of upd_stg_gated_aggregate."""
+        """(K|Q|V|skip weight [4C, C], its bias [4C]) for one GEMM in front of upd_stg_gated_aggregate; built once per
+        parameter version (4 C x C matrices: C = fT_h * d_model can be thousands wide)."""
         C = self.lin_key.in_features
         dev = self.lin_key.weight.device
-        skip = self.lin_skip.weight if self.lin_skip is not None else torch.zeros(C, C, device=dev)
-        w = torch.cat([self.lin_key.weight, self.lin_query.weight, self.lin_value.weight, skip], 0).detach().contiguous()
-        b = torch.cat([self.lin_key.bias, self.lin_query.bias, self.lin_value.bias,
-                       torch.zeros(C, device=dev)], 0).detach().contiguous()
-        return w, b
+        key = (dev,) + tuple(p._version for p in self.parameters())
+        if getattr(self, "_fused_key", None) != key:
+            skip = self.lin_skip.weight if self.lin_skip is not None else torch.zeros(C, C, device=dev)
+            w = torch.cat([self.lin_key.weight, self.lin_query.weight, self.lin_value.weight, skip], 0).detach().contiguous()
+            b = torch.cat([self.lin_key.bias, self.lin_query.bias, self.lin_value.bias,
+                           torch.zeros(C, device=dev)], 0).detach().contiguous()
+            self._fused, self._fused_key = (w, b), key
+        return self._fused
 
 
 class SpatialBlockParams(nn.Module):
