@@ -227,3 +227,22 @@ def test_nsx_product_keys_and_loader(tmp_path):
         m.evaluation_step(GraphData(x=torch.from_numpy(g["x"]), edge_index=ei, num_nodes=6))
     with pytest.raises(ValueError, match="divisible"):
         NsDiff_model_spatial(dict(cfg, device="cpu", pred_len=101), "NsDiff_model")
+
+
+def test_nsx_block_plan_and_shapes_match_oracle_and_reference_keys():
+    """U-Net structure of the spatial denoiser: product plan == oracle plan (same blocks, channels, lengths), for the fixture
+    architectures and a three-resolution one; odd lengths that the reference's UGnet would mis-size are rejected."""
+    from oracle import nsdiff_spatial_oracle as nsx
+    from updgm_b200.diffstg import block_plan
+    from updgm_b200.nsdiff_spatial import ugnet_shapes
+    for name in ("nsx_small_evalstep.npz", "nsx_yaml_evalstep.npz"):
+        g, cfg, shapes, seed = _load(name)
+        own = [sum(block_plan(cfg, T_total=cfg["pred_len"]), [])]
+        ref = [[(p[len(nsx.UG):],) + tuple(rest) for (p, *rest) in sum(nsx.block_plan(cfg), [])]]
+        assert own == ref
+        sh = ugnet_shapes(cfg)
+        assert {nsx.UG + k: list(v) for k, v in sh.items()} == {k: v for k, v in shapes.items() if k.startswith(nsx.UG)}
+    cfg3 = dict(cfg, channel_multipliers=[2, 2, 2], pred_len=96, n_blocks=1)
+    plan = sum(block_plan(cfg3, T_total=96), [])
+    assert [b[4] for b in plan if b[1] == "res"][:3] == [96, 48, 24] and plan[-1][4] == 96
+    assert sum(nsx.block_plan(cfg3), []) == [(nsx.UG + p,) + tuple(rest) for (p, *rest) in plan]
