@@ -367,8 +367,7 @@ class PreparedUGnet:
         """x [N, C_in, T_total] (or, with ``projected``, already x_proj(x) [N, d_h, T_total]) -> the out block's result
         [N, C_out, T_out]; t: index into the step-embedding table."""
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            # the 1x1 projections are plain matmuls (cuDNN's heuristic picks an FFT algorithm for some of these shapes:
-            # 30 ms per call at [10^4, 3, 100])
+            # the 1x1 projections are plain (batched) matmuls: no cuDNN algorithm choice on these tiny-channel shapes
             if not projected:
                 x = torch.matmul(self.xproj_w[:, :, 0], x) + self.xproj_b[None, :, None]
             hs = [x]
