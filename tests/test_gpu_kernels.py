@@ -43,7 +43,7 @@ def _pack_ns(sd, F, T=20, schedule="linear"):
     return kernels.pack_denoiser(sd, kernels.KIND_NSDIFF, F, T, schedules.stack_rows(tab, schedules.NSDIFF_ROWS), _dev())
 
 
-IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param(2, id="tcgen05x3"), pytest.param(3, id="tcgen05x3w")]
+IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param(2, id="tcgen05x2"), pytest.param(3, id="tcgen05x3w")]
 
 
 # ---------------------------------------------------------------- tcgen05 descriptor known-answer
@@ -141,6 +141,11 @@ def test_nsdiff_vs_oracle_multiwindow(impl, F):
             ref[w * B:(w + 1) * B, c * S:(c + 1) * S] = seq[-1].reshape(B, S, O, F)
     dev = _dev()
     packed = _pack_ns(sd, F, T)
+    if impl == 3 and F > 2:
+        # the three-tile orchestration is built for F <= 2 only (register budget of 768 threads); the C ABI says so
+        with pytest.raises(RuntimeError, match="unsupported"):
+            kernels.nsdiff_sample(packed, y0.to(dev), gx.to(dev), n_win, B, K, S, O, F, T, noise=noise.to(dev), impl=impl)
+        return
     out = kernels.nsdiff_sample(packed, y0.to(dev), gx.to(dev), n_win, B, K, S, O, F, T, noise=noise.to(dev), impl=impl)
     _assert_traj(out, ref, "F=%d" % F)
 
@@ -162,7 +167,7 @@ def _random_ns_weights(F, T):
 @pytest.mark.parametrize("tc_impl", [0, 2, 3])
 def test_tc_matches_simt_bitwise_structure_large(tc_impl):
     """Full-size tile coverage: 5 windows x K=100 x O=200 (100k rows; 782 tiles = several rotations of the persistent
-    grid for the 2-tile and both 3-tile kernels) -- every tensor-core implementation agrees with the FFMA kernel."""
+    grid for the 2-tile and the 3-tile orchestration) -- every tensor-core implementation agrees with the FFMA kernel."""
     kernels, _ = _k()
     _, sd = load_wo_fx_checkpoint()
     dev = _dev()
@@ -421,10 +426,10 @@ def test_fx_tcgen05_attention_against_fp64(Lq, S, causal, use_delta):
     assert torch.equal(tail, torch.tensor([1., 1., 0, 0, 0, 0, 0, 0], device=dev).expand(B * Lq, 8))
 
 
-@pytest.mark.parametrize("impl", [2, 3])
+@pytest.mark.parametrize("impl", [3])
 def test_three_tile_kernels_full_bench_shape_against_two_tile(impl):
     """BASELINE config-2 shape at a size where every SM runs many rotations (30 windows x 100 rows x K=100 x O=100 =
-    30 M rows): the three-tile kernels reproduce the two-tile kernel (same Philox noise) to reordering error."""
+    30 M rows): the three-tile orchestration reproduces the two-tile one (same Philox noise) to reordering error."""
     kernels, schedules = _k()
     dev = _dev()
     g = load_golden("psample_loop_randF1.npz")
@@ -434,7 +439,7 @@ def test_three_tile_kernels_full_bench_shape_against_two_tile(impl):
     n_win, B, K, O = 30, 100, 100, 100
     gx = torch.rand(n_win * B, O, 1, device=dev) * 0.3 + 0.05
     y0 = torch.randn(n_win * B, O, 1, device=dev)
-    a = kernels.nsdiff_sample(packed, y0, gx, n_win, B, K, 10, O, 1, 20, seed=5, window_base=3, impl=0)
+    a = kernels.nsdiff_sample(packed, y0, gx, n_win, B, K, 10, O, 1, 20, seed=5, window_base=3, impl=2)
     b = kernels.nsdiff_sample(packed, y0, gx, n_win, B, K, 10, O, 1, 20, seed=5, window_base=3, impl=impl)
     rms = float(a.pow(2).mean().sqrt())
     assert torch.isfinite(b).all()

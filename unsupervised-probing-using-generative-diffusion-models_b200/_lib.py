@@ -16,8 +16,9 @@ SYMBOLS = (
     "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_dts_attention", "upd_dts_attention_bwd", "upd_dts_layernorm", "upd_dts_layernorm_bwd", "upd_stg_posterior", "upd_nsx_step", "upd_stg_gated_aggregate", "upd_stg_tcn_ln", "upd_stg_tcn_ln_cat", "upd_fx_split", "upd_fx_add_ln_split", "upd_fx_attention", "upd_fx_attention_hs16", "upd_fx_embed_split",
 )
 
+ABI_VERSION = 6     # = UPD_ABI_VERSION of the csrc/ this binding was written against (argument lists below)
 KIND_NSDIFF, KIND_TMDM = 0, 1
-IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X3, IMPL_TCGEN05_X3W = 0, 1, 2, 3
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X2, IMPL_TCGEN05_X3W = 0, 1, 2, 3
 _fp = ctypes.POINTER(ctypes.c_float)
 
 
@@ -46,6 +47,10 @@ def lib():
     L.upd_error_string.argtypes = [ctypes.c_int]
     L.upd_last_cuda_error.restype = ctypes.c_int
     L.upd_abi_version.restype = ctypes.c_int
+    if L.upd_abi_version() != ABI_VERSION:
+        # a stale build would be called with mismatched argument lists (silent memory corruption): refuse it
+        raise RuntimeError("{} has ABI version {}, this package needs {}: rebuild it (python -c 'import "
+                           "__graft_entry__ as g; g.build()')".format(path, L.upd_abi_version(), ABI_VERSION))
     L.upd_denoiser_pack_bytes.restype = ctypes.c_size_t
     L.upd_denoiser_pack_bytes.argtypes = [ctypes.c_int] * 3
     L.upd_denoiser_pack.restype = ctypes.c_int

@@ -193,6 +193,23 @@ int upd_denoiser_pack(const UpdDenoiserWeights* w, void* out_host, size_t capaci
   }
   fp(L.scales)[0] = 1.f / s2;
   fp(L.scales)[1] = 1.f / s3;
+  // NsDiff: layers 2 and 3 read an L2-normalised vector, so their base-2 pre-activation is bounded by
+  // (|W_row|_2 + |b|) |e| log2e (+1 % for the rounding of the split operand).  The tcgen05 kernel drops its ex2
+  // overflow guard when this bound is below 120; 0 = no bound (TMDM: no normalisation).
+  if (ns) {
+    double zmax = 0.0;
+    const float* ws[2] = {w->lin2_w, w->lin3_w};
+    const float* bs[2] = {w->lin2_b, w->lin3_b};
+    const float* es[2] = {w->embed2, w->embed3};
+    for (int l = 0; l < 2; ++l)
+      for (int n = 0; n < 128; ++n) {
+        double nrm = 0.0, emax = 0.0;
+        for (int k = 0; k < 128; ++k) nrm += (double)ws[l][n * 128 + k] * ws[l][n * 128 + k];
+        for (int t = 0; t < L.TE; ++t) emax = fmax(emax, fabs((double)es[l][t * 128 + n]));
+        zmax = fmax(zmax, 1.01 * (sqrt(nrm) + fabs((double)bs[l][n])) * emax * 1.4426950408889634);
+      }
+    fp(L.scales)[2] = isfinite(zmax) ? (float)zmax : 0.f;
+  }
   memcpy(fp(L.sched), w->sched, (size_t)L.n_sched * T * 4);
   // fp32 k-major transposes for the FFMA kernel
   for (int k = 0; k < IN; ++k)
@@ -214,7 +231,7 @@ static int sample_common(int kind, const void* packed, const float* y0_hat, cons
   if (kind == UPD_KIND_TMDM && !y0_hat) return UPD_ERR_BAD_ARG;
   if (!dims_ok(kind, F, T)) return UPD_ERR_UNSUPPORTED;
   if (noise && (K % S) != 0) return UPD_ERR_BAD_ARG;
-  if (impl != UPD_IMPL_TCGEN05 && impl != UPD_IMPL_SIMT && impl != UPD_IMPL_TCGEN05_X3 && impl != UPD_IMPL_TCGEN05_X3W)
+  if (impl != UPD_IMPL_TCGEN05 && impl != UPD_IMPL_SIMT && impl != UPD_IMPL_TCGEN05_X2 && impl != UPD_IMPL_TCGEN05_X3W)
     return UPD_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0) return UPD_ERR_BAD_ARG;
   int sms = 0;
@@ -228,10 +245,18 @@ static int sample_common(int kind, const void* packed, const float* y0_hat, cons
 #ifdef UPD_TRACE
   { const char* e = getenv("UPD_TRACE_PTR"); p.trace = e ? (long long*)strtoull(e, nullptr, 16) : nullptr; }
 #endif
-  cudaError_t e = (impl == UPD_IMPL_SIMT)         ? upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream)
-                  : (impl == UPD_IMPL_TCGEN05_X3) ? upd_launch_sampler_tc3(p, kind, F, sms, (cudaStream_t)stream)
-                  : (impl == UPD_IMPL_TCGEN05_X3W) ? upd_launch_sampler_tc3w(p, kind, F, sms, (cudaStream_t)stream)
-                                                  : upd_launch_sampler_tc(p, kind, F, sms, (cudaStream_t)stream);
+  cudaError_t e;
+  if (impl == UPD_IMPL_SIMT) {
+    e = upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream);
+  } else if (impl == UPD_IMPL_TCGEN05) {
+    // the library's choice: the measured-faster tile count for (kind, F); a step count whose
+    // embedding tables do not fit next to the weight image in shared memory (T > ~40) runs on the FFMA kernel
+    e = upd_launch_sampler_tc(p, kind, F, upd_default_tiles(kind, F), sms, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) e = upd_launch_sampler_tc(p, kind, F, 2, sms, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) e = upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream);
+  } else {
+    e = upd_launch_sampler_tc(p, kind, F, impl == UPD_IMPL_TCGEN05_X3W ? 3 : 2, sms, (cudaStream_t)stream);
+  }
   if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
   return e == cudaSuccess ? UPD_OK : cuda_fail(e);
 }

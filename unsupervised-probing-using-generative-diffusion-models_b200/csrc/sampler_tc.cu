@@ -1,167 +1,284 @@
-// Fused persistent reverse-diffusion sampler on tcgen05 tensor cores (UPD_IMPL_TCGEN05, the product path).
+// Fused persistent reverse-diffusion sampler on tcgen05 tensor cores (UPD_IMPL_TCGEN05 / UPD_IMPL_TCGEN05_X3W).
 //
 // One launch carries every (window,row,sample,position) of a sweep through all T reverse steps without leaving
-// the SM: weights resident in shared memory (bulk-copied once per CTA), activations ping-ponging between two
-// TMEM buffers, three chained GEMMs per step on tcgen05 (A from TMEM, B from shared memory, fp16/tf32 hi-lo
-// split with three passes = fp32-grade accuracy), NsDiff / TMDM posterior algebra and Philox noise in registers.
-// It is organised around the pipe that actually bounds this MLP -- MUFU (514 softplus = 1028 ex2/lg2 per
-// denoiser row-step) -- not the tensor pipe:
+// the SM: weights resident in shared memory (bulk-copied once per CTA), activations in TMEM, three chained GEMMs per
+// step on tcgen05 (A from TMEM, B from shared memory, fp16/tf32 hi-lo split with three passes = fp32-grade accuracy),
+// NsDiff / TMDM posterior algebra and Philox noise in registers.  It is organised around the pipe that actually
+// bounds this MLP -- MUFU (386 softplus = 772 ex2/lg2 per denoiser row-step) -- not the tensor pipe:
 //
-//   * one CTA per SM, 512 threads = 2 tiles x 8 warps.  A tile is 128 denoiser rows (row = TMEM lane).  Each
-//     TMEM lane quadrant is served by TWO warps that split the 128 hidden columns in halves, so four warps
-//     per scheduler are resident: while a tile waits for its MMAs (or at a barrier) the other tile still has
-//     two warps per scheduler to keep the MUFU pipe fed.  TMEM (512 columns = 2 tiles x 2 buffers x 128)
-//     is what limits the SM to two tiles; warps, not tiles, are what hide latency.
-//   * softplus is evaluated in base 2: L = lg2(1 + ex2(z')), z' = (acc*inv + b) * (e*log2e).  NsDiff
-//     L2-normalises every hidden layer, so the factor ln2 between softplus and L cancels; for TMDM (no
-//     normalisation) and for the heads it is folded into the scalar applied to the next accumulator.
-//     6 instructions per hidden element instead of 9.
-//   * hidden activations are re-encoded IN PLACE over the accumulator columns they came from, 16 columns
-//     at a time: K-slice j of the next A operand = fp16 hi in columns [16j,16j+8), lo in [16j+8,16j+16).
-//   * the two tiles take the MUFU-heavy phases in strict turns (named-barrier hand-off, mufu_turn_*): one tile's
-//     softplus epilogue runs at the full MUFU rate while the other's MMAs, head FMAs and posterior are in flight.
-//   * per-row reductions (sum of squares for F.normalize, head partial sums) are exchanged between the two
-//     column halves through shared memory, riding on the barrier that precedes each MMA issue anyway.
-//   * the sigma head's softplus acts on the L2-normalised hidden vector (components in [0,1]): it is a
-//     polynomial, and because a polynomial of hn = L/||L|| is a sum of power sums of L, both heads are
-//     accumulated inside the layer-3 epilogue and rescaled once ||L|| is known -- 386 instead of 514 MUFU
-//     softplus per row-step and no second pass over the row.
-//   * row state (y, y0_hat, gx), the posterior algebra and the A1 operand belong to the half-0 warp of each
-//     row; the half-1 warp draws the Philox noise for it while it would otherwise idle.
+//   * one CTA per SM, TILES x 8 warps.  A tile is 128 denoiser rows (row = TMEM lane).  Each TMEM lane quadrant is
+//     served by TWO warps that split the 128 hidden columns in halves; per-row reductions (sum of squares for
+//     F.normalize, head sums) cross the halves through shared memory on the barrier that precedes each MMA anyway.
+//   * TILES = 2 (UPD_IMPL_TCGEN05): each tile ping-pongs between two private 128-column TMEM buffers and the tiles
+//     take the MUFU-heavy phases in strict turns (named-barrier hand-off): one tile's softplus epilogue runs while the
+//     other's MMAs, posterior and operand build are in flight.
+//   * TILES = 3 (UPD_IMPL_TCGEN05_X3W): TMEM (512 columns) has no room for three ping-pong pairs, but a tile needs both
+//     buffers only while its MMAs are in flight, so four 128-column buffers rotate among three tiles: MMA number m of
+//     the CTA-wide sequence (tile m % 3) reads A from buffer (m+2) % 4 and accumulates into (m+1) % 4 -- the A buffer
+//     of MMA m-1, free once that MMA has completed, which the issuer checks on the other tile's mbarrier.  24 warps,
+//     free-running.
+//   * softplus is evaluated in base 2: L = lg2(1 + 2^z'), z' = (acc*inv + b) * (e*log2e).  NsDiff L2-normalises every
+//     hidden layer, so the factor ln2 between softplus and L cancels; for TMDM and the heads it is folded into the
+//     scalar applied to the next accumulator.  The epilogue arithmetic is packed fp32x2 (sampler_math.cuh): 6-7 warp
+//     instructions per hidden element, and a compile-time share of the elements (UPD_PMASK*) evaluates lg2(1+u) as a
+//     polynomial on the FMA pipe so that the MUFU pipe and the issue port run out together.
+//   * hidden activations are re-encoded IN PLACE over the accumulator columns they came from, 16 columns at a time:
+//     K-slice j of the next A operand = fp16 hi in columns [16j,16j+8), lo in [16j+8,16j+16).  The normalisation of
+//     layer l is a scalar applied to the accumulator of layer l+1 (W(h/|h|) = (Wh)/|h|).
+//   * the sigma head's inner softplus acts on the L2-normalised hidden vector (components in [0,1]): a polynomial,
+//     and because a polynomial of hn = L/||L|| is a sum of power sums of L, both heads are accumulated inside the
+//     layer-3 epilogue and rescaled once ||L|| is known -- no second pass over the row.
+//   * row state (y, y0_hat, gx), the posterior algebra and the A1 operand belong to the half-0 warp of each row; the
+//     half-1 warp draws the Philox noise for it while it would otherwise idle.
+//
+// Limits (surfaced as UPD_ERR_UNSUPPORTED by the launcher, include/upd_b200.h): F <= 4; T such that the weight image
+// with its three [T,128] step-embedding tables fits 227 KB of shared memory (T <= ~40 with two tiles).
+#include "sampler_math.cuh"
 #include "sampler_params.cuh"
 #include "tc_helpers.cuh"
 #include "upd_common.cuh"
 
 namespace {
 
-constexpr int TC_THREADS = 512;
 constexpr uint32_t UMMA_LBO = 2048;   // K-adjacent core matrices (layout in upd_common.cuh)
 constexpr uint32_t UMMA_SBO = 128;    // N-adjacent core matrices
-#ifndef UPD_HANDOFF_GROUP
-#define UPD_HANDOFF_GROUP 4
-#endif
-constexpr int PP_BAR0 = 13;           // named barriers 13/14: MUFU turn of tile 0 / tile 1 (see mufu_turn_*)
+constexpr int PP_BAR0 = 13;           // named barriers 13/14: MUFU turn of tile 0 / tile 1 (two-tile kernel only)
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
+// Which of the 8 column pairs of a 16-column group take the one-MUFU (polynomial) softplus: bit i = pair i.
+// Layers 1 and 2 (plain epilogue) and layer 3 (epilogue + head sums) are balanced separately.
+#ifndef UPD_PMASK12
+#define UPD_PMASK12 0x00
+#endif
+#ifndef UPD_PMASK3
+#define UPD_PMASK3 0x00
+#endif
+// MUFU turn-taking of the two-tile kernel (0 = free-running)
+#ifndef UPD_TURNS
+#define UPD_TURNS 1
+#endif
+
 struct __align__(8) TcSync {
   unsigned long long wbar;
-  unsigned long long mma_bar[2];
+  unsigned long long mma_bar[3];
   uint32_t tmem_base;
   uint32_t pad;
 };
 
-// lg2(1 + 2^z): softplus(z*ln2)/ln2.  Two MUFU ops; z is clamped where the caller cannot bound it.
-__device__ __forceinline__ float lg2_1p_ex2(float z) {
-  float u, l;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(z));
-  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + u));
-  return l;
+template <int KIND, int F>
+struct SamplerShape {
+  static constexpr bool NS = (KIND == 0);
+  // exchange area per tile (floats per row): 2 layers x 2 halves of sums of squares; layer-3 sum of squares; per
+  // feature: eps sum, noise draw and (NsDiff) the four sigma-head sums handed from the half-1 warp to the row's owner
+  static constexpr uint32_t XCH_TILE_FLOATS = (2 * 2 + 1 + 2 * F + (NS ? 4 * F : 0)) * 128;
+  static constexpr uint32_t STEP_BYTES = NS ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
+};
+
+// z' of a pair of columns.  FIRST: layer 1 (bias rides in the GEMM).
+template <bool FIRST>
+__device__ __forceinline__ float2 preact2(uint32_t a0, uint32_t a1, float2 inv2, float2 b, float2 e) {
+  const float2 acc = make_float2(__uint_as_float(a0), __uint_as_float(a1));
+  // (acc*inv + b) as one FMA: the pre-activation differs from the reference's two roundings by < 1 ulp, far below the
+  // reordering of the 128-term sums it comes from
+  return FIRST ? sm::fmul2(acc, e) : sm::fmul2(sm::ffma2(acc, inv2, b), e);
 }
 
-// The same function with ONE MUFU op: lg2(1 + 2^z) = max(z,0) + lg2(1 + u), u = 2^-|z| in (0,1], and lg2(1+u) as a
-// degree-8 minimax polynomial on the FMA pipe (|error| 4e-8 exact, 1.8e-7 in fp32 Horner -- the size of lg2.approx's own
-// error on these arguments).  Inside a MUFU turn the epilogue is MUFU-bound (32768 MUFU ops per tile-phase = 2048 clk
-// at 16/clk/SM); evaluating UPD_POLY_LG2 of every 4 elements this way trades 1 MUFU op for 10 FMA-pipe instructions.
-// MEASURED (B200, bench shape, parity green in every variant): 0 of 4: 3.72 G row-steps/s, 1 of 4: 3.73, 2 of 4: 3.48,
-// 3 of 4: 3.29, 4 of 4: 3.14 -- inside a MUFU turn the issue slots are as full as the MUFU pipe, so the trade does not
-// pay.  Kept (default off) as the record of that experiment.
-#ifndef UPD_POLY_LG2
-#define UPD_POLY_LG2 0
-#endif
-__device__ __forceinline__ float lg2_1p_ex2_poly(float z) {
-  float u;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(u) : "f"(-fabsf(z)));
-  float p = -9.0889083222e-03f;
-  p = fmaf(p, u, 5.1134437323e-02f);
-  p = fmaf(p, u, -1.3592693210e-01f);
-  p = fmaf(p, u, 2.4041023850e-01f);
-  p = fmaf(p, u, -3.4654855728e-01f);
-  p = fmaf(p, u, 4.7846421599e-01f);
-  p = fmaf(p, u, -7.2113221884e-01f);
-  p = fmaf(p, u, 1.4426876307e+00f);
-  p = fmaf(p, u, 4.2314418636e-08f);
-  return fmaxf(z, 0.0f) + p;
+// The epilogues are software pipelines over UNITS of 8 accumulator columns (4 pairs) with three stages,
+//   P: accumulator -> pre-activation z' (FMA pipe),   A: z' -> w (ex2),   B: w -> L (lg2 or its polynomial), consume,
+// arranged as a ROLLED loop whose body holds B(i), A(i+1), P(i+2), B(i+1), A(i+2), P(i+3): every MUFU instruction of the
+// body has its input ready when the body starts, so a warp's MUFU stream never drains while it waits for a TMEM load, a
+// shared-memory operand or an ex2 result.  (The first packed-math version ran the stages of a 16-column group back to
+// back, fully unrolled: ptxas sank the TMEM prefetch below the arithmetic, finished one group before touching the next,
+// and the two warps of an SMSP fell into lock-step, both in their MUFU-free load/split sections at once -- clock64
+// stamps showed 2950 cycles per phase for 2048 cycles of MUFU work.  ptxas does not move code across a loop edge.)
+// PMASK: bit i = pair i of the unit takes the one-MUFU (polynomial) softplus.
+struct UnitZ { float2 z[4]; };
+struct UnitW {
+  float2 w[4];   // MUFU form: 1 + 2^z';  polynomial form: 2^-|z'|
+  float2 z[4];   // z' (dead, and dropped by the compiler, for unguarded MUFU pairs)
+};
+
+template <bool FIRST>
+__device__ __forceinline__ void stage_p(const uint32_t* __restrict__ r, const float* __restrict__ e,
+                                        const float* __restrict__ b, float2 inv2, UnitZ& Z) {
+  const float4 e0 = *reinterpret_cast<const float4*>(e), e1 = *reinterpret_cast<const float4*>(e + 4);
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b0 = FIRST ? z4 : *reinterpret_cast<const float4*>(b), b1 = FIRST ? z4 : *reinterpret_cast<const float4*>(b + 4);
+  Z.z[0] = preact2<FIRST>(r[0], r[1], inv2, make_float2(b0.x, b0.y), make_float2(e0.x, e0.y));
+  Z.z[1] = preact2<FIRST>(r[2], r[3], inv2, make_float2(b0.z, b0.w), make_float2(e0.z, e0.w));
+  Z.z[2] = preact2<FIRST>(r[4], r[5], inv2, make_float2(b1.x, b1.y), make_float2(e1.x, e1.y));
+  Z.z[3] = preact2<FIRST>(r[6], r[7], inv2, make_float2(b1.z, b1.w), make_float2(e1.z, e1.w));
 }
 
-// softplus(x) for x in [0,1] without MUFU: x/2 + P(x^2), P = degree-4 near-minimax fit of log(2 cosh(sqrt(u)/2))
-// on u in [0,1] (|error| < 4e-9 before fp32 rounding, 1e-7 after).  The sigma head applies softplus to the
-// L2-normalised, non-negative hidden vector, whose components always lie in [0,1]; taking those 128 of the 514
-// softplus per row-step off the MUFU pipe removes a quarter of the kernel's transcendental work.
-constexpr float SPU_C0 = 0.6931471824645996f, SPU_C1 = 0.12499982863664627f, SPU_C2 = -0.005206969100981951f,
-                SPU_C3 = 0.0003433137317188084f, SPU_C4 = -2.16761418414535e-05f;
-
-// MUFU hand-off between the two tiles of a CTA.  Left alone the tiles fall into lock-step (measured with clock64
-// stamps: both in their softplus epilogue at once, each at half MUFU rate, then both waiting on interleaved MMAs
-// with the MUFU pipe idle: 24.8k cycles per step).  A tile therefore takes the MUFU-heavy phases (the three
-// softplus epilogues of a step) in turns: wait for the partner to finish its phase, run, hand over.  While one
-// tile computes softplus the other has its MMAs, head FMAs and posterior algebra in flight.
-__device__ __forceinline__ void mufu_turn_begin(int tile_id) { tc::named_bar_sync(PP_BAR0 + tile_id, TC_THREADS); }
-__device__ __forceinline__ void mufu_turn_end(int tile_id) { tc::named_bar_arrive(PP_BAR0 + (tile_id ^ 1), TC_THREADS); }
-
-// One 16-column group of an accumulator -> activations -> fp16 hi/lo A operand, in place.
-// FIRST: layer 1 (bias rides in the GEMM).  CLAMP: guard ex2 overflow where inputs are unbounded.
-template <bool FIRST, bool CLAMP>
-__device__ __forceinline__ float epilogue_group(const uint32_t (&r)[16], uint32_t (&o)[16], const float* __restrict__ e,
-                                                const float* __restrict__ b, float inv) {
-  float ss = 0.f;
-#pragma unroll
-  for (int j = 0; j < 16; j += 4) {
-    float4 e4 = *reinterpret_cast<const float4*>(e + j);
-    float4 b4 = FIRST ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(b + j);
-    // (acc*inv + b) as one FMA: the pre-activation differs from the reference's two roundings by < 1 ulp, far
-    // below the reordering of the 128-term sums it comes from
-    float z0 = FIRST ? __uint_as_float(r[j]) * e4.x : fmaf(__uint_as_float(r[j]), inv, b4.x) * e4.x;
-    float z1 = FIRST ? __uint_as_float(r[j + 1]) * e4.y : fmaf(__uint_as_float(r[j + 1]), inv, b4.y) * e4.y;
-    float z2 = FIRST ? __uint_as_float(r[j + 2]) * e4.z : fmaf(__uint_as_float(r[j + 2]), inv, b4.z) * e4.z;
-    float z3 = FIRST ? __uint_as_float(r[j + 3]) * e4.w : fmaf(__uint_as_float(r[j + 3]), inv, b4.w) * e4.w;
-    if (CLAMP) { z0 = fminf(z0, 126.f); z1 = fminf(z1, 126.f); z2 = fminf(z2, 126.f); z3 = fminf(z3, 126.f); }
-    // UPD_POLY_LG2 of these four go through the one-MUFU form (0: none, 1: h3, 2: h1 and h3, 4: all)
-    float h0 = (UPD_POLY_LG2 >= 4) ? lg2_1p_ex2_poly(z0) : lg2_1p_ex2(z0);
-    float h1 = (UPD_POLY_LG2 >= 2) ? lg2_1p_ex2_poly(z1) : lg2_1p_ex2(z1);
-    float h2 = (UPD_POLY_LG2 >= 3) ? lg2_1p_ex2_poly(z2) : lg2_1p_ex2(z2);
-    float h3 = (UPD_POLY_LG2 >= 1) ? lg2_1p_ex2_poly(z3) : lg2_1p_ex2(z3);
-    ss = fmaf(h0, h0, ss); ss = fmaf(h1, h1, ss); ss = fmaf(h2, h2, ss); ss = fmaf(h3, h3, ss);
-    tc::split_f16x2(h0, h1, o[j / 2], o[8 + j / 2]);
-    tc::split_f16x2(h2, h3, o[j / 2 + 1], o[8 + j / 2 + 1]);
-  }
-  return ss;
+template <bool GUARD, int PMASK>
+__device__ __forceinline__ void stage_a(const UnitZ& Z, UnitW& W) {
+  sm::static_for<4>([&](auto ii) {
+    constexpr int i = decltype(ii)::value;
+    W.z[i] = Z.z[i];
+    if constexpr (((PMASK >> i) & 1) != 0) W.w[i] = sm::softplus2_poly_a(Z.z[i]);
+    else W.w[i] = sm::softplus2_mufu_a<GUARD>(Z.z[i]);
+  });
 }
 
-// This warp's 64 columns of one hidden layer: 4 groups, TMEM loads software-pipelined one group ahead.
-constexpr int HANDOFF_GROUP = UPD_HANDOFF_GROUP;   // the MUFU turn is handed over after this many of the 4 groups
+template <bool GUARD, int PMASK>
+__device__ __forceinline__ void stage_b(const UnitW& W, float2 (&h)[4]) {
+  sm::static_for<4>([&](auto ii) {
+    constexpr int i = decltype(ii)::value;
+    if constexpr (((PMASK >> i) & 1) != 0) h[i] = sm::softplus2_poly_b(W.w[i], W.z[i]);
+    else h[i] = sm::softplus2_mufu_b<GUARD>(W.w[i], W.z[i]);
+  });
+}
 
-// UPD_PRELOAD: the first 16-column group of the accumulator is fetched from TMEM BEFORE the tile asks for its MUFU turn
-// (the MMAs are complete by then), so that the first MUFU instruction issues right at the hand-over instead of a TMEM
-// round trip later.  MEASURED (B200, bench shape, parity green): 3.715 vs 3.721 G row-steps/s without it -- the hand-over
-// gap is not the TMEM load.  Kept (default off) as the record of that experiment.
-#ifndef UPD_PRELOAD
-#define UPD_PRELOAD 0
-#endif
+// MUFU hand-off between the two tiles of a CTA (TILES == 2).  Left alone the tiles fall into lock-step (measured with
+// clock64 stamps in round 1: both in their softplus epilogue at once, each at half MUFU rate, then both waiting on
+// interleaved MMAs with the MUFU pipe idle).  A tile therefore takes the MUFU-heavy phases (the three softplus
+// epilogues of a step) in turns: wait for the partner to finish its phase, run, hand over.
+template <int TILES>
+__device__ __forceinline__ void mufu_turn_begin(int tile_id) {
+  if (TILES == 2 && UPD_TURNS) tc::named_bar_sync(PP_BAR0 + tile_id, 512);
+}
+template <int TILES>
+__device__ __forceinline__ void mufu_turn_end(int tile_id) {
+  if (TILES == 2 && UPD_TURNS) tc::named_bar_arrive(PP_BAR0 + (tile_id ^ 1), 512);
+}
 
-template <bool FIRST, bool CLAMP>
+// Stage B's consumer for the hidden layers: sum of squares + fp16 hi/lo split of one unit, written back in place.
+// K-slice j of the next A operand = hi words in columns [16j,16j+8), lo words in [16j+8,16j+16); unit u holds the
+// elements 8u .. 8u+7 = words 4(u&1) .. 4(u&1)+3 of slice u/2.
+template <bool SUMSQ>
+__device__ __forceinline__ void store_unit(uint32_t slice_addr, int odd, const float2 (&h)[4], float2& ss2) {
+  uint32_t hi[4], lo[4];
+  sm::static_for<4>([&](auto ii) {
+    constexpr int i = decltype(ii)::value;
+    if (SUMSQ) ss2 = sm::ffma2(h[i], h[i], ss2);
+    sm::split_f16x2(h[i].x, h[i].y, hi[i], lo[i]);
+  });
+  tc::tmem_st4(slice_addr + 4u * odd, hi[0], hi[1], hi[2], hi[3]);
+  tc::tmem_st4(slice_addr + 8u + 4u * odd, lo[0], lo[1], lo[2], lo[3]);
+}
+
+// This warp's 64 columns of one hidden layer -> activations -> fp16 hi/lo A operand, in place.
+template <int TILES, bool FIRST, bool GUARD, bool SUMSQ>
 __device__ __forceinline__ float epilogue_half(uint32_t buf, const float* __restrict__ e, const float* __restrict__ b,
                                                float inv, int tile_id) {
-  float ss = 0.f;
-  uint32_t r[16], rn[16], o[16];
+  constexpr int PM0 = UPD_PMASK12 & 15, PM1 = (UPD_PMASK12 >> 4) & 15;     // even / odd units
+  float2 ss2 = make_float2(0.f, 0.f);
+  const float2 inv2 = sm::splat(inv);
+  uint32_t r[16];
+  UnitZ z0, z1, zn;
+  UnitW w0, w1;
+  float2 h[4];
   tc::tmem_ld16(buf, r);
   tc::wait_ld();
-#if UPD_PRELOAD
-  mufu_turn_begin(tile_id);
-#endif
+  stage_p<FIRST>(r, e, b, inv2, z0);
+  stage_p<FIRST>(r + 8, e + 8, b + 8, inv2, z1);
+  tc::tmem_ld16(buf + 16u, r);
+  stage_a<GUARD, PM0>(z0, w0);
+#pragma unroll 1
+  for (int q = 0; q < 3; ++q) {
+    // carried in: w0 = A(unit 2q), z1 = P(unit 2q+1), r <- group q+1 in flight
+    tc::wait_ld();
+    stage_p<FIRST>(r, e + 16 * (q + 1), b + 16 * (q + 1), inv2, z0);            // unit 2q+2
+    stage_p<FIRST>(r + 8, e + 16 * (q + 1) + 8, b + 16 * (q + 1) + 8, inv2, zn); // unit 2q+3
+    tc::tmem_ld16_if(q < 2, buf + 16u * (q + 2), r);
+    stage_b<GUARD, PM0>(w0, h);
+    store_unit<SUMSQ>(buf + 16u * q, 0, h, ss2);
+    stage_a<GUARD, PM1>(z1, w1);
+    stage_b<GUARD, PM1>(w1, h);
+    store_unit<SUMSQ>(buf + 16u * q, 1, h, ss2);
+    stage_a<GUARD, PM0>(z0, w0);
+    z1 = zn;
+  }
+  // tail: units 6 and 7
+  stage_b<GUARD, PM0>(w0, h);
+  store_unit<SUMSQ>(buf + 48u, 0, h, ss2);
+  stage_a<GUARD, PM1>(z1, w1);
+  mufu_turn_end<TILES>(tile_id);
+  stage_b<GUARD, PM1>(w1, h);
+  store_unit<SUMSQ>(buf + 48u, 1, h, ss2);
+  return ss2.x + ss2.y;
+}
+
+// Head sums of one warp's 64 columns (see the header and sampler_math.cuh): pe = sum w4 L, and for NsDiff
+// pb = sum ws L, m_k = sum ws L^(2k), ss = sum L^2 -- all as packed pairs (even / odd columns), folded at the end.
+template <bool NS, int F>
+struct HeadSums {
+  float2 ss, pe[F], pb[F], m1[F], m2[F], m3[F];
+  __device__ __forceinline__ void clear() {
+    ss = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    if (q < 3) tc::tmem_ld16(buf + 16u * (q + 1), rn);
-    ss += epilogue_group<FIRST, CLAMP>(r, o, e + 16 * q, b + 16 * q, inv);
-    tc::tmem_st16(buf + 16u * q, o);
-    if (q == HANDOFF_GROUP - 1) mufu_turn_end(tile_id);
-    if (q < 3) {
-      tc::wait_ld();
-#pragma unroll
-      for (int i = 0; i < 16; ++i) r[i] = rn[i];
+    for (int f = 0; f < F; ++f) {
+      pe[f] = make_float2(0.f, 0.f);
+      if (NS) { pb[f] = make_float2(0.f, 0.f); m1[f] = pb[f]; m2[f] = pb[f]; m3[f] = pb[f]; }
     }
   }
-  return ss;
+  __device__ __forceinline__ void add(float2 h, const float* __restrict__ w4, const float* __restrict__ ws) {
+    // w4 / ws point at this pair's two columns of feature 0; features are 128 floats apart
+    if (NS) {
+      const float2 u = sm::fmul2(h, h);
+      ss = sm::fadd2(ss, u);
+      const float2 u2 = sm::fmul2(u, u), u3 = sm::fmul2(u2, u);
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        const float2 a = *reinterpret_cast<const float2*>(w4 + f * 128);
+        const float2 s = *reinterpret_cast<const float2*>(ws + f * 128);
+        pe[f] = sm::ffma2(a, h, pe[f]);
+        pb[f] = sm::ffma2(s, h, pb[f]);
+        m1[f] = sm::ffma2(s, u, m1[f]);
+        m2[f] = sm::ffma2(s, u2, m2[f]);
+        m3[f] = sm::ffma2(s, u3, m3[f]);
+      }
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) pe[f] = sm::ffma2(*reinterpret_cast<const float2*>(w4 + f * 128), h, pe[f]);
+    }
+  }
+};
+
+// Layer-3 epilogue of this warp's 64 columns: the same pipeline; stage B feeds the head sums, nothing is written back.
+template <int TILES, bool NS, int F, bool GUARD>
+__device__ __forceinline__ void heads_half(uint32_t buf, const float* __restrict__ e, const float* __restrict__ b,
+                                           const float* __restrict__ w4, const float* __restrict__ ws, float inv,
+                                           HeadSums<NS, F>& H, int tile_id) {
+  constexpr int PM0 = UPD_PMASK3 & 15, PM1 = (UPD_PMASK3 >> 4) & 15;
+  const float2 inv2 = sm::splat(inv);
+  uint32_t r[16];
+  UnitZ z0, z1, zn;
+  UnitW w0, w1;
+  float2 h[4];
+  auto consume = [&](int col) {
+    sm::static_for<4>([&](auto ii) {
+      constexpr int i = decltype(ii)::value;
+      H.add(h[i], w4 + col + 2 * i, ws + col + 2 * i);
+    });
+  };
+  tc::tmem_ld16(buf, r);
+  tc::wait_ld();
+  stage_p<false>(r, e, b, inv2, z0);
+  stage_p<false>(r + 8, e + 8, b + 8, inv2, z1);
+  tc::tmem_ld16(buf + 16u, r);
+  stage_a<GUARD, PM0>(z0, w0);
+#pragma unroll 1
+  for (int q = 0; q < 3; ++q) {
+    tc::wait_ld();
+    stage_p<false>(r, e + 16 * (q + 1), b + 16 * (q + 1), inv2, z0);
+    stage_p<false>(r + 8, e + 16 * (q + 1) + 8, b + 16 * (q + 1) + 8, inv2, zn);
+    tc::tmem_ld16_if(q < 2, buf + 16u * (q + 2), r);
+    stage_b<GUARD, PM0>(w0, h);
+    consume(16 * q);
+    stage_a<GUARD, PM1>(z1, w1);
+    stage_b<GUARD, PM1>(w1, h);
+    consume(16 * q + 8);
+    stage_a<GUARD, PM0>(z0, w0);
+    z1 = zn;
+  }
+  stage_b<GUARD, PM0>(w0, h);
+  consume(48);
+  stage_a<GUARD, PM1>(z1, w1);
+  mufu_turn_end<TILES>(tile_id);
+  stage_b<GUARD, PM1>(w1, h);
+  consume(56);
 }
 
 #ifdef UPD_TRACE
@@ -170,29 +287,27 @@ __device__ __forceinline__ float epilogue_half(uint32_t buf, const float* __rest
 #define UPD_STAMP(k) do { } while (0)
 #endif
 
-template <int KIND, int F>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int KIND, int F, int TILES>
+__global__ void __launch_bounds__(TILES * 256, 1)
 sampler_tc_kernel(const UpdSamplerParams p) {
-  constexpr bool NS = (KIND == 0);
+  using Shape = SamplerShape<KIND, F>;
+  constexpr bool NS = Shape::NS;
+  constexpr bool ROT = (TILES == 3);
+  constexpr int THREADS = TILES * 256;
   constexpr int IN = NS ? 3 * F : 2 * F;
   constexpr int K1 = ((IN + 1 + 7) / 8) * 8;
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
   extern __shared__ __align__(128) unsigned char smem[];
   auto sf = [&](uint32_t off) { return reinterpret_cast<float*>(smem + off); };
-  constexpr uint32_t STEP_BYTES = NS ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
   const uint32_t steps_off = upd_align128(L.tc_image_bytes);
-  const uint32_t xch_off = upd_align128(steps_off + STEP_BYTES * p.T);
-  // exchange area per tile: ssx[2 layers][2 halves][128 rows]; headx[1 + 7F][128 rows] = layer-3 sum of squares,
-  // F eps sums, F noise draws, 5F sigma-head sums handed from the half-1 warp to the row's owner
-  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0 && F > 1) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
-  const uint32_t sync_off = upd_align128(xch_off + 2 * XCH_TILE_FLOATS * 4);
+  const uint32_t xch_off = upd_align128(steps_off + Shape::STEP_BYTES * p.T);
+  const uint32_t sync_off = upd_align128(xch_off + TILES * Shape::XCH_TILE_FLOATS * 4);
   TcSync* sync = reinterpret_cast<TcSync*>(smem + sync_off);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     tc::mbar_init(tc::smem_u32(&sync->wbar), 1);
-    tc::mbar_init(tc::smem_u32(&sync->mma_bar[0]), 1);
-    tc::mbar_init(tc::smem_u32(&sync->mma_bar[1]), 1);
+    for (int i = 0; i < 3; ++i) tc::mbar_init(tc::smem_u32(&sync->mma_bar[i]), 1);
     tc::fence_mbar_init();
   }
   if (warp == 0) tc::tmem_alloc<512>(tc::smem_u32(&sync->tmem_base));
@@ -211,7 +326,7 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   }
   tc::mbar_wait(tc::smem_u32(&sync->wbar), 0);
   // step-embedding tables to base 2 (e * log2e), per-step posterior scalars: once per CTA
-  for (int i = tid; i < L.TE * 128; i += TC_THREADS) {
+  for (int i = tid; i < L.TE * 128; i += THREADS) {
     sf(L.e1)[i] *= LOG2E; sf(L.e2)[i] *= LOG2E; sf(L.e3)[i] *= LOG2E;
   }
   if (tid < p.T) {
@@ -224,19 +339,41 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   const int trow = quad * 32 + lane;                        // row within the tile = TMEM lane
   const bool owner = (half == 0);
   const bool issuer = owner && quad == 0 && lane == 0;
-  const uint32_t col0 = (uint32_t)tile_id * 256u;
   const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
-  const uint32_t buf0 = tmem_base + lane_sel + col0, buf1 = buf0 + 128u;        // whole-row views (owner A1 write)
-  const uint32_t my0 = buf0 + 64u * half, my1 = buf1 + 64u * half;              // this warp's column half
-  const uint32_t mma0 = tmem_base + col0, mma1 = mma0 + 128u;
+  // TMEM buffers.  Two tiles: private ping-pong pair (cur = the buffer that holds the next A operand).  Three tiles:
+  // m = index of this tile's next MMA in the CTA-wide sequence, A in buffer (m+2)%4, accumulator in (m+1)%4.
+  long long m = tile_id;
+  uint32_t cur = 0;
+  auto a_col = [&]() -> uint32_t { return ROT ? tmem_base + 128u * (uint32_t)((m + 2) & 3) : tmem_base + (uint32_t)tile_id * 256u + 128u * cur; };
+  auto d_col = [&]() -> uint32_t { return ROT ? tmem_base + 128u * (uint32_t)((m + 1) & 3) : tmem_base + (uint32_t)tile_id * 256u + 128u * (cur ^ 1u); };
   const uint32_t bar = tc::smem_u32(&sync->mma_bar[tile_id]);
+  uint32_t phase = 0;
+  // issuer: launch one layer's MMAs (A operand complete in a_col) and commit to this tile's mbarrier
+  auto wait_prev_mma = [&]() {       // three tiles: the accumulator of MMA m is the A buffer of MMA m-1
+    if (ROT && m > 0) {
+      const long long pm = m - 1;
+      tc::mbar_wait(tc::smem_u32(&sync->mma_bar[pm % 3]), (uint32_t)((pm / 3) & 1));
+      tc::fence_after_sync();
+    }
+  };
+  // every thread: wait for the layer just issued; returns this warp's column half of its accumulator
+  auto wait_layer = [&]() -> uint32_t {
+    const uint32_t acc = d_col() + lane_sel + 64u * half;
+    if (ROT) { tc::mbar_wait(bar, (uint32_t)((m / 3) & 1)); m += 3; }
+    else { tc::mbar_wait(bar, phase); phase ^= 1u; cur ^= 1u; }
+    tc::fence_after_sync();
+    return acc;
+  };
   const uint32_t img = tc::smem_u32(smem);
-  float* ssx = sf(xch_off) + tile_id * XCH_TILE_FLOATS;     // [2][2][128]
-  float* headx = ssx + ((NS && F > 1) ? 3 : 2) * 2 * 128;   // [1 + 7F][128] (single-pass heads) or [3F][128]
-  // named barriers: 1,2 = all 256 threads of a tile (precede every MMA issue); 5..12 = the two warps that share
+  float* ssx = sf(xch_off) + tile_id * Shape::XCH_TILE_FLOATS;     // [2 layers][2 halves][128]
+  float* headx = ssx + 2 * 2 * 128;                                 // [1 + 2F (+ 4F)][128]
+  // named barriers: 1..3 = all 256 threads of a tile (precede every MMA issue); 4.. = the two warps that share
   // a TMEM lane quadrant (64 threads), for the half<->half exchanges that need no tile-wide rendezvous
-  const int full_bar = 1 + tile_id, pair_bar = 5 + tile_id * 4 + quad;
+  const int full_bar = 1 + tile_id, pair_bar = 4 + tile_id * 4 + quad;
   const float inv_ws2 = sf(L.scales)[0] * (NS ? 1.0f : LN2), inv_ws3 = sf(L.scales)[1] * (NS ? 1.0f : LN2);
+  // NsDiff: |z'| of layers 2 and 3 is bounded by (|W_row| + |b|) |e| log2e because their input is L2-normalised; the
+  // packer stores that bound (scales[2]); below 120 the ex2 overflow guard is compiled out of those epilogues.
+  const bool guard23 = !NS || !(sf(L.scales)[2] > 0.f && sf(L.scales)[2] < 120.f);
   const float* e1 = sf(L.e1) + 64 * half;
   const float* e2 = sf(L.e2) + 64 * half;
   const float* e3 = sf(L.e3) + 64 * half;
@@ -244,14 +381,13 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   const float* b3 = sf(L.b3) + 64 * half;
   const float* w4 = sf(L.w4) + 64 * half;
   const float* wsg = sf(L.ws) + 64 * half;
-  uint32_t phase = 0;
-  // c0 * sum_j ws[f][j]: the constant term of the sigma-head polynomial (see layer-3 epilogue)
+  // ln2 * sum_j ws[f][j]: the constant term of the sigma-head polynomial
   float ws_sum[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) {
     float a = 0.f;
     if (NS) for (int j = 0; j < 128; ++j) a += sf(L.ws)[f * 128 + j];
-    ws_sum[f] = SPU_C0 * a;
+    ws_sum[f] = sm::SPH_LN2 * a;
   }
 
   const long long n_tiles = (p.n_rows + 127) / 128;
@@ -259,12 +395,12 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   bool tracing = false;
 #endif
   // Every tile slot of every CTA runs the same number of iterations (slots past the end compute on a clamped
-  // row and store nothing): the MUFU hand-off below is a strict alternation and must never wait for a
-  // partner that has already left.
-  const long long n_iters = (n_tiles + 2LL * gridDim.x - 1) / (2LL * gridDim.x);
-  if (tile_id == 1) tc::named_bar_arrive(PP_BAR0, TC_THREADS);          // tile 0 takes the first turn
+  // row and store nothing): the MUFU hand-off and the buffer rotation are strict alternations and must never wait
+  // for a partner that has already left.
+  const long long n_iters = (n_tiles + (long long)TILES * gridDim.x - 1) / ((long long)TILES * gridDim.x);
+  if (TILES == 2 && UPD_TURNS && tile_id == 1) tc::named_bar_arrive(PP_BAR0, 512);          // tile 0 takes the first turn
   for (long long it = 0; it < n_iters; ++it) {
-    const long long tile = (it * gridDim.x + blockIdx.x) * 2 + tile_id;
+    const long long tile = (it * gridDim.x + blockIdx.x) * TILES + tile_id;
     const long long row = tile * 128 + trow;
     const bool live = row < p.n_rows;
     UpdRowIndex ix = upd_row_index(p, live ? row : p.n_rows - 1);
@@ -306,7 +442,7 @@ sampler_tc_kernel(const UpdSamplerParams p) {
             a[i] = __float_as_uint(hi);
             a[8 + i] = __float_as_uint(tc::to_tf32(in[i] - hi));
           }
-          tc::tmem_st16(buf0, a);
+          tc::tmem_st16(a_col() + lane_sel, a);
         } else {
           uint32_t a[32];
 #pragma unroll
@@ -316,7 +452,7 @@ sampler_tc_kernel(const UpdSamplerParams p) {
             a[i] = __float_as_uint(hi);
             a[16 + i] = __float_as_uint(tc::to_tf32(v - hi));
           }
-          tc::tmem_st32(buf0, a);
+          tc::tmem_st32(a_col() + lane_sel, a);
         }
         tc::wait_st();
       }
@@ -325,19 +461,17 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       UPD_STAMP(1);
       if (issuer) {
         tc::fence_after_sync();
-        tc::issue_layer_tf32x3(mma1, mma0, K1, img + L.u1hi, img + L.u1lo, UMMA_LBO, UMMA_SBO);
+        wait_prev_mma();
+        tc::issue_layer_tf32x3(d_col(), a_col(), K1, img + L.u1hi, img + L.u1lo, UMMA_LBO, UMMA_SBO);
         tc::mma_commit(bar);
       }
-      tc::mbar_wait(bar, phase); phase ^= 1u;
-      tc::fence_after_sync();
+      uint32_t acc = wait_layer();
       UPD_STAMP(2);
 
-      // ---------------- layer 1 epilogue -> A2 (in place, buf1); layer 2 ----------------
-#if !UPD_PRELOAD
-      mufu_turn_begin(tile_id);
-#endif
+      // ---------------- layer 1 epilogue -> A2 (in place); layer 2 ----------------
+      mufu_turn_begin<TILES>(tile_id);
       UPD_STAMP(13);
-      float ss = epilogue_half<true, true>(my1, e1 + t * 128, nullptr, 1.f, tile_id);
+      float ss = epilogue_half<TILES, true, true, NS>(acc, e1 + t * 128, nullptr, 1.f, tile_id);
       if (NS) ssx[(0 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
       UPD_STAMP(3);
@@ -346,21 +480,20 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       UPD_STAMP(4);
       if (issuer) {
         tc::fence_after_sync();
-        tc::issue_layer_f16x3_g16(mma0, mma1, img + L.u2hi, img + L.u2lo, UMMA_LBO, UMMA_SBO);
+        wait_prev_mma();
+        tc::issue_layer_f16x3_g16(d_col(), a_col(), img + L.u2hi, img + L.u2lo, UMMA_LBO, UMMA_SBO);
         tc::mma_commit(bar);
       }
       float inv = inv_ws2;
       if (NS) inv = inv_ws2 / fmaxf(sqrtf(ssx[0 * 128 + trow] + ssx[1 * 128 + trow]), 1e-12f);   // F.normalize, folded past the GEMM
-      tc::mbar_wait(bar, phase); phase ^= 1u;
-      tc::fence_after_sync();
+      acc = wait_layer();
       UPD_STAMP(5);
 
-      // ---------------- layer 2 epilogue -> A3 (in place, buf0); layer 3 ----------------
-#if !UPD_PRELOAD
-      mufu_turn_begin(tile_id);
-#endif
+      // ---------------- layer 2 epilogue -> A3 (in place); layer 3 ----------------
+      mufu_turn_begin<TILES>(tile_id);
       UPD_STAMP(14);
-      ss = epilogue_half<false, !NS>(my0, e2 + t * 128, b2, inv, tile_id);
+      if (guard23) ss = epilogue_half<TILES, false, true, NS>(acc, e2 + t * 128, b2, inv, tile_id);
+      else ss = epilogue_half<TILES, false, false, NS>(acc, e2 + t * 128, b2, inv, tile_id);
       if (NS) ssx[(1 * 2 + half) * 128 + trow] = ss;
       tc::wait_st();
       UPD_STAMP(6);
@@ -369,90 +502,43 @@ sampler_tc_kernel(const UpdSamplerParams p) {
       UPD_STAMP(7);
       if (issuer) {
         tc::fence_after_sync();
-        tc::issue_layer_f16x3_g16(mma1, mma0, img + L.u3hi, img + L.u3lo, UMMA_LBO, UMMA_SBO);
+        wait_prev_mma();
+        tc::issue_layer_f16x3_g16(d_col(), a_col(), img + L.u3hi, img + L.u3lo, UMMA_LBO, UMMA_SBO);
         tc::mma_commit(bar);
       }
       inv = inv_ws3;
       if (NS) inv = inv_ws3 / fmaxf(sqrtf(ssx[2 * 128 + trow] + ssx[3 * 128 + trow]), 1e-12f);
-      tc::mbar_wait(bar, phase); phase ^= 1u;
-      tc::fence_after_sync();
+      acc = wait_layer();
       UPD_STAMP(8);
 
-      if constexpr (!(NS && F > 1)) {
       // ---------------- layer 3 epilogue + heads (denoise.py:50 / tmdm_model.py:63) ----------------
       // NsDiff heads read hn = h/||h|| (= L/||L||): eps = lin4(hn), sigma = softplus(sigma_lin(softplus(hn))).
-      // ||L|| is only known once the whole row is done, so instead of a second pass over the row the layer-3
-      // epilogue accumulates everything the heads need as sums that are rescaled afterwards:
+      // ||L|| is only known once the whole row is done, so the layer-3 epilogue accumulates everything the heads need
+      // as sums that are rescaled afterwards:
       //   lin4(hn)                 = inv3 * sum_j w4_j L_j
-      //   sigma_lin(softplus(hn))  = sum_j ws_j (hn_j/2 + P(hn_j^2))          (hn_j in [0,1], P above)
-      //                            = inv3/2 * sum_j ws_j L_j + c0 * sum_j ws_j + sum_k c_k inv3^(2k) * sum_j ws_j L_j^(2k)
-      // i.e. the weighted power sums M_k = sum_j ws_j L_j^(2k), k = 1..4.  These FMAs ride in the MUFU-bound
-      // phase, where issue slots are free; no TMEM round trip of the row, no second pass.
-      float pe[F], pb[F], m1[F], m2[F], m3[F], m4[F];
-#pragma unroll
-      for (int f = 0; f < F; ++f) { pe[f] = 0.f; pb[f] = 0.f; m1[f] = 0.f; m2[f] = 0.f; m3[f] = 0.f; m4[f] = 0.f; }
-      const float* e3t = e3 + t * 128;
-      ss = 0.f;
-#if !UPD_PRELOAD
-      mufu_turn_begin(tile_id);
-#endif
+      //   sigma_lin(softplus(hn))  = sum_j ws_j (hn_j/2 + ln2 + u_j/8 + C2 u_j^2 + C3 u_j^3),   u_j = hn_j^2
+      //                            = inv3/2 * PB + ln2 * sum_j ws_j + inv3^2/8 * M1 + C2 inv3^4 * M2 + C3 inv3^6 * M3
+      // with PB = sum_j ws_j L_j and the weighted power sums M_k = sum_j ws_j L_j^(2k).
+      HeadSums<NS, F> hs;
+      hs.clear();
+      mufu_turn_begin<TILES>(tile_id);
       UPD_STAMP(15);
-      {
-        uint32_t r[16], rn[16];
-        tc::tmem_ld16(my1, r);
-        tc::wait_ld();
-#if UPD_PRELOAD
-        mufu_turn_begin(tile_id);
-#endif
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (q < 3) tc::tmem_ld16(my1 + 16u * (q + 1), rn);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int c = 16 * q + j;
-            float h = lg2_1p_ex2(fminf(fmaf(__uint_as_float(r[j]), inv, b3[c]) * e3t[c], 126.f));
-            if (NS) {
-              float u = h * h;
-              ss += u;
-              float u2 = u * u, u3 = u2 * u, u4 = u2 * u2;
-#pragma unroll
-              for (int f = 0; f < F; ++f) {
-                const float wv = wsg[f * 128 + c];
-                pe[f] = fmaf(w4[f * 128 + c], h, pe[f]);
-                pb[f] = fmaf(wv, h, pb[f]);
-                m1[f] = fmaf(wv, u, m1[f]);
-                m2[f] = fmaf(wv, u2, m2[f]);
-                m3[f] = fmaf(wv, u3, m3[f]);
-                m4[f] = fmaf(wv, u4, m4[f]);
-              }
-            } else {
-#pragma unroll
-              for (int f = 0; f < F; ++f) pe[f] = fmaf(w4[f * 128 + c], h, pe[f]);
-            }
-          }
-          if (q < 3) {
-            tc::wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) r[i] = rn[i];
-          }
-        }
-      }
-      mufu_turn_end(tile_id);
+      if (guard23) heads_half<TILES, NS, F, true>(acc, e3 + t * 128, b3, w4, wsg, inv, hs, tile_id);
+      else heads_half<TILES, NS, F, false>(acc, e3 + t * 128, b3, w4, wsg, inv, hs, tile_id);
       UPD_STAMP(9);
       const bool last = (t == 0);
       if (!owner) {
         // the half that owns no row state hands over its partial sums and draws this step's noise
-        headx[0 * 128 + trow] = ss;
+        headx[0 * 128 + trow] = hs.ss.x + hs.ss.y;
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-          headx[(1 + f) * 128 + trow] = pe[f];
+          headx[(1 + f) * 128 + trow] = hs.pe[f].x + hs.pe[f].y;
           headx[(1 + F + f) * 128 + trow] = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
           if (NS) {
-            headx[(1 + 2 * F + f) * 128 + trow] = pb[f];
-            headx[(1 + 3 * F + f) * 128 + trow] = m1[f];
-            headx[(1 + 4 * F + f) * 128 + trow] = m2[f];
-            headx[(1 + 5 * F + f) * 128 + trow] = m3[f];
-            headx[(1 + 6 * F + f) * 128 + trow] = m4[f];
+            headx[(1 + 2 * F + f) * 128 + trow] = hs.pb[f].x + hs.pb[f].y;
+            headx[(1 + 3 * F + f) * 128 + trow] = hs.m1[f].x + hs.m1[f].y;
+            headx[(1 + 4 * F + f) * 128 + trow] = hs.m2[f].x + hs.m2[f].y;
+            headx[(1 + 5 * F + f) * 128 + trow] = hs.m3[f].x + hs.m3[f].y;
           }
         }
         __threadfence_block();
@@ -463,16 +549,15 @@ sampler_tc_kernel(const UpdSamplerParams p) {
         // ---------------- posterior update (owner warps) ----------------
         if (NS) {
           const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
-          const float inv3 = 1.0f / fmaxf(sqrtf(ss + headx[trow]), 1e-12f);
+          const float inv3 = 1.0f / fmaxf(sqrtf((hs.ss.x + hs.ss.y) + headx[trow]), 1e-12f);
           const float i2 = inv3 * inv3, i4 = i2 * i2;
 #pragma unroll
           for (int f = 0; f < F; ++f) {
-            float eps = (pe[f] + headx[(1 + f) * 128 + trow]) * inv3 + sf(L.b4)[f];
-            float lin = 0.5f * inv3 * (pb[f] + headx[(1 + 2 * F + f) * 128 + trow]);
-            float poly = fmaf(i2, SPU_C1 * (m1[f] + headx[(1 + 3 * F + f) * 128 + trow]), ws_sum[f]);
-            poly = fmaf(i4, SPU_C2 * (m2[f] + headx[(1 + 4 * F + f) * 128 + trow]), poly);
-            poly = fmaf(i4 * i2, SPU_C3 * (m3[f] + headx[(1 + 5 * F + f) * 128 + trow]), poly);
-            poly = fmaf(i4 * i4, SPU_C4 * (m4[f] + headx[(1 + 6 * F + f) * 128 + trow]), poly);
+            float eps = ((hs.pe[f].x + hs.pe[f].y) + headx[(1 + f) * 128 + trow]) * inv3 + sf(L.b4)[f];
+            float lin = 0.5f * inv3 * ((hs.pb[f].x + hs.pb[f].y) + headx[(1 + 2 * F + f) * 128 + trow]);
+            float poly = fmaf(i2, sm::SPH_C1 * ((hs.m1[f].x + hs.m1[f].y) + headx[(1 + 3 * F + f) * 128 + trow]), ws_sum[f]);
+            poly = fmaf(i4, sm::SPH_C2 * ((hs.m2[f].x + hs.m2[f].y) + headx[(1 + 4 * F + f) * 128 + trow]), poly);
+            poly = fmaf(i4 * i2, sm::SPH_C3 * ((hs.m3[f].x + hs.m3[f].y) + headx[(1 + 5 * F + f) * 128 + trow]), poly);
             float sig = upd_softplus_accurate(lin + poly + sf(L.bs)[f]);
             y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, headx[(1 + F + f) * 128 + trow], last);
           }
@@ -480,84 +565,10 @@ sampler_tc_kernel(const UpdSamplerParams p) {
           const UpdTmStep st = reinterpret_cast<const UpdTmStep*>(smem + steps_off)[t];
 #pragma unroll
           for (int f = 0; f < F; ++f) {
-            float eps = (pe[f] + headx[(1 + f) * 128 + trow]) * LN2 + sf(L.b4)[f];
+            float eps = ((hs.pe[f].x + hs.pe[f].y) + headx[(1 + f) * 128 + trow]) * LN2 + sf(L.b4)[f];
             y[f] = upd_tm_update(st, y[f], y0h[f], eps, headx[(1 + F + f) * 128 + trow], last);
           }
         }
-      }
-      } else {
-      // ---------------- layer 3 epilogue + heads, two passes (NsDiff, F > 1) ----------------
-      // With several features the head sums cost 6F FMAs per element, which would make the MUFU turn issue-bound;
-      // here pass 1 (in the MUFU turn) only produces L3 and its sum of squares, and pass 2 (outside the turn,
-      // overlapping the other tile's softplus) evaluates the heads on hn = L3/||L3|| re-read from TMEM.
-      float pe[F], ps[F];
-#pragma unroll
-      for (int f = 0; f < F; ++f) { pe[f] = 0.f; ps[f] = 0.f; }
-      const float* e3t = e3 + t * 128;
-      mufu_turn_begin(tile_id);
-      UPD_STAMP(15);
-      ss = 0.f;
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        uint32_t r[16];
-        tc::tmem_ld16(my1 + 16u * q, r);
-        tc::wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float h = lg2_1p_ex2(fminf(fmaf(__uint_as_float(r[j]), inv, b3[16 * q + j]) * e3t[16 * q + j], 126.f));
-          ss = fmaf(h, h, ss);
-          r[j] = __float_as_uint(h);
-        }
-        tc::tmem_st16(my1 + 16u * q, r);
-      }
-      ssx[(2 * 2 + half) * 128 + trow] = ss;
-      mufu_turn_end(tile_id);
-      tc::wait_st();
-      UPD_STAMP(9);
-      tc::named_bar_sync(pair_bar, 64);
-      UPD_STAMP(10);
-      const float inv3 = 1.0f / fmaxf(sqrtf(ssx[4 * 128 + trow] + ssx[5 * 128 + trow]), 1e-12f);
-#pragma unroll 1
-      for (int q = 0; q < 4; ++q) {
-        uint32_t r[16];
-        tc::tmem_ld16(my1 + 16u * q, r);
-        tc::wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float hn = __uint_as_float(r[j]) * inv3, u = hn * hn;
-          float sp = fmaf(SPU_C4, u, SPU_C3);
-          sp = fmaf(sp, u, SPU_C2);
-          sp = fmaf(sp, u, SPU_C1);
-          sp = fmaf(sp, u, SPU_C0);
-          sp = fmaf(0.5f, hn, sp);
-#pragma unroll
-          for (int f = 0; f < F; ++f) {
-            pe[f] = fmaf(w4[f * 128 + 16 * q + j], hn, pe[f]);
-            ps[f] = fmaf(wsg[f * 128 + 16 * q + j], sp, ps[f]);
-          }
-        }
-      }
-      const bool last = (t == 0);
-      UPD_STAMP(11);
-      if (!owner) {
-#pragma unroll
-        for (int f = 0; f < F; ++f) {
-          headx[f * 128 + trow] = pe[f];
-          headx[(F + f) * 128 + trow] = ps[f];
-          headx[(2 * F + f) * 128 + trow] = last ? 0.f : upd_draw(p, ix, f, F, p.T - t);
-        }
-        __threadfence_block();
-        tc::named_bar_arrive(pair_bar, 64);
-      } else {
-        tc::named_bar_sync(pair_bar, 64);
-        const UpdNsStep st = reinterpret_cast<const UpdNsStep*>(smem + steps_off)[t];
-#pragma unroll
-        for (int f = 0; f < F; ++f) {
-          float eps = (pe[f] + headx[f * 128 + trow]) + sf(L.b4)[f];
-          float sig = upd_softplus_accurate((ps[f] + headx[(F + f) * 128 + trow]) + sf(L.bs)[f]);
-          y[f] = upd_ns_update(st, y[f], y0h[f], gxv[f], eps, sig, headx[(2 * F + f) * 128 + trow], last);
-        }
-      }
       }
       UPD_STAMP(12);
     }
@@ -572,31 +583,31 @@ sampler_tc_kernel(const UpdSamplerParams p) {
   if (warp == 0) tc::tmem_dealloc<512>(tmem_base);
 }
 
-template <int KIND, int F>
+template <int KIND, int F, int TILES>
 cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
+  using Shape = SamplerShape<KIND, F>;
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
-  constexpr uint32_t STEP_BYTES = (KIND == 0) ? sizeof(UpdNsStep) : sizeof(UpdTmStep);
-  constexpr uint32_t XCH_TILE_FLOATS = (KIND == 0 && F > 1) ? (3 * 2 + 3 * F) * 128 : (2 * 2 + 1 + 7 * F) * 128;
-  size_t smem = upd_align128(upd_align128(upd_align128(L.tc_image_bytes) + STEP_BYTES * p.T) + 2 * XCH_TILE_FLOATS * 4) +
-                sizeof(TcSync) + 128;
+  size_t smem = upd_align128(upd_align128(upd_align128(L.tc_image_bytes) + Shape::STEP_BYTES * p.T) +
+                             TILES * Shape::XCH_TILE_FLOATS * 4) + sizeof(TcSync) + 128;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  auto kern = sampler_tc_kernel<KIND, F>;
+  auto kern = sampler_tc_kernel<KIND, F, TILES>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   long long n_tiles = (p.n_rows + 127) / 128;
-  long long ctas = (n_tiles + 1) / 2;
+  long long ctas = (n_tiles + TILES - 1) / TILES;
   int grid = (int)(ctas < sms ? ctas : sms);
   if (grid < 1) grid = 1;
-  kern<<<grid, TC_THREADS, smem, stream>>>(p);
+  kern<<<grid, TILES * 256, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
 }  // namespace
 
-cudaError_t upd_launch_sampler_tc(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream) {
-#define UPD_CASE(KK, FF) if (kind == KK && F == FF) return launch<KK, FF>(p, sms, stream);
-  UPD_CASE(0, 1) UPD_CASE(0, 2) UPD_CASE(0, 3) UPD_CASE(0, 4)
-  UPD_CASE(1, 1) UPD_CASE(1, 2) UPD_CASE(1, 3) UPD_CASE(1, 4)
+cudaError_t upd_launch_sampler_tc(const UpdSamplerParams& p, int kind, int F, int tiles, int sms, cudaStream_t stream) {
+#define UPD_CASE(KK, FF, TT) if (kind == KK && F == FF && tiles == TT) return launch<KK, FF, TT>(p, sms, stream);
+  UPD_CASE(0, 1, 2) UPD_CASE(0, 2, 2) UPD_CASE(0, 3, 2) UPD_CASE(0, 4, 2)
+  UPD_CASE(1, 1, 2) UPD_CASE(1, 2, 2) UPD_CASE(1, 3, 2) UPD_CASE(1, 4, 2)
+  UPD_CASE(0, 1, 3) UPD_CASE(0, 2, 3) UPD_CASE(1, 1, 3) UPD_CASE(1, 2, 3)
 #undef UPD_CASE
   return cudaErrorInvalidValue;
 }

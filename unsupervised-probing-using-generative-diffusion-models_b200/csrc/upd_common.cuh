@@ -6,7 +6,10 @@
 #define UPD_HID 128           // hidden width of the conditional MLP denoiser (denoise.py:28-30)
 #define UPD_MAX_F 4
 #define UPD_MAX_T 64
-#define UPD_ABI_VERSION 5
+#define UPD_ABI_VERSION 6
+#ifndef UPD_DEFAULT_TILES
+#define UPD_DEFAULT_TILES 2    // row tiles per SM of the tcgen05 sampler when the caller leaves the choice to the library
+#endif
 
 #ifdef __CUDACC__
 #define UPD_HD __host__ __device__ __forceinline__
@@ -25,7 +28,8 @@
 //     u1hi,u1lo           : [lin1 | bias column | 0-pad] as tf32 hi/lo, K1 = roundup(in+1, 8):
 //                           elem(n,k) at (k/4)*2048 + n*16 + (k%4)*4
 //     fp32 tail           : b2,b3 [128]; e1,e2,e3 [TE,128]; w4 [F,128]; ws [F,128]; b4,bs [4];
-//                           scales [4] = (1/wscale2, 1/wscale3, 0, 0); sched [n_sched, T]
+//                           scales [4] = (1/wscale2, 1/wscale3, zmax23, 0) -- zmax23: bound of the base-2
+//                           pre-activations of layers 2/3 (NsDiff; 0 = unbounded); sched [n_sched, T]
 //   [simt extra] fp32, k-major transposes for the FFMA kernel: w1t [in,128], b1 [128],
 //                           w2t [128,128], w3t [128,128]
 // ---------------------------------------------------------------------------------------------
