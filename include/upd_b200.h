@@ -45,14 +45,15 @@ enum {
 
 /* Sampler implementations (same results within fp32 round-off). */
 enum {
-  UPD_IMPL_TCGEN05 = 0,      /* tcgen05/TMEM tensor-core kernel (default, the product path); the
-                                library picks two or three row tiles per SM for (kind, F), and
-                                runs a step count whose tables do not fit in shared memory
-                                (T > ~40) on the FFMA kernel instead of failing                */
+  UPD_IMPL_TCGEN05 = 0,      /* tcgen05/TMEM tensor-core sampler (default, the product path): the
+                                warp-specialised kernel for F <= 2, the two-tile kernel for F = 3, 4;
+                                a step count whose tables do not fit in shared memory (T > ~40) runs
+                                on the FFMA kernel instead of failing                          */
   UPD_IMPL_SIMT = 1,         /* fp32 FFMA kernel (bring-up / cross-check of the tensor path)   */
-  UPD_IMPL_TCGEN05_X2 = 2,   /* tcgen05 kernel, forced two tiles per SM, MUFU turn-taking      */
-  UPD_IMPL_TCGEN05_X3W = 3   /* tcgen05 kernel, forced three tiles per SM in TMEM rotation;
-                                UPD_ERR_UNSUPPORTED for F > 2 or when shared memory is exceeded */
+  UPD_IMPL_TCGEN05_X2 = 2,   /* forced: two tiles per SM taking MUFU turns (sampler_tc.cu);
+                                UPD_ERR_UNSUPPORTED when shared memory is exceeded (T > ~40)   */
+  UPD_IMPL_TCGEN05_WS = 4    /* forced: warp-specialised kernel, 16 epilogue warps + 4 row warps
+                                (sampler_ws.cu); UPD_ERR_UNSUPPORTED for F > 2                 */
 };
 
 const char* upd_error_string(int code);

@@ -43,7 +43,7 @@ def _pack_ns(sd, F, T=20, schedule="linear"):
     return kernels.pack_denoiser(sd, kernels.KIND_NSDIFF, F, T, schedules.stack_rows(tab, schedules.NSDIFF_ROWS), _dev())
 
 
-IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param(2, id="tcgen05x2"), pytest.param(3, id="tcgen05x3w")]
+IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param(2, id="tcgen05x2"), pytest.param(4, id="tcgen05ws")]
 
 
 # ---------------------------------------------------------------- tcgen05 descriptor known-answer
@@ -141,8 +141,8 @@ def test_nsdiff_vs_oracle_multiwindow(impl, F):
             ref[w * B:(w + 1) * B, c * S:(c + 1) * S] = seq[-1].reshape(B, S, O, F)
     dev = _dev()
     packed = _pack_ns(sd, F, T)
-    if impl == 3 and F > 2:
-        # the three-tile orchestration is built for F <= 2 only (register budget of 768 threads); the C ABI says so
+    if impl == 4 and F > 2:
+        # the warp-specialised kernel is built for F <= 2 only (shared memory of its head-sum exchange); the C ABI says so
         with pytest.raises(RuntimeError, match="unsupported"):
             kernels.nsdiff_sample(packed, y0.to(dev), gx.to(dev), n_win, B, K, S, O, F, T, noise=noise.to(dev), impl=impl)
         return
@@ -164,10 +164,10 @@ def _random_ns_weights(F, T):
     return sd
 
 
-@pytest.mark.parametrize("tc_impl", [0, 2, 3])
+@pytest.mark.parametrize("tc_impl", [0, 2, 4])
 def test_tc_matches_simt_bitwise_structure_large(tc_impl):
     """Full-size tile coverage: 5 windows x K=100 x O=200 (100k rows; 782 tiles = several rotations of the persistent
-    grid for the 2-tile and the 3-tile orchestration) -- every tensor-core implementation agrees with the FFMA kernel."""
+    grid for both tcgen05 orchestrations) -- every tensor-core implementation agrees with the FFMA kernel."""
     kernels, _ = _k()
     _, sd = load_wo_fx_checkpoint()
     dev = _dev()
@@ -426,10 +426,10 @@ def test_fx_tcgen05_attention_against_fp64(Lq, S, causal, use_delta):
     assert torch.equal(tail, torch.tensor([1., 1., 0, 0, 0, 0, 0, 0], device=dev).expand(B * Lq, 8))
 
 
-@pytest.mark.parametrize("impl", [3])
-def test_three_tile_kernels_full_bench_shape_against_two_tile(impl):
-    """BASELINE config-2 shape at a size where every SM runs many rotations (30 windows x 100 rows x K=100 x O=100 =
-    30 M rows): the three-tile orchestration reproduces the two-tile one (same Philox noise) to reordering error."""
+@pytest.mark.parametrize("impl", [4])
+def test_warp_specialised_kernel_full_bench_shape_against_two_tile(impl):
+    """BASELINE config-2 shape at a size where every SM runs many tile pairs (30 windows x 100 rows x K=100 x O=100 =
+    30 M rows): the warp-specialised kernel reproduces the two-tile one (same Philox noise) to reordering error."""
     kernels, schedules = _k()
     dev = _dev()
     g = load_golden("psample_loop_randF1.npz")

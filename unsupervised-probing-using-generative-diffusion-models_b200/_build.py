@@ -22,9 +22,9 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_NAME = "libupd_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
 BUILD_DIR = os.path.join(PKG_DIR, "build")
-SOURCES = ["api.cu", "sampler_simt.cu", "sampler_tc.cu", "selftest_umma.cu", "mpv_reduce.cu", "sigma_est.cu",
+SOURCES = ["api.cu", "sampler_simt.cu", "sampler_tc.cu", "sampler_ws.cu", "selftest_umma.cu", "mpv_reduce.cu", "sigma_est.cu",
            "infill_steps.cu", "stg_steps.cu", "fx_fused.cu", "fx_attention.cu", "dts_attention.cu", "dts_norm.cu"]
-HEADERS = ["upd_common.cuh", "sampler_params.cuh", "sampler_math.cuh", "tc_helpers.cuh"]
+HEADERS = ["upd_common.cuh", "sampler_params.cuh", "sampler_math.cuh", "sampler_epi.cuh", "tc_helpers.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

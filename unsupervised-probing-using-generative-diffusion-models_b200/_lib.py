@@ -18,7 +18,7 @@ SYMBOLS = (
 
 ABI_VERSION = 6     # = UPD_ABI_VERSION of the csrc/ this binding was written against (argument lists below)
 KIND_NSDIFF, KIND_TMDM = 0, 1
-IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X2, IMPL_TCGEN05_X3W = 0, 1, 2, 3
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X2, IMPL_TCGEN05_WS = 0, 1, 2, 4
 _fp = ctypes.POINTER(ctypes.c_float)
 
 

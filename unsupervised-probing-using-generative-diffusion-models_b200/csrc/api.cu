@@ -231,7 +231,7 @@ static int sample_common(int kind, const void* packed, const float* y0_hat, cons
   if (kind == UPD_KIND_TMDM && !y0_hat) return UPD_ERR_BAD_ARG;
   if (!dims_ok(kind, F, T)) return UPD_ERR_UNSUPPORTED;
   if (noise && (K % S) != 0) return UPD_ERR_BAD_ARG;
-  if (impl != UPD_IMPL_TCGEN05 && impl != UPD_IMPL_SIMT && impl != UPD_IMPL_TCGEN05_X2 && impl != UPD_IMPL_TCGEN05_X3W)
+  if (impl != UPD_IMPL_TCGEN05 && impl != UPD_IMPL_SIMT && impl != UPD_IMPL_TCGEN05_X2 && impl != UPD_IMPL_TCGEN05_WS)
     return UPD_ERR_BAD_ARG;
   if ((reinterpret_cast<uintptr_t>(packed) & 127) != 0) return UPD_ERR_BAD_ARG;
   int sms = 0;
@@ -249,13 +249,15 @@ static int sample_common(int kind, const void* packed, const float* y0_hat, cons
   if (impl == UPD_IMPL_SIMT) {
     e = upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream);
   } else if (impl == UPD_IMPL_TCGEN05) {
-    // the library's choice: the measured-faster tile count for (kind, F); a step count whose
-    // embedding tables do not fit next to the weight image in shared memory (T > ~40) runs on the FFMA kernel
-    e = upd_launch_sampler_tc(p, kind, F, upd_default_tiles(kind, F), sms, (cudaStream_t)stream);
-    if (e == cudaErrorInvalidValue) e = upd_launch_sampler_tc(p, kind, F, 2, sms, (cudaStream_t)stream);
+    // the library's choice: the warp-specialised kernel where it is built (F <= 2), else the two-tile kernel; a step
+    // count whose embedding tables do not fit next to the weight image in shared memory (T > ~40) runs on the FFMA kernel
+    e = upd_launch_sampler_ws(p, kind, F, sms, (cudaStream_t)stream);
+    if (e == cudaErrorInvalidValue) e = upd_launch_sampler_tc(p, kind, F, sms, (cudaStream_t)stream);
     if (e == cudaErrorInvalidValue) e = upd_launch_sampler_simt(p, kind, F, sms, (cudaStream_t)stream);
+  } else if (impl == UPD_IMPL_TCGEN05_WS) {
+    e = upd_launch_sampler_ws(p, kind, F, sms, (cudaStream_t)stream);
   } else {
-    e = upd_launch_sampler_tc(p, kind, F, impl == UPD_IMPL_TCGEN05_X3W ? 3 : 2, sms, (cudaStream_t)stream);
+    e = upd_launch_sampler_tc(p, kind, F, sms, (cudaStream_t)stream);
   }
   if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
   return e == cudaSuccess ? UPD_OK : cuda_fail(e);

@@ -48,7 +48,7 @@ __device__ __forceinline__ float upd_draw(const UpdSamplerParams& p, const UpdRo
 }
 
 cudaError_t upd_launch_sampler_simt(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);
-// tiles = 2 or 3 row tiles per SM (sampler_tc.cu); cudaErrorInvalidValue = shape not built / shared memory exceeded
-cudaError_t upd_launch_sampler_tc(const UpdSamplerParams& p, int kind, int F, int tiles, int sms, cudaStream_t stream);
-// tile count UPD_IMPL_TCGEN05 uses for (kind, F): the measured-faster orchestration
-inline int upd_default_tiles(int kind, int F) { return (F <= 2) ? UPD_DEFAULT_TILES : 2; }
+// two-tile tcgen05 sampler (sampler_tc.cu): F <= 4; cudaErrorInvalidValue = shape not built / shared memory exceeded
+cudaError_t upd_launch_sampler_tc(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);
+// warp-specialised tcgen05 sampler (sampler_ws.cu): F <= 2; cudaErrorInvalidValue otherwise
+cudaError_t upd_launch_sampler_ws(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);

@@ -28,7 +28,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x2000;\n\t"   // suspend-time hint: sleep in hardware, do not spin on the issue port
         "selp.u32 %0, 1, 0, p;\n\t"
         "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
   } while (!done);
@@ -163,23 +163,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-               ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-// tmem_ld16 under a warp-uniform predicate (software pipelines: no load past the last group, no branch in the body)
-__device__ __forceinline__ void tmem_ld16_if(bool pred, uint32_t taddr, uint32_t (&r)[16]) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %17, 0;\n\t"
-      "@p tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
-      "}"
-      : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-        "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-      : "r"(taddr), "r"((uint32_t)pred) : "memory");
-}
 // width-generic forms (N = 8, 16, 32 columns of this thread's TMEM lane)
 template <int N> __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t (&r)[N]) {
   static_assert(N == 8 || N == 16 || N == 32, "TMEM 32x32b shapes used here: x8, x16, x32");
@@ -223,6 +206,23 @@ __device__ __forceinline__ void issue_layer_f16x3_g16(uint32_t d_tmem, uint32_t 
     uint64_t b_hi = smem_desc(bhi_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
     uint64_t b_lo = smem_desc(blo_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
     mma_f16_ts(d_tmem, a_lo, b_hi, IDESC_F16_M128_N128, j > 0);
+    mma_f16_ts(d_tmem, a_hi, b_lo, IDESC_F16_M128_N128, true);
+    mma_f16_ts(d_tmem, a_hi, b_hi, IDESC_F16_M128_N128, true);
+  }
+}
+// The same contraction restricted to the even (parity 0) or odd (parity 1) K-slices: the warp-specialised sampler issues
+// the even slices of a layer as soon as every epilogue warp has written the first 16 of its 32 columns, so that half of
+// the layer's tensor time is spent while the epilogue of the other 16 columns is still running.
+__device__ __forceinline__ void issue_kparity_f16x3_g16(uint32_t d_tmem, uint32_t a_tmem, uint32_t bhi_smem,
+                                                        uint32_t blo_smem, uint32_t lbo, uint32_t sbo, int parity) {
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const int j = 2 * jj + parity;
+    uint32_t a_hi = a_tmem + 16u * j;
+    uint32_t a_lo = a_hi + 8u;
+    uint64_t b_hi = smem_desc(bhi_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
+    uint64_t b_lo = smem_desc(blo_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
+    mma_f16_ts(d_tmem, a_lo, b_hi, IDESC_F16_M128_N128, parity != 0 || jj > 0);
     mma_f16_ts(d_tmem, a_hi, b_lo, IDESC_F16_M128_N128, true);
     mma_f16_ts(d_tmem, a_hi, b_hi, IDESC_F16_M128_N128, true);
   }

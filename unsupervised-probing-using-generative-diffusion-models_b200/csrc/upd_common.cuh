@@ -7,9 +7,6 @@
 #define UPD_MAX_F 4
 #define UPD_MAX_T 64
 #define UPD_ABI_VERSION 6
-#ifndef UPD_DEFAULT_TILES
-#define UPD_DEFAULT_TILES 2    // row tiles per SM of the tcgen05 sampler when the caller leaves the choice to the library
-#endif
 
 #ifdef __CUDACC__
 #define UPD_HD __host__ __device__ __forceinline__

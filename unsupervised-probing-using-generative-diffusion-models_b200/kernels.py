@@ -5,7 +5,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_X2, IMPL_TCGEN05_X3W, KIND_NSDIFF, KIND_TMDM  # noqa: F401
+from ._lib import IMPL_SIMT, IMPL_TCGEN05, IMPL_TCGEN05_X2, IMPL_TCGEN05_WS, KIND_NSDIFF, KIND_TMDM  # noqa: F401
 
 DEN = "model.diffussion_model."   # the reference's spelling, part of the checkpoint key names
 

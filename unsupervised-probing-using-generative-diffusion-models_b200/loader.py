@@ -37,23 +37,37 @@ def diffusion_models(task_model, net_param, **kwargs):
     raise ValueError("the definition  don't exit\n\tyou can define it before using it")
 
 
+def _load_checkpoint(path):
+    """{'net_param': dict, 'state_dict': OrderedDict} as utils/utils.py:611-622 saves it.  The reference full-unpickles
+    (utils/utils.py:670); here the tensor-only loader is tried first -- the shipped checkpoints hold nothing but tensors,
+    plain containers and a ``torch.device`` in net_param -- so that a third-party ``model_trained`` cannot run code on
+    load.  A checkpoint that needs arbitrary pickled classes is refused unless UPD_ALLOW_PICKLE=1 opts in."""
+    import os
+    import pickle
+    try:
+        with torch.serialization.safe_globals([torch.device]):
+            return torch.load(path, map_location="cpu", weights_only=True)
+    except pickle.UnpicklingError as exc:
+        if os.environ.get("UPD_ALLOW_PICKLE") != "1":
+            raise RuntimeError("{} is not a tensor-only checkpoint ({}); set UPD_ALLOW_PICKLE=1 to full-unpickle it as "
+                               "the reference does".format(path, str(exc).splitlines()[0])) from exc
+        with open(path, "rb") as f:
+            return torch.load(f, map_location=lambda storage, loc: storage, weights_only=False)
+
+
 def load_diffusion_model(path, device, infer_para=None, dataparallel=True, **kwargs):
     """utils/utils.py:660-689: full-pickle load, ``infer_para`` merged before construction (so it can
     change n_z_samples / parallel_sample / diffusion_steps), ``module.`` prefixes stripped,
     ``net_param['device']`` overwritten, strict state-dict load.  -> (model, loaded_net_param)."""
     device = _lib.require_cuda(device)
-    with open(path, "rb") as f:
-        state = torch.load(f, map_location=lambda storage, loc: storage, weights_only=False)
+    state = _load_checkpoint(path)
     loaded_net_param = state["net_param"]
     if infer_para is not None:
         loaded_net_param.update(infer_para)
     loaded_state_dict = state["state_dict"]
-    if not torch.cuda.device_count() > 1 or not dataparallel:
-        loaded_state_dict = {k.replace("module.", ""): v for k, v in loaded_state_dict.items()}
-    else:
-        # the reference keeps the prefix when several GPUs are visible because it would wrap the model in
-        # DataParallel; this build runs one process per GPU and never wraps, so the prefix always goes
-        loaded_state_dict = {k.replace("module.", ""): v for k, v in loaded_state_dict.items()}
+    # the reference keeps the ``module.`` prefix when several GPUs are visible because it would wrap the model in
+    # DataParallel; this build runs one process per GPU and never wraps, so the prefix always goes
+    loaded_state_dict = {k.replace("module.", ""): v for k, v in loaded_state_dict.items()}
     loaded_net_param["device"] = device
     model = diffusion_models(task_model=loaded_net_param["task_model"], net_param=loaded_net_param,
                              train_model_select=kwargs["train_model_select"]).to(device)

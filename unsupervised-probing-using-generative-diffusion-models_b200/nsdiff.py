@@ -104,7 +104,7 @@ class _NsDiffBase(nn.Module):
         self.register_buffer("scaler_mean", torch.zeros(self.dataset_nf))
         self.register_buffer("scaler_std", torch.zeros(self.dataset_nf))
         # three-tile rotation kernel where it is the faster one (several features: +6.5 %, csrc/sampler_tc3w.cu)
-        self.sampler_impl = kernels.IMPL_TCGEN05_X3W if self.dataset_nf > 1 else kernels.IMPL_TCGEN05
+        self.sampler_impl = kernels.IMPL_TCGEN05      # the library picks the kernel for (kind, F, T), include/upd_b200.h
         self._packed = None
         self._packed_key = None
         self._windows_drawn = 0

@@ -72,7 +72,7 @@ class TMDM_model(nn.Module):
         self.register_buffer("scaler_std", torch.ones(self.dataset_nf))
         self.model = TmdmNet(self.configs, self.device)
         self.cond_pred_model = NsTransformer(self.configs, vae=True)
-        self.sampler_impl = kernels.IMPL_TCGEN05_X3W        # +1.3 % over the two-tile kernel for TMDM (csrc/sampler_tc3w.cu)
+        self.sampler_impl = kernels.IMPL_TCGEN05      # the library picks the kernel for (kind, F, T), include/upd_b200.h
         self._packed = None
         self._packed_key = None
         self._windows_drawn = 0

@@ -15,6 +15,8 @@ import threading
 from pathlib import Path
 
 import numpy as np
+import weakref
+
 import torch
 import yaml
 
@@ -428,8 +430,17 @@ def _scale_windows(model, stacked, device):
 
 
 # Statistics computed on the device while a freshly sampled sweep is still resident, keyed by the host
-# cache's storage address, so summarize_*() right after run_*_cache() does not upload the cache again.
+# cache's storage address, so summarize_*() right after run_*_cache() does not upload the cache again.  An entry is
+# only trusted while it provably describes the tensors handed to summarize_*: it holds a weak reference to the cache
+# (a freed block reused by another tensor misses), the cache's version counter (any in-place edit of an element
+# misses: views share the counter) and the scaler table the "raw" statistics were baked with.
 _FRESH_STATS = {}
+
+
+def _scaler_snapshot(model):
+    if model is None or not hasattr(model, "scaler_mean") or not hasattr(model, "scaler_std"):
+        return None
+    return (tuple(model.scaler_mean.detach().float().cpu().tolist()), tuple(model.scaler_std.detach().float().cpu().tolist()))
 
 
 def partition_windows(n_windows, world_size, rank):
@@ -493,19 +504,28 @@ def sample_sweep(model, stacked_windows, device=None, pin=True, reduce=True, win
     if reduce:
         if len(_FRESH_STATS) > 8:
             _FRESH_STATS.clear()
-        _FRESH_STATS[cache.untyped_storage().data_ptr()] = (tuple(cache.shape), stats)
+        _FRESH_STATS[cache.untyped_storage().data_ptr()] = (weakref.ref(cache), cache._version, tuple(cache.shape),
+                                                            _scaler_snapshot(model), stats)
     cache.upd_stats = stats
     return cache
 
 
-def _fresh_stats_for(pred_future_list, elem_shape):
-    """Stats remembered by sample_sweep if ``pred_future_list`` is exactly that sweep's list of views."""
+def _fresh_stats_for(pred_future_list, elem_shape, model=None, need_scaler=False):
+    """Stats remembered by sample_sweep if ``pred_future_list`` is exactly that sweep's list of views, unmodified
+    (and, for the raw-unit statistics, if ``model`` still carries the scaler they were computed with)."""
     if not pred_future_list or not isinstance(pred_future_list[0], torch.Tensor):
         return None
-    hit = _FRESH_STATS.get(pred_future_list[0].untyped_storage().data_ptr())
+    key = pred_future_list[0].untyped_storage().data_ptr()
+    hit = _FRESH_STATS.get(key)
     if hit is None:
         return None
-    shape, stats = hit
+    ref, version, shape, scaler, stats = hit
+    owner = ref()
+    if owner is None or owner.untyped_storage().data_ptr() != key or pred_future_list[0]._version != version:
+        _FRESH_STATS.pop(key, None)
+        return None
+    if need_scaler and scaler != _scaler_snapshot(model):
+        return None
     W, B, K, O, F = shape
     if len(pred_future_list) != W or tuple(elem_shape) != (B, O, F, K):
         return None
@@ -519,7 +539,11 @@ def _samples_per_row(model):
     cfg = model.configs
     S = int(getattr(cfg, "parallel_sample", 1))
     K = int(getattr(cfg, "n_z_samples", 1))
-    S = min(S, K) if S > 0 else 1
+    if S <= 0 or K // S == 0:
+        # the reference's chunk loop `for _ in range(n_z_samples // parallel_sample)` is then empty and its
+        # torch.cat(outs, dim=1) raises (NsDiff_model.py:227-247, tmdm_adapter.py:132-151): same failure here, no clamp
+        raise RuntimeError("torch.cat(): expected a non-empty list of Tensors (n_z_samples={} // parallel_sample={} "
+                           "chunks)".format(K, S))
     return (K // S) * S
 
 
@@ -770,7 +794,7 @@ def summarize_pred_future_list(pred_future_list, model=None):
     scale = _scaler_table(model)
     if scale is not None and scale.shape[1] != elems[0].shape[-2]:
         scale = None
-    fresh = _fresh_stats_for(elems, elems[0].shape)
+    fresh = _fresh_stats_for(elems, elems[0].shape, model=model, need_scaler=scale is not None)
     key = "raw" if scale is not None else "scaled"
     if fresh is not None and key in fresh:
         r = fresh[key]
