@@ -15,8 +15,13 @@ reverse-diffusion sampler (W*B*K = 1.81e6 trajectories, 3.62e9 denoiser row-step
   value : whole-job trajectories/s with the windows already resident in HBM (device-timed, max over ranks)
   e2e   : the same through the public host API (uncertainty.sample_sweep) with HOST buffers: H2D of the
           windows from pinned memory, D2H of the trajectory cache + per-window MPV inside the timed region
-Multi-GPU (weak scaling): every rank sweeps its own W windows (rank-seeded series), one all-gather of the
-per-window statistics, no data-path collective.
+Multi-GPU (torchrun, STRONG scaling -- BASELINE's "MPV sweep wall time at 1/2/4/8 B200"): the same ONE 181-window sweep
+is sharded over the ranks in contiguous window blocks (uncertainty.partition_windows); every step ends with the single
+all-gather of per-window statistics, inside the timed region; value = the sweep's 1.81e6 trajectories / max-over-ranks
+time.  The weak-scaling figure (every rank sweeps its own 181 windows) is reported as the side key "weak".
+Extra keys at N = 1: "parity" (a whole window through the CPU oracle with recorded noise against the GPU path, with the
+north-star tolerances), "configs" (BASELINE configs 1, 3, 4-truncated, 5: e2e rate, dominant kernel, roofline fraction),
+"sweep_wall", "cpu_baseline".
 `--impl reference` times the reference's CPU implementation of the same path: the reference is pure Python
 that cannot travel to the GPU box, so this arm runs the CPU oracle port (oracle/, pinned to the reference by
 the golden fixtures; f(x) part "parity unpinned") on all host threads, on a bounded sample of the workload.
@@ -39,6 +44,9 @@ METRIC = "sampled trajectories/sec (K x windows), NsDiff MPV sweep"
 UNIT = "trajectories/s"
 YAML = os.path.join(ROOT, "tests", "golden", "ews_results", "model_compare", "NsDiff", "biomass", "model_trained.yaml")
 MACS_PER_ROW_STEP_F1 = 3 * 1 * 128 + 2 * 128 * 128 + 2 * 128 * 1          # 33 408 for F = 1
+# tensor work actually issued per row-step: three split passes of the two 128x128 layers (fp16) + of the 8-wide layer 1
+# (tf32, half rate: counted twice); the dense fp16 rate of an SM is 8192 FLOP/clk (2.25 PFLOP/s / 148 SMs / 1.86 GHz)
+ISSUED_F16_FLOPS_PER_ROW_STEP = 3 * 2 * (2 * 128 * 128) + 2 * (3 * 2 * 8 * 128)
 
 
 def workload_config():
@@ -192,10 +200,172 @@ def run_reference_arm(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------------
+def _ev():
+    return torch.cuda.Event(enable_timing=True)
+
+
+def _timed_ms(fn, n, dev):
+    fn()
+    torch.cuda.synchronize(dev)
+    a, b = _ev(), _ev()
+    a.record()
+    for _ in range(n):
+        r = fn()
+    b.record()
+    torch.cuda.synchronize(dev)
+    return a.elapsed_time(b) / n, r
+
+
+def other_configs(dev, peaks):
+    """BASELINE configs 1, 3, 4 (truncated) and 5 through the public sweep API on one GPU: e2e rate with host windows in
+    and the trajectory cache out, the dominant kernel and a roofline fraction each (a few seconds per config).  Seeded
+    random weights of the YAML architectures except config 1, which is the reference's shipped checkpoint."""
+    import yaml
+    from updgm_b200 import kernels, uncertainty as U
+    G = os.path.join(ROOT, "tests", "golden", "ews_results")
+    out = {}
+    bf16 = peaks["bf16_sustained"]
+
+    def guarded(name, fn):
+        try:
+            t0 = time.perf_counter()
+            out[name] = fn()
+            out[name]["bench_seconds"] = time.perf_counter() - t0
+        except Exception as exc:                      # a failing side config must not take the headline line with it
+            out[name] = {"error": "{}: {}".format(type(exc).__name__, str(exc)[:200])}
+
+    def config1():
+        m, _ = U.load_model_from_dir(os.path.join(G, "NsDiff_machine", "wo_fx"), device=dev)
+        g = torch.Generator().manual_seed(0)
+        x = torch.zeros(10000, 2)
+        e = torch.randn(10000, 2, generator=g) * 0.1
+        for t in range(1, 10000):
+            x[t] = 0.99 * x[t - 1] + e[t]
+        series = x * m.scaler_std.cpu() + m.scaler_mean.cpu()
+        wins = series.unfold(0, 200, 10).permute(0, 2, 1).unsqueeze(1).contiguous().pin_memory()      # [981,1,200,2]
+        W, K, O, F, T = wins.shape[0], 100, 200, 2, 20
+        e2e_ms, _ = _timed_ms(lambda: U.sample_sweep(m, wins, device=dev), 3, dev)
+        xs = m.scaler_transform(wins.to(dev)).view(W, 200, 2)
+        with torch.no_grad():
+            y0, gx = m.condition(xs)
+        traj = torch.empty((W, K, O, F), dtype=torch.float32, device=dev)
+        k_ms, _ = _timed_ms(lambda: kernels.nsdiff_sample(m.packed_weights(), y0, gx, W, 1, K, 100, O, F, T, seed=1, out=traj,
+                                                          impl=m.sampler_impl), 5, dev)
+        rs = W * K * O * T
+        tf = 2.0 * (3 * F * 128 + 2 * 128 * 128 + 2 * 128 * F) * rs / (k_ms * 1e-3) / 1e12
+        return {"workload": "configs[0]: NsDiff SLBP, shipped wo_fx checkpoint, W=981 windows, K=100, F=2, O=200",
+                "e2e": {"value": W * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_sweep": e2e_ms},
+                "dominant_kernel": "sampler_ws_kernel<NsDiff,F=2>", "kernel_ms": k_ms, "kernel_share_of_e2e": k_ms / e2e_ms,
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16, "unit": "TFLOP/s", "frac": tf / bf16,
+                             "row_steps_per_s": rs / (k_ms * 1e-3)}}
+
+    def config3():
+        from updgm_b200.tmdm import TMDM_model
+        cfg = yaml.safe_load(open(os.path.join(G, "model_compare", "TMDM", "neuronal", "model_trained.yaml")))
+        torch.manual_seed(123)
+        tm = TMDM_model(dict(cfg["net"], device=dev)).eval()
+        g = torch.Generator().manual_seed(0)
+        s = torch.sigmoid((torch.randn(100, 1000, 1, generator=g) * 0.1).cumsum(1))
+        wins = s.unfold(1, 100, 5).permute(1, 0, 3, 2).contiguous().pin_memory()                        # [181,100,100,1]
+        W, B, K, Lr, T = wins.shape[0], 100, 100, 150, 20
+        e2e_ms, _ = _timed_ms(lambda: U.sample_sweep(tm, wins, device=dev), 2, dev)
+        with torch.no_grad():
+            y0 = tm.condition(wins.to(dev).view(W * B, 100, 1))
+        traj = torch.empty((W * B, K, Lr, 1), dtype=torch.float32, device=dev)
+        k_ms, _ = _timed_ms(lambda: kernels.tmdm_sample(tm.packed_weights(), y0, W, B, K, 10, Lr, 1, T, seed=1, out=traj,
+                                                        impl=tm.sampler_impl), 2, dev)
+        rs = W * B * K * Lr * T
+        tf = 2.0 * (2 * 128 + 2 * 128 * 128 + 128) * rs / (k_ms * 1e-3) / 1e12
+        return {"workload": "configs[2]: TMDM neuronal ER-100, W=181, B=100, K=100, 150 positions per trajectory",
+                "e2e": {"value": W * B * K / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_sweep": e2e_ms},
+                "dominant_kernel": "sampler_ws_kernel<TMDM,F=1>", "kernel_ms": k_ms, "kernel_share_of_e2e": k_ms / e2e_ms,
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16, "unit": "TFLOP/s", "frac": tf / bf16,
+                             "row_steps_per_s": rs / (k_ms * 1e-3)}}
+
+    def config4():
+        from updgm_b200.diffusionts import DiffusionTS_model
+        cfg = yaml.safe_load(open(os.path.join(G, "model_compare", "DiffusionTS", "SIS", "model_trained.yaml")))
+        torch.manual_seed(123)
+        d = DiffusionTS_model(dict(cfg["net"], device=dev, n_z_samples=10, parallel_sample=10)).eval()
+        d.rows_per_launch = 1000
+        g = torch.Generator().manual_seed(0)
+        wins = torch.sigmoid((torch.randn(1, 100, 100, 1, generator=g) * 0.1).cumsum(2)).pin_memory()   # 1 window, 100 nodes
+        U.sample_sweep(d, wins[:, :10].contiguous(), device=dev)                                        # warm-up (100 rows)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        cache = U.sample_sweep(d, wins, device=dev)
+        torch.cuda.synchronize(dev)
+        sec = time.perf_counter() - t0
+        n = cache.shape[0] * cache.shape[1] * cache.shape[2]
+        # SURVEY 8a14: 0.43 GFLOP per forward per sequence, 100 forwards + 128 forward/backward (3x) passes per trajectory
+        flop = (100 + 3 * 128) * 0.43e9
+        tf = n / sec * flop / 1e12
+        return {"workload": "configs[3] truncated: DiffusionTS SIS, 1 window x 100 nodes x K=10 (of 199 windows x K=100), "
+                            "seq 200, 100 sampling steps with Langevin infill",
+                "e2e": {"value": n / sec, "unit": UNIT, "ms_per_sweep": sec * 1e3},
+                "dominant_kernel": "dts_attn_fwd / dts_attn_bwd (see profiles/)",
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16, "unit": "TFLOP/s", "frac": tf / bf16,
+                             "note": "whole sweep, algorithmic 208 GFLOP per trajectory (SURVEY 8a14)"}}
+
+    def config5():
+        from updgm_b200.diffstg import DiffSTG
+        import networkx as nx
+        from types import SimpleNamespace
+        cfg = yaml.safe_load(open(os.path.join(G, "model_compare", "DiffSTG", "biomass", "model_trained.yaml")))
+        torch.manual_seed(123)
+        m = DiffSTG(dict(cfg["net"], device=dev)).eval()
+        Gr = nx.barabasi_albert_graph(100, 12, seed=0)
+        ei = torch.tensor(list(Gr.to_directed().edges)).t().contiguous()
+        graph = SimpleNamespace(edge_index=ei.to(dev), num_nodes=100)
+        g = torch.Generator().manual_seed(0)
+        wins = (torch.randn(4, 100, 100, 1, generator=g) * 0.1).cumsum(2).contiguous().pin_memory()     # 4 windows
+        U.sample_sweep(m, wins[:1], device=dev, graph_data=graph)
+        e2e_ms, cache = _timed_ms(lambda: U.sample_sweep(m, wins, device=dev, graph_data=graph), 2, dev)
+        n = cache.shape[0] * cache.shape[1] * cache.shape[2]                                            # window x node x sample
+        tf = n / (e2e_ms * 1e-3) * 1.0e9 / 1e12                                                         # ~1 GFLOP per node-trajectory
+        return {"workload": "configs[4] at (T_h, T_p) = (100, 100): DiffSTG biomass, BA-100 graph, 4 windows x 100 nodes x "
+                            "100 samples (10 rounds x 10 replicas), 20 DDIM steps",
+                "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "node-trajectories/s", "ms_per_sweep": e2e_ms},
+                "dominant_kernel": "stg_tcn_ln_kernel (see profiles/)",
+                "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16, "unit": "TFLOP/s", "frac": tf / bf16,
+                             "note": "whole sweep, ~1 GFLOP per node-trajectory (SURVEY 8a15 estimate)"}}
+
+    guarded("config1_nsdiff_slbp", config1)
+    guarded("config3_tmdm_neuronal", config3)
+    guarded("config4_diffusionts_sis", config4)
+    guarded("config5_diffstg_biomass", config5)
+    return out
+
+
+def parity_and_cpu_baseline(cfg, model, dev, threads):
+    """One whole window of the workload (1e6 denoiser rows x 20 steps) through the CPU oracle with recorded noise:
+    (a) the north-star parity check of the GPU path on exactly that window and noise, (b) the CPU baseline rate."""
+    from oracle import parity
+    net = dict(cfg["net"])
+    series = make_series(0)
+    x = series[:, 400:500, :].contiguous()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref = parity.nsdiff_window_reference(sd, net, x, seed=11, with_fx=True, threads=threads)      # also the warm-up
+    with torch.no_grad():
+        outs, _ = model.evaluation_step(x.to(dev), noise=ref["noise"][0])
+    chk = parity.compare(outs, ref["ref"])
+    chk["what"] = ("window 80 of the sweep, whole (100 rows x K=100 x O=100 x T=20), f(x)+g(x)+sampler on the GPU vs the CPU "
+                   "oracle on the same recorded noise; f(x) itself is parity-unpinned (DESIGN.md)")
+    times = []
+    for rep in range(2):
+        times.append(parity.nsdiff_window_reference(sd, net, x, seed=12 + rep, with_fx=True, threads=threads)["seconds"])
+    sec = sum(times) / len(times)
+    rate = x.shape[0] * net["n_z_samples"] / sec
+    base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": "100 of 100 rows of one window x K=100 (x2 repeats after 1 warm-up), f(x)+g(x)+sampler, "
+                      "{:.1f} s per repeat".format(sec)}
+    return chk, base
+
+
 def run_own_arm(args, rank, world, local_rank):
     import torch.distributed as dist
     import updgm_b200  # noqa: F401
-    from updgm_b200 import kernels, uncertainty as U
+    from updgm_b200 import _lib, kernels, uncertainty as U
     from updgm_b200.nsdiff import NsDiff_model
 
     dev = torch.device("cuda", local_rank)
@@ -209,33 +379,38 @@ def run_own_arm(args, rank, world, local_rank):
     S = int(net["parallel_sample"])
     K = (int(net["n_z_samples"]) // S) * S
     T = net["diffusion_steps"]
-    series = make_series(rank)
-    stacked = U.stacked_sliding_windows(series, L, 5).contiguous()             # [W,B,L,F] raw units, host
+    # ONE sweep (the series of rank 0), sharded over the ranks in contiguous window blocks: strong scaling
+    stacked = U.stacked_sliding_windows(make_series(0), L, 5).contiguous()      # [W,B,L,F] raw units, host
     W, B = stacked.shape[0], stacked.shape[1]
+    lo, hi = U.partition_windows(W, world, rank)
+    Wl = hi - lo
     host_windows = stacked.pin_memory()
-    x_dev = model.scaler_transform(host_windows.to(dev)).contiguous()
-    traj = torch.empty((W * B, K, O, F), dtype=torch.float32, device=dev)
+    x_dev = model.scaler_transform(host_windows[lo:hi].to(dev)).contiguous()
+    traj = torch.empty((max(Wl, 1) * B, K, O, F), dtype=torch.float32, device=dev)
     packed = model.packed_weights()
-    n_traj = W * B * K
-    row_steps = n_traj * O * T
+    n_traj = W * B * K                                  # of the whole sweep
+    row_steps_local = Wl * B * K * O * T
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    from updgm_b200 import _lib
-    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
     sampler_ms = []
 
     def step_resident(i, timed):
         with torch.no_grad():
-            y0, gx = model.condition(x_dev.view(W * B, L, F))
-            a, b = ev(), ev()
+            y0, gx = model.condition(x_dev.view(Wl * B, L, F))
+            a, b = _ev(), _ev()
             a.record()
-            kernels.nsdiff_sample(packed, y0, gx, W, B, K, S, O, F, T, seed=1234, window_base=i * W, out=traj)
+            kernels.nsdiff_sample(packed, y0, gx, Wl, B, K, S, O, F, T, seed=1234, window_base=i * W + lo, out=traj,
+                                  impl=model.sampler_impl)
             b.record()
-            red = kernels.mpv_reduce(traj, W, B)
+            red = kernels.mpv_reduce(traj, Wl, B)
+            if world > 1:                              # the one collective of a sweep, inside the timed region
+                local = torch.cat([red["mpv"].view(-1, 1), red["pred_mean"].view(-1, 1), red["mpv_f"]], dim=1)
+                stats = U.gather_window_stats(local, W)
+                assert stats.shape[0] == W
         if timed:
             sampler_ms.append((a, b))
         return red
@@ -245,84 +420,108 @@ def run_own_arm(args, rank, world, local_rank):
     barrier()
     launches0 = _lib.kernel_launches()                 # own kernels only: every C-ABI launch is counted in _lib.check
     with ClockSampler(local_rank) as clocks:
-        t0, t1 = ev(), ev()
+        t0, t1 = _ev(), _ev()
         t0.record()
         for i in range(args.steps):
-            red = step_resident(args.warmup + i, True)
+            step_resident(args.warmup + i, True)
         t1.record()
         barrier()
         resident_ms = t0.elapsed_time(t1)
     launches = _lib.kernel_launches() - launches0      # per step: sampler, g(x), Welford + window means, and f(x)'s
                                                        # attention / LayerNorm-split / split kernels per 4096-row chunk
-    if world > 1:                                      # the one collective of a sweep (outside no stage of compute)
-        local = torch.cat([red["mpv"].view(-1, 1), red["pred_mean"].view(-1, 1), red["mpv_f"]], dim=1)
-        stats = U.gather_window_stats(local, W * world)
-        assert stats.shape[0] == W * world
     kern_ms = sum(a.elapsed_time(b) for a, b in sampler_ms) / len(sampler_ms)
 
-    # ---- end to end through the public host API: pinned host windows in, trajectory cache + MPV out ----
+    # ---- end to end through the public host API: pinned host windows in, trajectory cache + per-window MPV out ----
+    def sweep_e2e():
+        if world > 1:
+            return U.distributed_sweep(model, host_windows, device=dev)[0]
+        return U.sample_sweep(model, host_windows, device=dev)
+
     for i in range(min(args.warmup, 2)):
-        U.sample_sweep(model, host_windows, device=dev)
+        sweep_e2e()
     barrier()
-    e0, e1 = ev(), ev()
+    e0, e1 = _ev(), _ev()
     e0.record()
     for i in range(args.steps):
-        cache = U.sample_sweep(model, host_windows, device=dev)
+        cache = sweep_e2e()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    h2d = host_windows.numel() * 4
-    d2h = cache.numel() * 4 + sum(v.numel() * 4 for part in cache.upd_stats.values() for v in part.values())
+    h2d = host_windows[lo:hi].numel() * 4
+    d2h = cache.numel() * 4 + (sum(v.numel() * 4 for part in cache.upd_stats.values() for v in part.values())
+                               if hasattr(cache, "upd_stats") else 0)
 
-    # ---- N > 1: ONE sweep (rank 0's series) sharded over the ranks: contiguous window blocks, rank-local caches, the
-    # single all-gather of per-window statistics -- the strong-scaling wall time of BASELINE's second metric
-    dist_ms = 0.0
+    # ---- N > 1, side measurement: weak scaling (every rank sweeps its OWN 181 windows, rank-seeded series) ----
+    weak_ms = 0.0
     if world > 1:
-        shared = U.stacked_sliding_windows(make_series(0), L, 5).contiguous().pin_memory()
-        U.distributed_sweep(model, shared, device=dev)                     # warm-up (NCCL communicator, allocator)
+        own = model.scaler_transform(U.stacked_sliding_windows(make_series(rank), L, 5).contiguous().to(dev)).contiguous()
+        big = torch.empty((W * B, K, O, F), dtype=torch.float32, device=dev)
+
+        def weak_step():
+            with torch.no_grad():
+                y0, gx = model.condition(own.view(W * B, L, F))
+                kernels.nsdiff_sample(packed, y0, gx, W, B, K, S, O, F, T, seed=99, window_base=0, out=big, impl=model.sampler_impl)
+                kernels.mpv_reduce(big, W, B)
+        weak_step()
         barrier()
-        w0 = time.perf_counter()
-        _, (lo, hi), stats = U.distributed_sweep(model, shared, device=dev)
-        torch.cuda.synchronize(dev)
-        dist_ms = (time.perf_counter() - w0) * 1e3
-        assert stats["mpv"].shape[0] == shared.shape[0]
+        w0_, w1_ = _ev(), _ev()
+        w0_.record()
+        for _ in range(2):
+            weak_step()
+        w1_.record()
+        barrier()
+        weak_ms = w0_.elapsed_time(w1_) / 2
 
-    times = torch.tensor([resident_ms, e2e_ms, dist_ms], dtype=torch.float64, device=dev)
+    vals = torch.tensor([resident_ms, e2e_ms, weak_ms, kern_ms, float(launches), float(h2d), float(d2h)], dtype=torch.float64, device=dev)
+    sums = vals.clone()
     if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    resident_ms, e2e_ms, dist_ms = times.tolist()
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    resident_ms, e2e_ms, weak_ms, kern_ms_max = vals.tolist()[:4]
+    launches_all, h2d_all, d2h_all = (int(v) for v in sums.tolist()[4:])
     if rank != 0:
         return
     peaks = measured_peaks()
-    value = n_traj * world * args.steps / (resident_ms * 1e-3)
-    e2e = n_traj * world * args.steps / (e2e_ms * 1e-3)
-    flops = 2.0 * MACS_PER_ROW_STEP_F1 * row_steps
+    value = n_traj * args.steps / (resident_ms * 1e-3)
+    e2e = n_traj * args.steps / (e2e_ms * 1e-3)
+    flops = 2.0 * MACS_PER_ROW_STEP_F1 * row_steps_local            # rank 0's launch
     achieved = flops / (kern_ms * 1e-3) / 1e12
+    rs_per_s = row_steps_local / (kern_ms * 1e-3)
+    clk = clocks.summary()
+    sm_hz = (clk.get("sm_mhz") or 1900.0) * 1e6
+    mufu_per_row_step = 2 * 386                                      # 384 hidden softplus + the sigma head's outer one: ex2 + lg2 each
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": config_dict(cfg, W, B),
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_dict(cfg, W, B, {"windows_per_gpu": Wl if world > 1 else W, "windows_total": W,
+                                          "sharding": "one {}-window sweep in contiguous window blocks over {} rank(s); one "
+                                                      "all-gather of [W, 2+F] statistics per sweep, inside the timed region"
+                                                      .format(W, world)}),
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d_all, "d2h_bytes_per_step": d2h_all,
                 "ms_per_step": e2e_ms / args.steps},
-        "gpu_launches": launches,
-        "clocks": clocks.summary(),
-        "roofline": {"bound": "tensor", "kernel": "sampler_tc_kernel<NsDiff,F=1>", "achieved": achieved,
+        "gpu_launches": launches_all,
+        "clocks": clk,
+        "roofline": {"bound": "tensor", "kernel": "sampler_ws_kernel<NsDiff,F=1>", "achieved": achieved,
                      "peak": peaks["bf16_sustained"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16_sustained"],
                      "traffic": ncu_traffic(), "peak_source": peaks["source"] + " (bf16 dense, sustained: kernel timed inside a long step)",
-                     "algorithmic_flops_per_launch": flops, "kernel_ms": kern_ms,
-                     "row_steps_per_s": row_steps / (kern_ms * 1e-3),
-                     "note": "algorithmic FLOPs = 2*33408 MAC per denoiser row-step (SURVEY 8a7); the MLP is MUFU-bound "
-                             "(514 softplus per row-step), see DESIGN.md"},
+                     "algorithmic_flops_per_launch": flops, "kernel_ms": kern_ms, "row_steps_per_s": rs_per_s,
+                     "mufu_frac": rs_per_s * mufu_per_row_step / (148 * 16 * sm_hz),
+                     "tensor_active": rs_per_s * ISSUED_F16_FLOPS_PER_ROW_STEP / (148 * 8192 * sm_hz),
+                     "note": "per GPU (rank 0's launch).  algorithmic FLOPs = 2*33408 MAC per denoiser row-step (SURVEY 8a7). "
+                             "mufu_frac = 772 ex2/lg2 per row-step against 16 MUFU lanes/clk/SM at the sampled SM clock -- the "
+                             "pipe that bounds this MLP; tensor_active = issued MMA work (3 split passes) against the dense "
+                             "fp16 rate; both derived from the measured row-steps/s, the ncu captures are in profiles/"},
     }
     if world > 1:
-        line["sweep_wall"] = {"one_sweep_sharded_ms": dist_ms, "windows": W, "ranks": world,
-                              "note": "one 181-window sweep split over the ranks (contiguous blocks) + one all-gather of "
-                                      "per-window MPV; max over ranks, wall clock"}
+        line["weak"] = {"value": n_traj * world / (weak_ms * 1e-3), "unit": UNIT, "ms_per_step": weak_ms,
+                        "note": "side measurement: every rank sweeps its own 181 windows (no collective in the loop)"}
     if world == 1:
         # BASELINE's second metric: MPV sweep wall time = windows -> sample -> reduce -> per-window MPV list, cache file
         # written (reference: diffusion_model_uncertainy.py:323-339 + :286-303).  One sweep, outside the timed region.
         import shutil
         import tempfile
+        series = make_series(0)
         tmp = tempfile.mkdtemp(prefix="upd_bench_")
         try:
             torch.cuda.synchronize(dev)
@@ -338,13 +537,15 @@ def run_own_arm(args, rank, world, local_rank):
                                   "note": "cache written by the background writer; MPV list is available at mpv_list_ms"}
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
-    if world == 1 and not os.environ.get("UPD_BENCH_SKIP_CPU"):   # (set only when the run is wrapped in ncu)
-        threads = os.cpu_count() or 1
-        rows = 100
-        rate, sec = cpu_reference_rate(cfg, rows=rows, n_steps=2, n_warm=1, threads=threads)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "{} of 100 rows of one window x K=100 (x2 repeats after 1 warm-up), "
-                                          "f(x)+g(x)+sampler+MPV, {:.1f} s per repeat".format(rows, sec)}
+        del preds, cache
+        if not os.environ.get("UPD_BENCH_SKIP_CONFIGS"):
+            line["configs"] = other_configs(dev, peaks)
+        if not os.environ.get("UPD_BENCH_SKIP_CPU"):                 # (set only when the run is wrapped in ncu)
+            line["parity"], line["cpu_baseline"] = parity_and_cpu_baseline(cfg, model, dev, os.cpu_count() or 1)
+    else:
+        line["sweep_wall"] = {"one_sweep_sharded_ms": e2e_ms / args.steps, "windows": W, "ranks": world,
+                              "note": "= e2e.ms_per_step: one 181-window sweep through uncertainty.distributed_sweep (host "
+                                      "windows in, rank-local caches + gathered MPV list out), device-timed, max over ranks"}
     print(json.dumps(line))
 
 

@@ -359,3 +359,90 @@ def test_public_header_is_plain_c(tmp_path):
     r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(src)],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_tmdm_checkpoint_with_temporal_embedding_tables_loads_strictly():
+    """The reference's TMDM embeddings are torch-timeseries DataEmbedding(..., 'fixed', 'h', ...) (TMDM.py:90,
+    tmdm_ns_transformer.py:53-56): a real checkpoint carries fixed sinusoidal time-mark tables the hot path never reads
+    (x_mark is None).  They -- and nothing else -- are dropped before the strict load."""
+    import yaml
+    from updgm_b200 import loader
+    from updgm_b200.tmdm import TMDM_model
+    cfg = yaml.safe_load(open(os.path.join(GOLDEN, "ews_results", "model_compare", "TMDM", "neuronal", "model_trained.yaml")))
+    m = TMDM_model(dict(cfg["net"], device="cpu"))
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    d = m.configs.d_model
+    extra = {}
+    for emb in ("cond_pred_model.enc_embedding", "cond_pred_model.dec_embedding", "model.enc_embedding"):
+        for name, n in (("hour_embed", 24), ("weekday_embed", 7), ("day_embed", 32), ("month_embed", 13)):
+            extra["{}.temporal_embedding.{}.emb.weight".format(emb, name)] = torch.zeros(n, d)
+    full = dict(sd, **extra)
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        m.load_state_dict(full, strict=True)
+    kept = loader.drop_unused_temporal_tables(m, full)
+    assert set(kept) == set(sd)
+    m.load_state_dict(kept, strict=True)
+    # anything else unexpected still fails the strict load
+    bad = dict(full, **{"model.diffussion_model.lin9.weight": torch.zeros(1)})
+    with pytest.raises(RuntimeError, match="Unexpected key"):
+        m.load_state_dict(loader.drop_unused_temporal_tables(m, bad), strict=True)
+
+
+def test_checkpoint_loader_is_tensor_only_by_default(tmp_path, monkeypatch):
+    """loader._load_checkpoint reads the shipped checkpoint with the tensor-only unpickler and refuses a checkpoint that
+    needs arbitrary classes unless UPD_ALLOW_PICKLE=1 opts into the reference's full unpickle (utils/utils.py:670)."""
+    from updgm_b200 import loader
+    st = loader._load_checkpoint(os.path.join(GOLDEN, "ews_results", "NsDiff_machine", "wo_fx", "model_trained"))
+    assert set(st) == {"net_param", "state_dict"} and len(st["state_dict"]) == 25
+
+    import fractions
+    p = tmp_path / "model_trained"
+    torch.save({"net_param": {"x": fractions.Fraction(1, 3)}, "state_dict": {}}, p)     # a class outside the tensor-only allowlist
+    monkeypatch.delenv("UPD_ALLOW_PICKLE", raising=False)
+    with pytest.raises(RuntimeError, match="UPD_ALLOW_PICKLE"):
+        loader._load_checkpoint(str(p))
+    monkeypatch.setenv("UPD_ALLOW_PICKLE", "1")
+    assert loader._load_checkpoint(str(p))["net_param"]["x"] == fractions.Fraction(1, 3)
+
+
+def test_samples_per_row_reproduces_the_reference_failure_modes():
+    """NsDiff: range(K // S) chunks, remainder dropped, an empty loop fails in torch.cat (NsDiff_model.py:227-247);
+    TMDM / DiffusionTS: S clamped to K, K % S must be 0 (tmdm_adapter.py:125-127, DiffusionTS_model.py:83-85)."""
+    from types import SimpleNamespace
+
+    class NsDiff_model_variants:      # only the class name and .configs matter to _samples_per_row
+        def __init__(self, K, S):
+            self.configs = SimpleNamespace(n_z_samples=K, parallel_sample=S)
+
+    class TMDM_model(NsDiff_model_variants):
+        pass
+
+    assert U._samples_per_row(NsDiff_model_variants(100, 10)) == 100
+    assert U._samples_per_row(NsDiff_model_variants(25, 10)) == 20
+    with pytest.raises(RuntimeError, match="non-empty list"):
+        U._samples_per_row(NsDiff_model_variants(5, 10))
+    assert U._samples_per_row(TMDM_model(5, 10)) == 5
+    with pytest.raises(ValueError, match="divisible"):
+        U._samples_per_row(TMDM_model(25, 10))
+
+
+def test_fresh_stats_are_dropped_when_the_cache_or_the_scaler_changes():
+    """The device-computed statistics remembered by sample_sweep are only reused for exactly that, unmodified, cache and
+    (for raw-unit statistics) the scaler they were baked with."""
+    from types import SimpleNamespace
+    cache = torch.zeros(3, 2, 4, 5, 1)
+    model = SimpleNamespace(scaler_mean=torch.tensor([1.0]), scaler_std=torch.tensor([2.0]))
+    stats = {"scaled": {"mpv": torch.arange(3.0)}, "raw": {"mpv": torch.arange(3.0) * 4}}
+    U._FRESH_STATS.clear()
+    import weakref
+    U._FRESH_STATS[cache.untyped_storage().data_ptr()] = (weakref.ref(cache), cache._version, tuple(cache.shape),
+                                                          U._scaler_snapshot(model), stats)
+    elems = U._as_cache_list(cache)
+    assert U._fresh_stats_for(elems, elems[0].shape) is stats
+    assert U._fresh_stats_for(elems, elems[0].shape, model=model, need_scaler=True) is stats
+    model.scaler_std = torch.tensor([3.0])                       # scaler_fit between sweep and summary
+    assert U._fresh_stats_for(elems, elems[0].shape, model=model, need_scaler=True) is None
+    assert U._fresh_stats_for(elems, elems[0].shape) is stats
+    elems[1].mul_(2.0)                                           # in-place edit of one element: views share the version
+    assert U._fresh_stats_for(elems, elems[0].shape) is None
+    assert not U._FRESH_STATS

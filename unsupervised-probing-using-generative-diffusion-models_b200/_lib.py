@@ -151,6 +151,22 @@ def stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def on_device(fn):
+    """Decorator for model methods that launch kernels: run with the CUDA device of ``self``'s parameters current, so
+    that a model living on cuda:1 while cuda:0 is current launches on cuda:1 (the C ABI validates and launches on the
+    CURRENT device with the stream it is handed)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 def require_cuda(device):
     device = torch.device(device)
     if device.type != "cuda":

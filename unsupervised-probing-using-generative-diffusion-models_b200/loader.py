@@ -55,6 +55,18 @@ def _load_checkpoint(path):
             return torch.load(f, map_location=lambda storage, loc: storage, weights_only=False)
 
 
+def drop_unused_temporal_tables(model, state_dict):
+    """The reference builds TMDM's three embeddings as torch-timeseries ``DataEmbedding(c_in, d_model, 'fixed', 'h',
+    dropout)`` (TMDM.py:90, tmdm_ns_transformer.py:53-56), which in that lineage registers a ``temporal_embedding`` of
+    fixed sinusoidal lookup tables (``*.temporal_embedding.{hour,weekday,day,month}_embed.emb.weight``).  The hot path
+    never passes time marks (x_mark is None: tmdm_adapter.py:123-124), so those tables are never read; the modules here
+    do not hold them.  They are dropped from a checkpoint -- and only they -- so that the strict load still checks every
+    tensor the path uses.  (torch-timeseries is not vendored and no TMDM checkpoint ships: the key names are the
+    lineage's, unverified.)"""
+    own = set(model.state_dict().keys())
+    return {k: v for k, v in state_dict.items() if k in own or ".temporal_embedding." not in k}
+
+
 def load_diffusion_model(path, device, infer_para=None, dataparallel=True, **kwargs):
     """utils/utils.py:660-689: full-pickle load, ``infer_para`` merged before construction (so it can
     change n_z_samples / parallel_sample / diffusion_steps), ``module.`` prefixes stripped,
@@ -71,6 +83,6 @@ def load_diffusion_model(path, device, infer_para=None, dataparallel=True, **kwa
     loaded_net_param["device"] = device
     model = diffusion_models(task_model=loaded_net_param["task_model"], net_param=loaded_net_param,
                              train_model_select=kwargs["train_model_select"]).to(device)
-    model.load_state_dict(loaded_state_dict, strict=True)
+    model.load_state_dict(drop_unused_temporal_tables(model, loaded_state_dict), strict=True)
     model = model.to(device)
     return model, loaded_net_param

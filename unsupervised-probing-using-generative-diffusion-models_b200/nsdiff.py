@@ -11,7 +11,7 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
-from . import kernels, schedules
+from . import _lib, kernels, schedules
 
 EPS = 10e-8  # NsDiff_model.py:37
 FX_ROWS_PER_CALL = 4096
@@ -139,6 +139,7 @@ class _NsDiffBase(nn.Module):
         self._packed = None
         return super()._apply(fn, *a, **k)
 
+    @_lib.on_device
     def condition(self, batch_x):
         """f(x) and g(x) once per window row: -> (y_0_hat [R,O,F] or None, gx [R,O,F])."""
         dev = self.model.diffussion_model.lin1.lin.weight.device
@@ -158,6 +159,7 @@ class _NsDiffBase(nn.Module):
             gx = torch.ones(batch_x.shape[0], self.pred_len, self.dataset_nf, device=dev)
         return y0, gx
 
+    @_lib.on_device
     def sample_windows(self, windows, noise=None, seed=None, window_base=None):
         """Batched hot path: ``windows`` [W, B, L(+O), F] already scaled -> trajectories
         [W*B, K, O, F] on the device (K = (n_z_samples // parallel_sample) * parallel_sample).
@@ -166,7 +168,7 @@ class _NsDiffBase(nn.Module):
         S = int(self.configs.parallel_sample)
         K = (int(self.configs.n_z_samples) // S) * S
         if K <= 0:
-            raise ValueError("n_z_samples // parallel_sample is zero")
+            raise RuntimeError("torch.cat(): expected a non-empty list of Tensors (n_z_samples // parallel_sample == 0: the reference's chunk loop is empty, NsDiff_model.py:227-247)")
         x = windows.reshape(W * B, windows.shape[2], windows.shape[3])[:, :self.windows, :]
         with torch.no_grad():
             y0, gx = self.condition(x)

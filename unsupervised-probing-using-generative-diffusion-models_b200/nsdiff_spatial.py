@@ -307,7 +307,7 @@ class NsDiff_model_spatial(nn.Module):
         n_chunks = int(self.configs.n_z_samples) // S
         K = n_chunks * S
         if K <= 0:
-            raise ValueError("n_z_samples // parallel_sample is zero")
+            raise RuntimeError("torch.cat(): expected a non-empty list of Tensors (n_z_samples // parallel_sample == 0: the reference's chunk loop is empty, NsDiff_model.py:227-247)")
         O, nf, T = self.pred_len, self.dataset_nf, self.diffusion_steps
         if seed is None:
             seed = torch.initial_seed()

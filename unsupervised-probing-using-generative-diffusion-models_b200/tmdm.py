@@ -6,7 +6,7 @@ from types import SimpleNamespace
 import torch
 import torch.nn as nn
 
-from . import kernels, schedules
+from . import _lib, kernels, schedules
 from .fx_encoder import DataEmbedding, NsTransformer
 from .nsdiff import ConditionalLinearParams
 
@@ -105,6 +105,7 @@ class TMDM_model(nn.Module):
             self._packed_key = key
         return self._packed
 
+    @_lib.on_device
     def condition(self, batch_x):
         """Condition mean over label_len + pred_len positions (tmdm_adapter.py:123-124)."""
         dev = self.model.diffussion_model.lin1.lin.weight.device
@@ -114,6 +115,7 @@ class TMDM_model(nn.Module):
         _, y0, _, _ = self.cond_pred_model(batch_x, None, dec_inp, None)
         return y0.contiguous()
 
+    @_lib.on_device
     def sample_windows(self, windows, noise=None, seed=None, window_base=None, y_0_hat=None):
         """windows [W,B,L(+O),F] scaled -> trajectories [W*B, K, pred_len, F] on the device."""
         W, B = windows.shape[0], windows.shape[1]

@@ -536,15 +536,22 @@ def _fresh_stats_for(pred_future_list, elem_shape, model=None, need_scaler=False
 
 
 def _samples_per_row(model):
+    """Samples a model's evaluation_step returns per row, with the reference's own failure modes: the NsDiff classes loop
+    ``range(n_z_samples // parallel_sample)`` (NsDiff_model.py:227 / :461 / :742: the remainder is dropped, and an empty
+    loop fails in torch.cat); TMDM and DiffusionTS clamp parallel_sample to n_z_samples and insist on divisibility
+    (tmdm_adapter.py:125-127, DiffusionTS_model.py:83-85)."""
     cfg = model.configs
     S = int(getattr(cfg, "parallel_sample", 1))
     K = int(getattr(cfg, "n_z_samples", 1))
-    if S <= 0 or K // S == 0:
-        # the reference's chunk loop `for _ in range(n_z_samples // parallel_sample)` is then empty and its
-        # torch.cat(outs, dim=1) raises (NsDiff_model.py:227-247, tmdm_adapter.py:132-151): same failure here, no clamp
-        raise RuntimeError("torch.cat(): expected a non-empty list of Tensors (n_z_samples={} // parallel_sample={} "
-                           "chunks)".format(K, S))
-    return (K // S) * S
+    if type(model).__name__.startswith("NsDiff"):
+        if S <= 0 or K // S == 0:
+            raise RuntimeError("torch.cat(): expected a non-empty list of Tensors (n_z_samples={} // parallel_sample={} "
+                               "chunks)".format(K, S))
+        return (K // S) * S
+    S = min(S, K)
+    if S <= 0 or K % S != 0:
+        raise ValueError("n_z_samples must be divisible by parallel_sample")
+    return K
 
 
 def _as_cache_list(cache, squeeze_rows=False):
