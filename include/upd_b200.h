@@ -297,6 +297,17 @@ int upd_stg_tcn_ln_cat(const float* x_dev, int CI1, const float* x2_dev, int CI2
  * against [W_hi | W_hi | W_lo | b_hi b_lo 0..] ; the two calls below produce A3 fused with what precedes the GEMM.
  * ------------------------------------------------------------------------------------------ */
 
+/* upd_gemm3 -- the dense layer itself: out[M, n_out] (fp32) = A3[M, Kp] x W3[Nw, Kp]^T (+ addend[M, n_out] if not NULL),
+ *   both operands fp16 row-major with Kp = 3K+8 as above (W3 rows padded to a multiple of 8, n_out <= Nw).  Replaces every
+ *   nn.Linear / Conv1d(k=1) of the condition encoders (mu_backbone.py:150-183 via torch-timeseries' AttentionLayer /
+ *   EncoderLayer / DecoderLayer, tmdm_ns_transformer.py:150-174), of the DiffusionTS transformer's forward
+ *   (DiffusionTS/diffusionts_transformer.py:123-438) and the (1,T+1) / K|Q|V|skip contractions of the graph blocks
+ *   (DiffSTG/ugnet.py:117-131, models/layer/gnn_conv.py:18-19).  Warp-specialised persistent tcgen05 kernel: TMA
+ *   (SWIZZLE_128B tensor maps, out-of-bounds rows / K columns zero-filled), accumulators in TMEM, fp32 epilogue.
+ *   Limits: Kp a multiple of 8, operands / output / addend 16-byte aligned; UPD_ERR_UNSUPPORTED otherwise. */
+int upd_gemm3(const void* a3_dev, const void* w3_dev, long long M, int Nw, int n_out, int Kp, float* out_dev,
+              const float* addend_dev, void* stream);
+
 /* upd_fx_split -- A3(act(x)).  act: 0 none, 1 ReLU, 2 GELU (erf) = the feed-forward activation between conv1 and conv2
  *   (EncoderLayer/DecoderLayer of torch-timeseries as called at mu_backbone.py:70-104).  H > 1: x_dev is an attention
  *   output [B, H, L, K/H] and the row (b,l) gathers its heads (the `out.transpose(1,2).reshape(B, L, -1)` of

@@ -480,3 +480,27 @@ def test_fx_attention_head_size_16_against_fp64(Lq, S, causal, use_delta):
         sc = sc.masked_fill(torch.ones(Lq, S, dtype=torch.bool, device=dev).triu(1), float("-inf"))
     ref = (torch.softmax(sc, -1) @ v).transpose(1, 2).reshape(B * Lq, d)
     assert float((o.double() - ref).abs().max() / ref.abs().max()) < 2e-5
+
+
+@pytest.mark.parametrize("M,n_out,K,with_add", [(1000, 512, 512, False), (129, 1, 512, False), (4096, 1536, 512, False),
+                                                 (777, 64, 64, True), (2500, 320, 80, True), (128, 256, 256, False),
+                                                 (300, 207, 200, False), (65, 40, 16, True)])
+def test_gemm3_tcgen05_against_fp64(M, n_out, K, with_add):
+    """upd_gemm3 (warp-specialised tcgen05 GEMM, TMA operands, TMEM accumulators) == A3 W3^T (+ addend) in float64 on
+    the same fp16 operands, for every tile width (64 / 128 / 256), ragged M / N / K tails and the addend path; and the
+    error-compensated operand reproduces x W^T + b to fp32 accuracy."""
+    from updgm_b200 import fx_encoder
+    dev = _dev()
+    torch.manual_seed(M + n_out)
+    x = torch.randn(M, K, device=dev)
+    lin = torch.nn.Linear(K, n_out).to(dev)
+    cache = fx_encoder._W3Cache()
+    w3 = cache.get([(lin.weight, lin.bias)])
+    a3 = fx_encoder.a3_split(x)
+    add = torch.randn(M, n_out, device=dev) if with_add else None
+    y = fx_encoder.gemm3(a3, w3, n_out, addend=add)
+    ref = a3.double() @ w3.double().t()[:, :n_out] + (0 if add is None else add.double())
+    assert torch.isfinite(y).all()
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5      # fp32 accumulation over 3K+8 terms
+    full = x.double() @ lin.weight.double().t() + lin.bias.double() + (0 if add is None else add.double())
+    assert float((y.double() - full).abs().max() / full.abs().max()) < 1e-5

@@ -13,7 +13,7 @@ SYMBOLS = (
     "upd_error_string", "upd_last_cuda_error", "upd_abi_version", "upd_denoiser_pack_bytes", "upd_denoiser_pack",
     "upd_nsdiff_sample", "upd_tmdm_sample", "upd_mpv_scratch_bytes", "upd_mpv_reduce", "upd_sigma_estimation",
     "upd_selftest_umma", "upd_dts_ddim_step", "upd_dts_adagrad_step", "upd_dts_infill", "upd_gauss_fill",
-    "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_dts_attention", "upd_dts_attention_bwd", "upd_dts_layernorm", "upd_dts_layernorm_bwd", "upd_stg_posterior", "upd_nsx_step", "upd_stg_gated_aggregate", "upd_stg_tcn_ln", "upd_stg_tcn_ln_cat", "upd_fx_split", "upd_fx_add_ln_split", "upd_fx_attention", "upd_fx_attention_hs16", "upd_fx_embed_split",
+    "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_dts_attention", "upd_dts_attention_bwd", "upd_dts_layernorm", "upd_dts_layernorm_bwd", "upd_stg_posterior", "upd_nsx_step", "upd_stg_gated_aggregate", "upd_stg_tcn_ln", "upd_stg_tcn_ln_cat", "upd_fx_split", "upd_gemm3", "upd_fx_add_ln_split", "upd_fx_attention", "upd_fx_attention_hs16", "upd_fx_embed_split",
 )
 
 ABI_VERSION = 6     # = UPD_ABI_VERSION of the csrc/ this binding was written against (argument lists below)
@@ -95,6 +95,8 @@ def lib():
     L.upd_stg_posterior.argtypes = [vp, vp, vp, ll, f32, f32, f32, vp, vp]
     L.upd_stg_gated_aggregate.restype = ctypes.c_int
     L.upd_stg_gated_aggregate.argtypes = [vp, vp, vp, vp, ll, i, i, i, vp, vp]
+    L.upd_gemm3.restype = ctypes.c_int
+    L.upd_gemm3.argtypes = [vp, vp, ll, i, i, i, vp, vp, vp]
     L.upd_fx_split.restype = ctypes.c_int
     L.upd_fx_split.argtypes = [vp, ll, i, i, i, i, vp, vp]
     L.upd_fx_add_ln_split.restype = ctypes.c_int

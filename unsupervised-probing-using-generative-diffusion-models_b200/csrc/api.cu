@@ -64,6 +64,9 @@ cudaError_t upd_launch_dts_layernorm(const float* x, const float* gamma, const f
 cudaError_t upd_launch_dts_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* stats,
                                          long long rows, int D, float* dx, cudaStream_t stream);
 
+cudaError_t upd_launch_gemm3(const void* a3, const void* w3, long long M, int Nw, int n_out, int Kp, float* out,
+                             const float* addend, int sms, cudaStream_t stream);
+
 namespace {
 
 thread_local int g_last_cuda_error = 0;
@@ -432,6 +435,17 @@ int upd_stg_tcn_ln_cat(const float* x_dev, int CI1, const float* x2_dev, int CI2
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_tcn_ln(x_dev, w1_dev, b1_dev, w2_dev, b2_dev, gamma_dev, beta_dev, N, CI1 + CI2, C, T, hn_dev,
                                    a3_dev, wsc_dev, sc_dev, x2_dev, CI2, (cudaStream_t)stream));
+}
+
+int upd_gemm3(const void* a3_dev, const void* w3_dev, long long M, int Nw, int n_out, int Kp, float* out_dev,
+              const float* addend_dev, void* stream) {
+  if (!a3_dev || !w3_dev || !out_dev || M <= 0 || Nw <= 0 || n_out <= 0 || n_out > Nw || Kp <= 0) return UPD_ERR_BAD_ARG;
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc != UPD_OK) return rc;
+  cudaError_t e = upd_launch_gemm3(a3_dev, w3_dev, M, Nw, n_out, Kp, out_dev, addend_dev, sms, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
 }
 
 int upd_fx_split(const float* x_dev, long long rows, int K, int H, int L, int act, void* a3_dev, void* stream) {

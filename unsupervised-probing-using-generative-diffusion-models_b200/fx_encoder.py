@@ -135,10 +135,18 @@ def add_ln_split(x2d, res2d, ln1, ln2=None, want_y=True, want_a3=True):
     return y, a3
 
 
-def gemm3(a3, w3, n_out):
-    """One fp16 tensor-core GEMM, fp32 accumulate and output: [rows, 3K+8] x [N, 3K+8]^T -> [rows, n_out]."""
-    y = torch.mm(a3, w3.t(), out_dtype=torch.float32)
-    return y if y.shape[1] == n_out else y[:, :n_out]
+def gemm3(a3, w3, n_out, addend=None):
+    """One fp16 tensor-core GEMM, fp32 accumulate and output: [rows, 3K+8] x [N, 3K+8]^T (+ addend) -> [rows, n_out]
+    (upd_gemm3: the warp-specialised tcgen05 kernel of csrc/gemm3.cu)."""
+    rows, kp = a3.shape
+    y = torch.empty((rows, n_out), dtype=torch.float32, device=a3.device)
+    if rows == 0:
+        return y
+    with torch.cuda.device(a3.device):
+        rc = _lib.lib().upd_gemm3(_lib.ptr(a3), _lib.ptr(w3), rows, w3.shape[0], n_out, kp, _lib.ptr(y),
+                                  None if addend is None else _lib.ptr(addend), _lib.stream_ptr(a3.device))
+    _lib.check(rc, "upd_gemm3")
+    return y
 
 
 class SLinear(nn.Linear):
