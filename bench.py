@@ -189,7 +189,7 @@ def run_reference_arm(args, rank, world):
     rate, sec = cpu_reference_rate(cfg, rows=rows, n_steps=args.steps, n_warm=args.warmup, threads=threads)
     sample = "{} of 100 rows of one window per step (K=100, T=20), f(x)+g(x)+sampler+MPV".format(rows)
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(cfg, 181, 100, {"reference_arm": "CPU oracle port of the reference path (torch CPU ops, "
                                                  "reference is Python and absent on the GPU box)"}),

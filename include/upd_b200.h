@@ -151,6 +151,19 @@ int upd_mpv_reduce(const float* traj_dev, const float* scale_dev, int n_win, int
                    float* var_dev, float* mean_dev, float* mpv_dev, float* pmean_dev, float* mpv_f_dev,
                    void* scratch_dev, void* stream);
 
+/* upd_gram_centered -- the contraction of `_slbp_intrinsic_dimension` (diffusion_model_uncertainy.py:686-698), batched over
+ *   windows: traj_dev [n_win, K, D = O*F] (one SLBP cache element per window, as the samplers write it) ->
+ *   gram_dev [n_win, K, K] (double) = C C^T / (K - 1), C = the K trajectories minus their mean.  It has the non-zero
+ *   spectrum of the (O*F)^2 sample covariance the reference diagonalises; the caller counts eigenvalues up to 80 %.
+ *   Limits: 2 <= K <= 128. */
+int upd_gram_centered(const float* traj_dev, int n_win, int K, int D, double* gram_dev, void* stream);
+
+/* upd_prediction_error -- `summarize_slbp_sensitivity`'s error term (diffusion_model_uncertainy.py:542-549), batched over
+ *   windows: err_dev [n_win, F] = mean over the O positions of | mean_dev - target_dev |, both [n_win, O, F] (mean_dev =
+ *   the per-position predictive means of upd_mpv_reduce, target_dev = the scaled future of each window).  F in 1..4. */
+int upd_prediction_error(const float* mean_dev, const float* target_dev, int n_win, int O, int F, float* err_dev,
+                         void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * upd_sigma_estimation -- replaces SigmaEstimation.forward, i.e. cond_pred_model_g, the whole
  *   "gx" uncertainty path (models/Diffusion_model/NsDiff/g_backbone.py:49-72, sigma.py:34-71).

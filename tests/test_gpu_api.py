@@ -292,3 +292,29 @@ def test_distributed_sweep_single_rank_group_equals_plain_sweep(model8):
     assert torch.equal(cache, ref)
     assert torch.equal(stats["mpv"], ref_stats["mpv"]) and torch.equal(stats["pred_mean"], ref_stats["pred_mean"])
     assert tuple(stats["mpv_f"].shape) == (5, 2)
+
+
+@pytest.mark.parametrize("K", [100, 7])
+def test_slbp_extras_batched_on_device_against_oracle(K):
+    """the intrinsic dimension of every window from ONE batched centred-Gram launch + one batched
+    eigenvalue solve (integer, exact against the oracle's (O*F)^2 covariance form, diffusion_model_uncertainy.py:686-698),
+    and the prediction error of every window from one launch on the Welford means (:542-549)."""
+    U = _U()
+    torch.manual_seed(40 + K)
+    W, O, F = 9, 200, 2
+    # K trajectories with a window-dependent number of dominant directions + noise
+    cache = torch.empty(W, 1, K, O, F)
+    for w in range(W):
+        r = 1 + w % 5
+        basis = torch.randn(r, O * F)
+        cache[w, 0] = (torch.randn(K, r) * torch.linspace(3.0, 1.0, r) @ basis + 0.3 * torch.randn(K, O * F)).view(K, O, F)
+    elems = [cache[w, 0].permute(1, 2, 0) for w in range(W)]                      # [O, F, K], as in an SLBP cache
+    targets = [torch.randn(O, F) for _ in range(W)]
+    mpv, dims = U.summarize_slbp_sampling_for_fig6(elems, pred_dim=1)
+    assert dims == [mpv_oracle.intrinsic_dimension(e.numpy()) for e in elems]
+    assert len(set(dims)) > 1
+    mpv2, err = U.summarize_slbp_sensitivity(elems, targets, model=None, pred_dim=1)
+    for w in range(W):
+        assert float(err[w]) == pytest.approx(mpv_oracle.slbp_prediction_error(elems[w].numpy(), targets[w].numpy(), 1), rel=2e-6)
+        assert float(mpv2[w]) == pytest.approx(mpv_oracle.slbp_mpv(elems[w].numpy(), 1), rel=2e-5)
+        assert float(mpv[w]) == pytest.approx(float(mpv2[w]), rel=1e-6)

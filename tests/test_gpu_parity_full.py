@@ -59,7 +59,7 @@ def test_config2_full_window_sampler_and_model_against_oracle():
     m.scaler_std.fill_(1.0)
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     x = _bench_series()[:, 400:500, :].contiguous()                                # window 80 of the bench sweep
-    r = parity.nsdiff_window_reference(sd, dict(cfg["net"]), x, seed=11, with_fx=True)
+    r = parity.nsdiff_window_reference(sd, dict(cfg["net"]), x, seed=11, with_fx=True, threads=os.cpu_count())
     B, O, F, K = r["ref"].shape
     assert (B, O, F, K) == (100, 100, 1, 100)
     # (1) the sampler alone at full size, same f(x) / g(x) as the oracle, the implementation the host selects
@@ -87,7 +87,7 @@ def test_config1_full_windows_shipped_checkpoint_against_oracle():
     net = {k: v for k, v in net_param.items() if k != "device"}
     for w, start in enumerate((0, 250, 500, 800)):
         x = s[start:start + 200].unsqueeze(0).contiguous()                          # [1, 200, 2], scaled units
-        r = parity.nsdiff_window_reference(sd, net, x, seed=20 + w, with_fx=False, variant_adds_eps=True)
+        r = parity.nsdiff_window_reference(sd, net, x, seed=20 + w, with_fx=False, variant_adds_eps=True, threads=os.cpu_count())
         assert tuple(r["ref"].shape) == (1, 200, 2, 100)
         outs, _ = m.evaluation_step(x.to(dev), noise=r["noise"][0])
         _assert_parity("config 1, window {} (impl {})".format(w, m.sampler_impl), outs, r["ref"])
@@ -105,7 +105,7 @@ def test_config3_full_window_tmdm_against_oracle():
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
     g = torch.Generator().manual_seed(4)
     x = torch.sigmoid((torch.randn(100, 100, 1, generator=g) * 0.2).cumsum(dim=1))
-    r = parity.tmdm_window_reference(sd, dict(m.configs.__dict__, device="cpu"), x, seed=31)
+    r = parity.tmdm_window_reference(sd, dict(m.configs.__dict__, device="cpu"), x, seed=31, threads=os.cpu_count())
     assert tuple(r["ref"].shape) == (100, 100, 1, 100)
     traj = m.sample_windows(x.unsqueeze(0).to(dev), noise=r["noise"], y_0_hat=r["y0"])
     _assert_parity("config 3, sampler (impl {})".format(m.sampler_impl), traj.permute(0, 2, 3, 1), r["ref"])

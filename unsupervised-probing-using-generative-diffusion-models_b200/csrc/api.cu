@@ -64,6 +64,9 @@ cudaError_t upd_launch_dts_layernorm(const float* x, const float* gamma, const f
 cudaError_t upd_launch_dts_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* stats,
                                          long long rows, int D, float* dx, cudaStream_t stream);
 
+cudaError_t upd_launch_gram_centered(const float* traj, int W, int K, int D, double* gram, cudaStream_t stream);
+cudaError_t upd_launch_prediction_error(const float* mean, const float* target, int W, int O, int F, float* err,
+                                        cudaStream_t stream);
 cudaError_t upd_launch_gemm3(const void* a3, const void* w3, long long M, int Nw, int n_out, int Kp, float* out,
                              const float* addend, int sms, cudaStream_t stream);
 
@@ -435,6 +438,27 @@ int upd_stg_tcn_ln_cat(const float* x_dev, int CI1, const float* x2_dev, int CI2
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_tcn_ln(x_dev, w1_dev, b1_dev, w2_dev, b2_dev, gamma_dev, beta_dev, N, CI1 + CI2, C, T, hn_dev,
                                    a3_dev, wsc_dev, sc_dev, x2_dev, CI2, (cudaStream_t)stream));
+}
+
+int upd_gram_centered(const float* traj_dev, int n_win, int K, int D, double* gram_dev, void* stream) {
+  if (!traj_dev || !gram_dev || n_win <= 0 || K <= 1 || D <= 0) return UPD_ERR_BAD_ARG;
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc != UPD_OK) return rc;
+  cudaError_t e = upd_launch_gram_centered(traj_dev, n_win, K, D, gram_dev, (cudaStream_t)stream);
+  if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
+  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
+}
+
+int upd_prediction_error(const float* mean_dev, const float* target_dev, int n_win, int O, int F, float* err_dev,
+                         void* stream) {
+  if (!mean_dev || !target_dev || !err_dev || n_win <= 0 || O <= 0) return UPD_ERR_BAD_ARG;
+  if (F < 1 || F > UPD_MAX_F) return UPD_ERR_UNSUPPORTED;
+  int sms = 0;
+  int rc = device_info(&sms);
+  if (rc != UPD_OK) return rc;
+  cudaError_t e = upd_launch_prediction_error(mean_dev, target_dev, n_win, O, F, err_dev, (cudaStream_t)stream);
+  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
 }
 
 int upd_gemm3(const void* a3_dev, const void* w3_dev, long long M, int Nw, int n_out, int Kp, float* out_dev,

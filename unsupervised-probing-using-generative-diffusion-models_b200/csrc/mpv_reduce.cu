@@ -129,6 +129,86 @@ window_means(const float* __restrict__ var_in, const float* __restrict__ mean_in
   }
 }
 
+
+// ---- SLBP extras ------------------------------------------------------------------------------------
+// Centred Gram matrix of a window's K trajectories, G = C C^T / (K - 1) with C = X - mean_K(X), X [K, D = O*F]: the K x K
+// matrix with the same non-zero spectrum as the (O*F)^2 sample covariance `_slbp_intrinsic_dimension` diagonalises
+// (diffusion_model_uncertainy.py:686-698).  One CTA per window; X is walked in chunks of DC columns staged (centred, in
+// double) in shared memory; every thread owns a fixed set of (i <= j) pairs and accumulates them in double.  The per-chunk
+// column means make the result independent of how D is cut.  Algorithmic traffic: 4 K D bytes read, 8 K^2 written.
+constexpr int GRAM_DC = 32, GRAM_MAXK = 128, GRAM_THREADS = 256, GRAM_PAIRS_PER_THREAD = (GRAM_MAXK * (GRAM_MAXK + 1) / 2 + GRAM_THREADS - 1) / GRAM_THREADS;
+
+__global__ void __launch_bounds__(GRAM_THREADS)
+gram_centered_kernel(const float* __restrict__ traj, int K, int D, double* __restrict__ gram) {
+  __shared__ double c[GRAM_MAXK][GRAM_DC + 1];
+  const float* x = traj + (long long)blockIdx.x * K * D;
+  double* g = gram + (long long)blockIdx.x * K * K;
+  const int n_pairs = K * (K + 1) / 2;
+  double acc[GRAM_PAIRS_PER_THREAD];
+#pragma unroll
+  for (int p = 0; p < GRAM_PAIRS_PER_THREAD; ++p) acc[p] = 0.0;
+  for (int d0 = 0; d0 < D; d0 += GRAM_DC) {
+    const int dc = min(GRAM_DC, D - d0);
+    for (int e = threadIdx.x; e < K * GRAM_DC; e += GRAM_THREADS) {
+      const int k = e / GRAM_DC, d = e - k * GRAM_DC;
+      c[k][d] = d < dc ? (double)x[(long long)k * D + d0 + d] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x < GRAM_DC) {                         // centre the chunk: mean over the K samples, per column
+      double m = 0.0;
+      for (int k = 0; k < K; ++k) m += c[k][threadIdx.x];
+      m /= K;
+      for (int k = 0; k < K; ++k) c[k][threadIdx.x] -= m;
+    }
+    __syncthreads();
+    int p = 0;
+    for (int q = threadIdx.x; q < n_pairs; q += GRAM_THREADS, ++p) {
+      // q -> (i, j), i <= j, row-major over the upper triangle
+      int i = (int)((2.0 * K + 1.0 - sqrt((2.0 * K + 1.0) * (2.0 * K + 1.0) - 8.0 * q)) * 0.5);
+      while (i * (2 * K - i + 1) / 2 > q) --i;
+      while ((i + 1) * (2 * K - i) / 2 <= q) ++i;
+      const int j = i + (q - i * (2 * K - i + 1) / 2);
+      double s = 0.0;
+#pragma unroll 8
+      for (int d = 0; d < GRAM_DC; ++d) s += c[i][d] * c[j][d];
+      acc[p] += s;
+    }
+    __syncthreads();
+  }
+  const double inv = 1.0 / (double)max(K - 1, 1);
+  int p = 0;
+  for (int q = threadIdx.x; q < n_pairs; q += GRAM_THREADS, ++p) {
+    int i = (int)((2.0 * K + 1.0 - sqrt((2.0 * K + 1.0) * (2.0 * K + 1.0) - 8.0 * q)) * 0.5);
+    while (i * (2 * K - i + 1) / 2 > q) --i;
+    while ((i + 1) * (2 * K - i) / 2 <= q) ++i;
+    const int j = i + (q - i * (2 * K - i + 1) / 2);
+    g[(long long)i * K + j] = acc[p] * inv;
+    g[(long long)j * K + i] = acc[p] * inv;
+  }
+}
+
+// Prediction error of a window (diffusion_model_uncertainy.py:542-549): | mean_K - target | averaged over the pred_len
+// positions, per feature.  mean [W, O, F] are the Welford means of upd_mpv_reduce, target [W, O, F] the (scaled) futures.
+__global__ void __launch_bounds__(128)
+prediction_error_kernel(const float* __restrict__ mean, const float* __restrict__ target, int O, int F,
+                        float* __restrict__ err) {
+  __shared__ double part[4][UPD_MAX_F];
+  const long long base = (long long)blockIdx.x * O * F;
+  double a[UPD_MAX_F];
+#pragma unroll
+  for (int f = 0; f < UPD_MAX_F; ++f) a[f] = 0.0;
+  for (int o = threadIdx.x; o < O; o += blockDim.x)
+    for (int f = 0; f < F; ++f) a[f] += fabs((double)mean[base + (long long)o * F + f] - (double)target[base + (long long)o * F + f]);
+#pragma unroll
+  for (int f = 0; f < UPD_MAX_F; ++f)
+    for (int off = 16; off; off >>= 1) a[f] += __shfl_xor_sync(0xffffffffu, a[f], off);
+  if ((threadIdx.x & 31) == 0)
+    for (int f = 0; f < UPD_MAX_F; ++f) part[threadIdx.x >> 5][f] = a[f];
+  __syncthreads();
+  if (threadIdx.x < F) err[(long long)blockIdx.x * F + threadIdx.x] =
+      (float)((part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]) / O);
+}
+
 }  // namespace
 
 cudaError_t upd_launch_mpv(const float* traj, const float* scale, int n_win, int B, int K, int O, int F,
@@ -151,5 +231,17 @@ cudaError_t upd_launch_mpv(const float* traj, const float* scale, int n_win, int
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   window_means<<<n_win, 128, 0, stream>>>(var_out, mean_out, B, E, F, mpv, pmean, mpv_f);
+  return cudaGetLastError();
+}
+
+cudaError_t upd_launch_gram_centered(const float* traj, int W, int K, int D, double* gram, cudaStream_t stream) {
+  if (K > GRAM_MAXK) return cudaErrorInvalidValue;
+  gram_centered_kernel<<<W, GRAM_THREADS, 0, stream>>>(traj, K, D, gram);
+  return cudaGetLastError();
+}
+
+cudaError_t upd_launch_prediction_error(const float* mean, const float* target, int W, int O, int F, float* err,
+                                        cudaStream_t stream) {
+  prediction_error_kernel<<<W, 128, 0, stream>>>(mean, target, O, F, err);
   return cudaGetLastError();
 }

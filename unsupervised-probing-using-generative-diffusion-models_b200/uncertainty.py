@@ -10,17 +10,17 @@ Line references in docstrings are to the reference file above unless another fil
 """
 import atexit
 import concurrent.futures
+import ctypes
 import os
 import threading
+import weakref
 from pathlib import Path
 
 import numpy as np
-import weakref
-
 import torch
 import yaml
 
-from . import kernels
+from . import _lib, kernels
 
 NETWORK_DYNAMICS = {"SIS", "neuronal", "biomass"}
 DEFAULT_SAMPLE_WINDOW_STEP = {"SIS": 50, "neuronal": 5, "biomass": 5, "SLBP": 10}
@@ -841,14 +841,21 @@ def summarize_slbp_sensitivity(pred_future_list, pred_datas, model=None, device=
         return [], []
     r = _stats_scaled(elems, want_mean=True)
     mpv_list = _np_scalars(r["mpv_f"][:, pred_dim])
-    err_list = []
-    for mean, target in zip(r["mean"], pred_datas):
-        target = torch.as_tensor(target).detach().float().cpu()
+    # prediction error: all windows in one launch on the Welford means (upd_prediction_error), no per-window upload
+    n = min(len(elems), len(pred_datas))
+    if n == 0:
+        return mpv_list, []
+    dev = torch.device("cuda", torch.cuda.current_device()) if model is None else _model_device(model)
+    with torch.cuda.device(dev):
+        target = torch.stack([torch.as_tensor(t).detach().float() for t in pred_datas[:n]]).to(dev)          # [n, O, F]
         if getattr(model, "scaler", None) is not None and hasattr(model, "scaler_transform"):
-            target = model.scaler_transform(target.to(_model_device(model))).to("cpu")
-        err = torch.abs(mean.squeeze(0) - target).mean(dim=0)
-        err_list.append(err[pred_dim].cpu().detach().numpy())
-    return mpv_list, err_list
+            target = model.scaler_transform(target)
+        mean = torch.stack([m.reshape(target.shape[1:]) for m in r["mean"][:n]]).to(dev)
+        err = torch.empty((n, target.shape[2]), dtype=torch.float32, device=dev)
+        rc = _lib.lib().upd_prediction_error(_lib.ptr(mean.contiguous()), _lib.ptr(target.contiguous()), n, target.shape[1],
+                                             target.shape[2], _lib.ptr(err), _lib.stream_ptr(dev))
+        _lib.check(rc, "upd_prediction_error")
+    return mpv_list, _np_scalars(err[:, pred_dim].cpu())
 
 
 def _slbp_intrinsic_dimension(trajectories):
@@ -868,6 +875,29 @@ def _slbp_intrinsic_dimension(trajectories):
     return int(torch.where(cum >= 0.8)[0][0].item() + 1)
 
 
+def _slbp_intrinsic_dimensions(elems, energy=0.8):
+    """:686-698 for a whole sweep: every window's centred K x K Gram matrix in one launch (upd_gram_centered, double),
+    one batched symmetric eigenvalue solve, and the count of leading eigenvalues reaching ``energy`` of the trace.
+    elems: list of [1, O, F, K] cache elements.  -> list of int (nan where the reference returns nan)."""
+    W = len(elems)
+    O, F, K = elems[0].shape[1:]
+    if K < 2:
+        return [np.nan] * W
+    dev = torch.device("cuda", torch.cuda.current_device())
+    # [W, K, O*F]: a fresh sweep's elements are permuted views of one contiguous [W,1,K,O,F] cache, so this is a reshape
+    traj = torch.stack([e[0].permute(2, 0, 1) for e in elems]).reshape(W, K, O * F).to(dev, torch.float32).contiguous()
+    gram = torch.empty((W, K, K), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        rc = _lib.lib().upd_gram_centered(_lib.ptr(traj), W, K, O * F, ctypes.c_void_p(gram.data_ptr()), _lib.stream_ptr(dev))
+        _lib.check(rc, "upd_gram_centered")
+        ev = torch.linalg.eigvalsh(gram).flip(-1).clamp_min(0)                  # descending
+        total = ev.sum(dim=-1, keepdim=True)
+        cum = torch.cumsum(ev / total.clamp_min(1e-300), dim=-1)
+        count = (cum < energy).sum(dim=-1) + 1
+    count, total = count.cpu().tolist(), total.squeeze(-1).cpu().tolist()
+    return [int(c) if t > 0 else np.nan for c, t in zip(count, total)]
+
+
 def summarize_slbp_sampling_for_fig6(pred_future_list, pred_dim=0):
     """:701-714 -> (mpv list of float, intrinsic-dimension list of int)."""
     elems = []
@@ -882,7 +912,10 @@ def summarize_slbp_sampling_for_fig6(pred_future_list, pred_dim=0):
         return [], []
     r = _stats_scaled(elems)
     mpv = [float(v) for v in r["mpv_f"][:, pred_dim].tolist()]
-    dims = [_slbp_intrinsic_dimension(pf.squeeze(0).permute(2, 0, 1).reshape(pf.shape[-1], -1)) for pf in elems]
+    if elems[0].shape[-1] <= 128:
+        dims = _slbp_intrinsic_dimensions(elems)
+    else:                                   # more samples than the Gram kernel is built for: one window at a time
+        dims = [_slbp_intrinsic_dimension(pf.squeeze(0).permute(2, 0, 1).reshape(pf.shape[-1], -1)) for pf in elems]
     return mpv, dims
 
 
