@@ -358,12 +358,6 @@ int upd_fx_attention(const float* q_dev, long long q_row_stride, const float* k_
                      long long kv_row_stride, const float* tau_dev, const float* delta_dev, int delta_pitch, int B, int H,
                      int Lq, int S, int head_dim, int causal, float scale, void* a3_dev, void* stream);
 
-/* Known-answer self test of the tcgen05 descriptors this library relies on: D[128,N] = A[128,K] * B[N,K]^T
- * with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K=128; mode 1: tf32 hi/lo
- * 3-pass, K=8*k8); flags bit 0 swaps the descriptor's LBO/SBO (negative control: must give a wrong D).  a_dev [128,K], b_dev [N=128,K], d_dev [128,128] fp32. */
-int upd_selftest_umma(const float* a_dev, const float* b_dev, float* d_dev, int K, int mode, int flags,
-                      void* stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,22 @@ IMPLS = [pytest.param(1, id="simt"), pytest.param(0, id="tcgen05"), pytest.param
 
 
 # ---------------------------------------------------------------- tcgen05 descriptor known-answer
+def _selftest_umma(a, b, mode=0, flags=0):
+    """D = A @ B^T through the tcgen05 path of the sampler (A via TMEM, B via shared memory): the tests-only library
+    libupd_selftest.so (csrc/selftest_umma.cu, built by _build.build_selftest(); not part of the product ABI)."""
+    import ctypes
+    from updgm_b200 import _build
+    L = ctypes.CDLL(_build.build_selftest())
+    L.upd_selftest_umma.restype = ctypes.c_int
+    L.upd_selftest_umma.argtypes = [ctypes.c_void_p] * 3 + [ctypes.c_int] * 3 + [ctypes.c_void_p]
+    d = torch.zeros((128, 128), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        rc = L.upd_selftest_umma(a.data_ptr(), b.data_ptr(), d.data_ptr(), a.shape[1], mode, flags,
+                                 torch.cuda.current_stream(a.device).cuda_stream)
+    assert rc == 0, rc
+    return d
+
+
 @pytest.mark.parametrize("mode,K", [(0, 128), (1, 8), (1, 16)])
 def test_umma_selftest(mode, K):
     kernels, _ = _k()
@@ -57,7 +73,7 @@ def test_umma_selftest(mode, K):
     a += torch.arange(128).float().view(-1, 1) * 0.01
     b += torch.arange(K).float().view(1, -1) * 0.02
     ref = a.double() @ b.double().t()
-    d = kernels.selftest_umma(a.to(_dev()), b.to(_dev()), mode=mode, flags=0).cpu().double()
+    d = _selftest_umma(a.to(_dev()), b.to(_dev()), mode=mode, flags=0).cpu().double()
     scale = (a.double().abs() @ b.double().abs().t())
     err = ((d - ref).abs() / scale).max().item()
     assert err < 4e-6, "tcgen05 3-pass contraction off: {:.3e}".format(err)
@@ -504,3 +520,29 @@ def test_gemm3_tcgen05_against_fp64(M, n_out, K, with_add):
     assert float((y.double() - ref).abs().max() / ref.abs().max()) < 1e-5      # fp32 accumulation over 3K+8 terms
     full = x.double() @ lin.weight.double().t() + lin.bias.double() + (0 if add is None else add.double())
     assert float((y.double() - full).abs().max() / full.abs().max()) < 1e-5
+
+
+def test_long_step_counts_run_on_the_ffma_kernel_instead_of_failing():
+    """include/upd_b200.h: the tcgen05 samplers keep three [T,128] step-embedding tables next to the 173 KB weight image
+    in shared memory, which fits T <= ~40 (every shipped YAML has T = 20).  A longer schedule is not an error for the
+    default implementation: UPD_IMPL_TCGEN05 runs it on the FFMA kernel; the forced tcgen05 variants say "unsupported"."""
+    kernels, _ = _k()
+    torch.manual_seed(9)
+    T, F, O, K = 56, 1, 30, 4
+    sd = _random_ns_weights(F, T)
+    dev = _dev()
+    packed = _pack_ns(sd, F, T)
+    gx = (torch.rand(3, O, F) * 0.3 + 0.05).to(dev)
+    a = kernels.nsdiff_sample(packed, None, gx, 3, 1, K, 2, O, F, T, seed=5, impl=0)
+    b = kernels.nsdiff_sample(packed, None, gx, 3, 1, K, 2, O, F, T, seed=5, impl=1)
+    assert torch.isfinite(a).all() and torch.equal(a, b)
+    for impl in (2, 4):
+        with pytest.raises(RuntimeError, match="unsupported"):
+            kernels.nsdiff_sample(packed, None, gx, 3, 1, K, 2, O, F, T, seed=5, impl=impl)
+    # and F = 3 (outside the warp-specialised kernel) takes the two-tile tcgen05 kernel under the default
+    sd3 = _random_ns_weights(3, 20)
+    p3 = _pack_ns(sd3, 3, 20)
+    gx3 = (torch.rand(2, O, 3) * 0.3 + 0.05).to(dev)
+    c = kernels.nsdiff_sample(p3, None, gx3, 2, 1, K, 2, O, 3, 20, seed=6, impl=0)
+    d = kernels.nsdiff_sample(p3, None, gx3, 2, 1, K, 2, O, 3, 20, seed=6, impl=2)
+    assert torch.equal(c, d)

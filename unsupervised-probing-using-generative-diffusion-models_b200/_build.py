@@ -22,7 +22,7 @@ INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_NAME = "libupd_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
 BUILD_DIR = os.path.join(PKG_DIR, "build")
-SOURCES = ["api.cu", "sampler_simt.cu", "sampler_tc.cu", "sampler_ws.cu", "selftest_umma.cu", "mpv_reduce.cu", "sigma_est.cu",
+SOURCES = ["api.cu", "sampler_simt.cu", "sampler_tc.cu", "sampler_ws.cu", "mpv_reduce.cu", "sigma_est.cu",
            "infill_steps.cu", "stg_steps.cu", "fx_fused.cu", "gemm3.cu", "fx_attention.cu", "dts_attention.cu", "dts_norm.cu"]
 HEADERS = ["upd_common.cuh", "sampler_params.cuh", "sampler_math.cuh", "sampler_epi.cuh", "tc_helpers.cuh"]
 NVCC_FLAGS = [
@@ -107,6 +107,30 @@ def build_library(force=False, verbose=False, variant=None, extra=()):
     return lib_path
 
 
+SELFTEST_LIB = os.path.join(PKG_DIR, "libupd_selftest.so")
+
+
+def build_selftest(force=False):
+    """tests-only library with the tcgen05 descriptor known-answer kernel (csrc/selftest_umma.cu); not part of the
+    product ABI and never loaded by the package."""
+    src = os.path.join(CSRC, "selftest_umma.cu")
+    h = _header_digest(())
+    with open(src, "rb") as f:
+        h.update(f.read())
+    digest, stamp = h.hexdigest(), SELFTEST_LIB + ".digest"
+    if not force and os.path.exists(SELFTEST_LIB) and os.path.exists(stamp):
+        with open(stamp) as f:
+            if f.read().strip() == digest:
+                return SELFTEST_LIB
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-shared", "-I", INCLUDE, "-o", SELFTEST_LIB, src]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed on selftest_umma.cu:\n" + proc.stdout + proc.stderr)
+    with open(stamp, "w") as f:
+        f.write(digest)
+    return SELFTEST_LIB
+
+
 if __name__ == "__main__":
     args = sys.argv[1:]
     variant = None
@@ -116,3 +140,5 @@ if __name__ == "__main__":
         del args[i:i + 2]
     print(build_library(force="--force" in args, verbose="-v" in args, variant=variant,
                         extra=[a for a in args if a.startswith("-D")]))
+    if variant is None:
+        print(build_selftest(force="--force" in args))

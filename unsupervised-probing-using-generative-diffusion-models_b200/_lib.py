@@ -12,7 +12,7 @@ _LIB = None
 SYMBOLS = (
     "upd_error_string", "upd_last_cuda_error", "upd_abi_version", "upd_denoiser_pack_bytes", "upd_denoiser_pack",
     "upd_nsdiff_sample", "upd_tmdm_sample", "upd_mpv_scratch_bytes", "upd_mpv_reduce", "upd_gram_centered", "upd_prediction_error", "upd_sigma_estimation",
-    "upd_selftest_umma", "upd_dts_ddim_step", "upd_dts_adagrad_step", "upd_dts_infill", "upd_gauss_fill",
+    "upd_dts_ddim_step", "upd_dts_adagrad_step", "upd_dts_infill", "upd_gauss_fill",
     "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_dts_attention", "upd_dts_attention_bwd", "upd_dts_layernorm", "upd_dts_layernorm_bwd", "upd_stg_posterior", "upd_nsx_step", "upd_stg_gated_aggregate", "upd_stg_tcn_ln", "upd_stg_tcn_ln_cat", "upd_fx_split", "upd_gemm3", "upd_fx_add_ln_split", "upd_fx_attention", "upd_fx_attention_hs16", "upd_fx_embed_split",
 )
 
@@ -70,8 +70,6 @@ def lib():
     L.upd_prediction_error.argtypes = [vp, vp, i, i, i, vp, vp]
     L.upd_sigma_estimation.restype = ctypes.c_int
     L.upd_sigma_estimation.argtypes = [ctypes.POINTER(UpdSigmaWeights), vp, i, i, i, i, i, i, ctypes.c_float, vp, vp]
-    L.upd_selftest_umma.restype = ctypes.c_int
-    L.upd_selftest_umma.argtypes = [vp, vp, vp, i, i, i, vp]
     ll, f32, u32 = ctypes.c_longlong, ctypes.c_float, ctypes.c_uint32
     L.upd_dts_ddim_step.restype = ctypes.c_int
     L.upd_dts_ddim_step.argtypes = [vp, vp, ll, f32, f32, f32, f32, f32, vp, i, vp, vp, vp, vp]

@@ -15,8 +15,6 @@ cudaError_t upd_launch_mpv(const float* traj, const float* scale, int n_win, int
                            cudaStream_t stream);
 cudaError_t upd_launch_sigma(const UpdSigmaWeights& w, const float* x, int rows, int Lw, int R, int F, int H,
                              int O, float add_eps, float* gx, cudaStream_t stream);
-cudaError_t upd_launch_selftest_umma(const float* a, const float* b, float* d, int K, int mode, int flags,
-                                     cudaStream_t stream);
 
 cudaError_t upd_launch_dts_ddim(const float* x0_raw, const float* img, long long n, float sqrt_recip, float sqrt_recipm1,
                                 float sqrt_an, float c, float sigma, const float* noise, int last, float* x_start,
@@ -317,16 +315,6 @@ int upd_sigma_estimation(const UpdSigmaWeights* w, const float* x_dev, int rows,
   if (rc != UPD_OK) return rc;
   cudaError_t e = upd_launch_sigma(*w, x_dev, rows, L, R, F, H, O, add_eps, gx_dev, (cudaStream_t)stream);
   if (e == cudaErrorInvalidValue) return UPD_ERR_UNSUPPORTED;
-  return e == cudaSuccess ? UPD_OK : cuda_fail(e);
-}
-
-int upd_selftest_umma(const float* a_dev, const float* b_dev, float* d_dev, int K, int mode, int flags, void* stream) {
-  if (!a_dev || !b_dev || !d_dev) return UPD_ERR_BAD_ARG;
-  if (mode == 0 ? (K != 128) : (K < 8 || K > 32 || K % 8)) return UPD_ERR_UNSUPPORTED;
-  int sms = 0;
-  int rc = device_info(&sms);
-  if (rc != UPD_OK) return rc;
-  cudaError_t e = upd_launch_selftest_umma(a_dev, b_dev, d_dev, K, mode, flags, (cudaStream_t)stream);
   return e == cudaSuccess ? UPD_OK : cuda_fail(e);
 }
 

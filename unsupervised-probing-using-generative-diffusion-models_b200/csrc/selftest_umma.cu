@@ -106,10 +106,16 @@ selftest_umma_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
 
 }  // namespace
 
-cudaError_t upd_launch_selftest_umma(const float* a, const float* b, float* d, int K, int mode, int flags,
-                                     cudaStream_t stream) {
+// Test-only entry point (libupd_selftest.so, built by _build.build_selftest(); NOT part of the product ABI):
+// D[128,128] = A[128,K] * B[128,K]^T with A staged in TMEM and B in shared memory (mode 0: fp16 hi/lo 3-pass, K = 128;
+// mode 1: tf32 hi/lo 3-pass, K = 8, 16, 24, 32); flags bit 0 swaps the descriptor's LBO/SBO (negative control).
+// Returns 0, 2 (unsupported K) or 3 (CUDA error).
+extern "C" int upd_selftest_umma(const float* a_dev, const float* b_dev, float* d_dev, int K, int mode, int flags,
+                                 void* stream) {
+  if (!a_dev || !b_dev || !d_dev) return 1;
+  if (mode == 0 ? (K != 128) : (K < 8 || K > 32 || K % 8)) return 2;
   cudaError_t e = cudaFuncSetAttribute(selftest_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  if (e != cudaSuccess) return e;
-  selftest_umma_kernel<<<1, 128, 65536, stream>>>(a, b, d, K, mode, flags);
-  return cudaGetLastError();
+  if (e != cudaSuccess) return 3;
+  selftest_umma_kernel<<<1, 128, 65536, (cudaStream_t)stream>>>(a_dev, b_dev, d_dev, K, mode, flags);
+  return cudaGetLastError() == cudaSuccess ? 0 : 3;
 }

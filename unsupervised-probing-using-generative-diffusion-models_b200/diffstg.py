@@ -21,6 +21,7 @@ is restated for the GPU:
 GEMMs / convolutions are library calls in plain fp32 (TF32 disabled).  There is no CPU path.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -353,7 +354,7 @@ class PreparedUGnet:
         agg = gated_aggregate(kqvs.contiguous(), rowptr, col, b["gnn_bias"], V, C)
         # up-sampling GEMM with the shortcut as its accumulator input: out = shortcut + agg W_up + bias
         if tc_ok:
-            up = torch.addmm(sc, a3_split(agg), b["up_w3"].t(), out_dtype=torch.float32)        # bias inside the GEMM
+            up = gemm3(a3_split(agg), b["up_w3"], c_out * T_in, addend=sc.contiguous())          # bias inside the GEMM
         else:
             up = torch.addmm(sc, agg, b["up_w"]) + b["up_b_full"]
         return up.view(N, c_out, T_in)
@@ -390,6 +391,37 @@ class PreparedUGnet:
                 x = run(blk, x if blk[1] == "upsample" else (x, hs.pop()))      # (x, skip): concatenated inside the kernel
             e = torch.matmul(self.out0_w[:, :, 0], x) + self.out0_b[None, :, None]
             return F.linear(e, self.out1_w, self.out1_b)
+
+
+class GraphedForward:
+    """CUDA-graph replay of ``PreparedUGnet.forward``.  One eps prediction is ~750 kernel launches of a few microseconds
+    each (12 residual blocks x (fused TCN, 3 GEMMs, 2 operand splits, gated aggregation, glue)): issued one by one from
+    Python the GPU waits for the host.  A forward depends on the step only through a row of the per-step bias tables, so
+    it is captured once per (step t, row count N) into a graph over static input buffers and replayed for every group of
+    replicas and every sweep after that; all graphs of a model share one memory pool (they never run concurrently)."""
+
+    def __init__(self, prep):
+        self.prep, self.graphs, self.static, self.pool = prep, {}, {}, None
+
+    def __call__(self, xt, xm, t, rowptr, col, V):
+        skey = (tuple(xt.shape), rowptr.data_ptr(), col.data_ptr(), int(V))
+        st = self.static.get(skey)
+        if st is None:
+            st = self.static[skey] = {"xt": torch.empty_like(xt), "xm": torch.empty_like(xm)}
+            self.prep.forward(xt, xm, t, rowptr, col, V)            # eager once per shape: lazy caches, cuDNN plans
+        st["xt"].copy_(xt)
+        st["xm"].copy_(xm)
+        g = self.graphs.get((skey, int(t)))
+        if g is None:
+            torch.cuda.current_stream(xt.device).synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, pool=self.pool):
+                out = self.prep.forward(st["xt"], st["xm"], t, rowptr, col, V)
+            if self.pool is None:
+                self.pool = graph.pool()
+            g = self.graphs[(skey, int(t))] = (graph, out)
+        g[0].replay()
+        return g[1]
 
 
 class DiffSTG(nn.Module):
@@ -488,6 +520,13 @@ class DiffSTG(nn.Module):
     def draws_per_round(self):
         return 1 + sum(1 for p in self.step_plan() if p[5])
 
+    use_cuda_graphs = os.environ.get("UPD_STG_GRAPHS", "1") != "0"
+
+    def _graphed_forward(self, prep):
+        if getattr(self, "_graphed", None) is None or self._graphed.prep is not prep:
+            self._graphed = GraphedForward(prep)
+        return self._graphed
+
     def predict_eps(self, xt, x_masked, t, edge_index, num_nodes):
         """UGnet.forward for rows that share step t; rows are replicas of the num_nodes-node graph."""
         dev = _lib.require_cuda(xt.device)
@@ -524,6 +563,7 @@ class DiffSTG(nn.Module):
             self._windows_drawn += W
         rowptr, col = self._csr(edge_index, num_nodes, dev)
         prep, lib, plan = self.prepared(), _lib.lib(), self.step_plan()
+        fwd = self._graphed_forward(prep) if self.use_cuda_graphs and noise is None and dev.type == "cuda" else prep.forward
         reps = [(w, k) for w in range(W) for k in range(K)]             # replica = (window, sample)
         per = max(1, self.rows_per_launch // V)
         if noise is not None:
@@ -553,7 +593,7 @@ class DiffSTG(nn.Module):
                 i_draw += 1
                 nxt = torch.empty_like(xt)
                 for (t1, t2, a, b, c, noisy) in plan:
-                    pred = prep.forward(xt, xm, t1, rowptr, col, V)
+                    pred = fwd(xt, xm, t1, rowptr, col, V)
                     z = None
                     if noisy:
                         z = draw(i_draw)

@@ -120,15 +120,3 @@ def sigma_estimation(weights, x, R, O, add_eps=0.0):
                                              _lib.ptr(gx), _lib.stream_ptr(dev))
     _lib.check(rc, "upd_sigma_estimation")
     return gx
-
-
-def selftest_umma(a, b, mode=0, flags=0):
-    """D = A @ B^T through the tcgen05 path of the sampler (A via TMEM, B via shared memory)."""
-    dev = a.device
-    _lib.require_cuda(dev)
-    d = torch.zeros((128, 128), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
-        rc = _lib.lib().upd_selftest_umma(_lib.ptr(a), _lib.ptr(b), _lib.ptr(d), a.shape[1], mode, flags,
-                                          _lib.stream_ptr(dev))
-    _lib.check(rc, "upd_selftest_umma")
-    return d
