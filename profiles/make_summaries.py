@@ -1,6 +1,7 @@
 """Turn the raw ncu outputs a gpurun call brought back (gpurun_out/) into the tracked summaries in profiles/.
 
-    python profiles/make_summaries.py r01        # reads gpurun_out/{launches.csv,sampler_raw.csv,sampler_src.csv}
+    python profiles/make_summaries.py r01                # reads gpurun_out/{launches.csv,sampler_raw.csv,sampler_src.csv}
+    python profiles/make_summaries.py r02 sampler_ws     # round 2: the warp-specialised kernel (file names follow the kernel)
 
 Inputs are produced on the GPU box by (see scratch job scripts / B200_PROFILING.md):
     UPD_BENCH_SKIP_CPU=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv \
@@ -16,7 +17,9 @@ import re
 import sys
 
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
-OWN = ("sampler_tc_kernel", "sampler_simt_kernel", "welford_over_samples", "window_means", "sigma_estimation_kernel",
+kern = sys.argv[2] if len(sys.argv) > 2 else "sampler_tc"
+OWN = ("sampler_ws_kernel", "gemm3_pair_kernel", "gemm3_kernel", "gram_centered_kernel", "prediction_error_kernel",
+       "sampler_tc_kernel", "sampler_simt_kernel", "welford_over_samples", "window_means", "sigma_estimation_kernel",
        "fx_attention_kernel", "fx_add_ln_split_kernel", "fx_split_kernel", "fx_embed_split_kernel")
 
 # ---- launch list -> shares ----
@@ -39,7 +42,7 @@ with open("profiles/%s_bench_launches_summary.txt" % tag, "w") as f:
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:22]:
         f.write("%12.2f %7.2f%% %7d  %s\n" % (t / 1e6, 100 * t / tot, n, k))
     mine = sum(t for k, (n, t) in agg.items() if k in OWN)
-    f.write("# own kernels: %.2f%% of GPU time; the rest are the f(x) encoder's library GEMMs (cuBLAS fp16, nvjet_hss) and embedding elementwise ops\n" % (100 * mine / tot))
+    f.write("# own kernels: %.2f%% of GPU time; the rest are torch elementwise / copy kernels of the f(x) embedding and any library GEMM left\n" % (100 * mine / tot))
 
 # ---- sampler: ncu --set full ----
 rows = list(csv.reader(open("gpurun_out/sampler_raw.csv")))
@@ -55,11 +58,11 @@ d = {}
 for h, u, v in zip(hdr, units, vals):
     if h in keep or (h.startswith("smsp__average_warps_issue_stalled") and h.endswith("per_issue_active.ratio")):
         d[h] = {"unit": u, "value": v}
-json.dump(d, open("profiles/%s_sampler_tc_ncu_full_metrics.json" % tag, "w"), indent=1)
+json.dump(d, open("profiles/%s_%s_ncu_full_metrics.json" % (tag, kern), "w"), indent=1)
 rd = float(d["dram__bytes_read.sum"]["value"]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3}[d["dram__bytes_read.sum"]["unit"]]
 wr = float(d["dram__bytes_write.sum"]["value"]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3}[d["dram__bytes_write.sum"]["unit"]]
-json.dump({"kernel": "sampler_tc_kernel<NsDiff,F=1>",
-           "source": "profiles/%s_sampler_tc_ncu_full_metrics.json (ncu --set full on the bench workload)" % tag,
+json.dump({"kernel": "%s_kernel<NsDiff,F=1>" % kern,
+           "source": "profiles/%s_%s_ncu_full_metrics.json (ncu --set full on the bench workload)" % (tag, kern),
            "dram_bytes_per_launch_bench_workload": rd + wr, "dram_read_bytes": rd, "dram_write_bytes": wr,
            "algorithmic_bytes_per_launch": 181 * 100 * 100 * 100 * 4 + 2 * 181 * 100 * 100 * 4},
           open("profiles/sampler_tc_ncu_full.json", "w"), indent=1)
@@ -87,7 +90,7 @@ for r in rows[2:]:
     for c in stall_cols:
         stall_tot[c] += int(r[ix[c]] or 0)
     top.append((samp, s, sorted([(c, int(r[ix[c]] or 0)) for c in stall_cols if int(r[ix[c]] or 0) > 0], key=lambda x: -x[1])[:2]))
-with open("profiles/%s_sampler_tc_sass_mix.txt" % tag, "w") as f:
+with open("profiles/%s_%s_sass_mix.txt" % (tag, kern), "w") as f:
     f.write("# ncu --page source of the same capture: SASS opcode mix (warp instructions) and sampled stall sites\n")
     f.write("# total warp instructions %d, samples %d\n" % (ti, ts))
     for op, (i, s) in sorted(by_op.items(), key=lambda kv: -kv[1][0])[:24]:
@@ -97,7 +100,7 @@ with open("profiles/%s_sampler_tc_sass_mix.txt" % tag, "w") as f:
     for samp, s, st in sorted(top, key=lambda t: -t[0])[:14]:
         f.write("%5.2f%%  %-64s %s\n" % (100 * samp / ts, s[:64], st))
 print(open("profiles/%s_bench_launches_summary.txt" % tag).read())
-print(open("profiles/%s_sampler_tc_sass_mix.txt" % tag).read())
+print(open("profiles/%s_%s_sass_mix.txt" % (tag, kern)).read())
 for k in ("gpu__time_duration.sum", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_elapsed", "sm__issue_active.avg.pct_of_peak_sustained_elapsed",
           "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "dram__bytes_read.sum", "dram__bytes_write.sum"):
     print(k, d[k])

@@ -10,6 +10,8 @@
 //   fx_add_ln_split_kernel . residual add + LayerNorm (+ the stack's final LayerNorm) -> fp32 y and A3(y)
 // One warp per row, float4 loads, 8-byte fp16 stores; HBM-bound: 4 B read + 6 B (+4 B) written per element.
 #include <cuda_fp16.h>
+
+#include "tc_helpers.cuh"
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -26,12 +28,9 @@ __device__ __forceinline__ float fx_act(float v, int act) {
 
 // 4 consecutive values -> hi/lo halves stored at columns c (hi), K + c (lo), 2K + c (hi) of one A3 row.
 __device__ __forceinline__ void fx_store4(__half* row, int K, int c, float4 v) {
-  __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-  float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-  __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
   uint2 hi, lo;
-  hi.x = *reinterpret_cast<uint32_t*>(&h01); hi.y = *reinterpret_cast<uint32_t*>(&h23);
-  lo.x = *reinterpret_cast<uint32_t*>(&l01); lo.y = *reinterpret_cast<uint32_t*>(&l23);
+  tc::split_f16x2(v.x, v.y, hi.x, lo.x);
+  tc::split_f16x2(v.z, v.w, hi.y, lo.y);
   *reinterpret_cast<uint2*>(row + c) = hi;
   *reinterpret_cast<uint2*>(row + K + c) = lo;
   *reinterpret_cast<uint2*>(row + 2 * K + c) = hi;

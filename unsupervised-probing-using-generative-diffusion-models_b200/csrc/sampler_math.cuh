@@ -10,6 +10,8 @@
 
 #include <utility>
 
+#include "tc_helpers.cuh"
+
 namespace sm {
 
 // compile-time loop: f(std::integral_constant<int, 0>) ... f(std::integral_constant<int, N-1>)
@@ -122,17 +124,7 @@ __device__ __forceinline__ float2 softplus2(float2 z) {
 // hi = fp16(a), lo = fp16(a - hi): 22 mantissa bits between them.  Four instructions per pair: F2FP (pack hi),
 // two FHADD (sm_100 mixed-precision add: fp32 + (-fp16) in one instruction, no unpack), F2FP (pack lo).
 // Element 2c goes to bits [0,16), element 2c+1 to bits [16,32), as the A operand wants them in a TMEM column.
-__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  uint32_t h;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
-  float la, lb;
-  asm("{ .reg .b16 h0, h1, n0, n1;\n\t"
-      "mov.b32 {h0,h1}, %2;\n\tneg.f16 n0, h0;\n\tneg.f16 n1, h1;\n\t"
-      "add.rn.f32.f16 %0, n0, %3;\n\tadd.rn.f32.f16 %1, n1, %4; }"
-      : "=f"(la), "=f"(lb) : "r"(h), "f"(a), "f"(b));
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(lb), "f"(la));
-  hi = h;
-}
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) { tc::split_f16x2(a, b, hi, lo); }
 
 // ---- sigma head: softplus on [0,1] without MUFU ---------------------------------------------------
 // The sigma head applies softplus to the L2-normalised, non-negative hidden vector hn (components in [0,1]):

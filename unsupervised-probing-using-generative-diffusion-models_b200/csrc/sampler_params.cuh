@@ -43,8 +43,19 @@ __device__ __forceinline__ float upd_draw(const UpdSamplerParams& p, const UpdRo
     idx = (idx * p.O + ix.o) * F + f;
     return p.noise[idx];
   }
-  return upd_gauss(p.seed, p.window_base + (unsigned long long)ix.w, (uint32_t)ix.b, (uint32_t)ix.k,
-                   (uint32_t)(ix.o * F + f), (uint32_t)draw);
+  return upd_pick4(upd_gauss4(p.seed, p.window_base + (unsigned long long)ix.w, (uint32_t)ix.b, (uint32_t)ix.k,
+                              (uint32_t)(ix.o * F + f), (uint32_t)draw >> 2), draw);
+}
+
+// The same stream for a sampler that consumes the draws of an element in order: `cache` holds the current group of four
+// and is refilled (one Philox call) when `draw` enters a new group.  Injected noise bypasses it.
+__device__ __forceinline__ float upd_draw_cached(const UpdSamplerParams& p, const UpdRowIndex& ix, int f, int F, int draw,
+                                                 float4& cache) {
+  if (p.noise != nullptr) return upd_draw(p, ix, f, F, draw);
+  if ((draw & 3) == 0)
+    cache = upd_gauss4(p.seed, p.window_base + (unsigned long long)ix.w, (uint32_t)ix.b, (uint32_t)ix.k,
+                       (uint32_t)(ix.o * F + f), (uint32_t)draw >> 2);
+  return upd_pick4(cache, draw);
 }
 
 cudaError_t upd_launch_sampler_simt(const UpdSamplerParams& p, int kind, int F, int sms, cudaStream_t stream);

@@ -32,8 +32,7 @@ sampler_simt_kernel(const UpdSamplerParams p) {
   float* b1 = w1t + IN * 128;
   float* b2 = b1 + 128;
   float* b3 = b2 + 128;
-  float* emb = b3 + 128;                                    // [3][TE][128]
-  float* w4 = emb + 3 * L.TE * 128;                         // [F][128]
+  float* w4 = b3 + 128;                                     // [F][128]
   float* wsg = w4 + F * 128;                                // [F][128]
   float* sched = wsg + F * 128;                             // [n_sched][T]
   float* hbuf = sched + L.n_sched * p.T;                    // [warps][ROWS][128]
@@ -42,9 +41,8 @@ sampler_simt_kernel(const UpdSamplerParams p) {
   for (int i = threadIdx.x; i < 128 * 128; i += blockDim.x) { w2t[i] = gf(L.w2t)[i]; w3t[i] = gf(L.w3t)[i]; }
   for (int i = threadIdx.x; i < IN * 128; i += blockDim.x) w1t[i] = gf(L.w1t)[i];
   for (int i = threadIdx.x; i < 128; i += blockDim.x) { b1[i] = gf(L.b1)[i]; b2[i] = gf(L.b2)[i]; b3[i] = gf(L.b3)[i]; }
-  for (int i = threadIdx.x; i < L.TE * 128; i += blockDim.x) {
-    emb[i] = gf(L.e1)[i]; emb[L.TE * 128 + i] = gf(L.e2)[i]; emb[2 * L.TE * 128 + i] = gf(L.e3)[i];
-  }
+  // the three [TE,128] step-embedding tables stay in global memory (one coalesced 512-byte row per layer and step, an
+  // L1/L2 hit): the kernel's shared memory does not grow with T, so every T <= UPD_MAX_T runs here
   for (int i = threadIdx.x; i < F * 128; i += blockDim.x) { w4[i] = gf(L.w4)[i]; wsg[i] = NS ? gf(L.ws)[i] : 0.f; }
   for (int i = threadIdx.x; i < L.n_sched * p.T; i += blockDim.x) sched[i] = gf(L.sched)[i];
   __syncthreads();
@@ -103,7 +101,7 @@ sampler_simt_kernel(const UpdSamplerParams p) {
       const float* bias = b1;
 #pragma unroll 1
       for (int layer = 0; layer < 3; ++layer) {
-        const float* e = emb + (layer * L.TE + t) * 128;
+        const float* e = gf(layer == 0 ? L.e1 : (layer == 1 ? L.e2 : L.e3)) + t * 128;
         if (layer > 0) {
           const float* wt = (layer == 1) ? w2t : w3t;
           bias = (layer == 1) ? b2 : b3;
@@ -191,7 +189,7 @@ template <int KIND, int F>
 cudaError_t launch(const UpdSamplerParams& p, int sms, cudaStream_t stream) {
   const UpdPackLayout L = upd_make_layout(KIND, F, p.T);
   constexpr int IN = (KIND == 1) ? 2 * F : 3 * F;
-  size_t smem = sizeof(float) * (2 * 128 * 128 + IN * 128 + 3 * 128 + 3 * L.TE * 128 + 2 * F * 128 +
+  size_t smem = sizeof(float) * (2 * 128 * 128 + IN * 128 + 3 * 128 + 2 * F * 128 +
                                  L.n_sched * p.T + SIMT_WARPS * ROWS * 128);
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   auto kern = sampler_simt_kernel<KIND, F>;

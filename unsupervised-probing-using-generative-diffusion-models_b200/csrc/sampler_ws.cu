@@ -308,6 +308,7 @@ sampler_ws_kernel(const UpdSamplerParams p) {
       bool live[2];
       UpdRowIndex ix[2];
       float y[2][F], y0h[2][F], gxv[2][F], zn[2][F];
+      float4 zc[2][F];                                   // the current group of four draws of every element
 #pragma unroll
       for (int tile = 0; tile < 2; ++tile) {
         row[tile] = ((it * gridDim.x + blockIdx.x) * 2 + tile) * 128 + trow;
@@ -318,7 +319,7 @@ sampler_ws_kernel(const UpdSamplerParams p) {
         for (int f = 0; f < F; ++f) {
           y0h[tile][f] = p.y0_hat ? p.y0_hat[cidx + f] : 0.f;
           gxv[tile][f] = NS ? p.gx[cidx + f] : 1.f;
-          const float z = upd_draw(p, ix[tile], f, F, 0);
+          const float z = upd_draw_cached(p, ix[tile], f, F, 0, zc[tile][f]);
           y[tile][f] = NS ? sqrtf(gxv[tile][f]) * z + y0h[tile][f] : z + y0h[tile][f];   // nsdiff_utils.py:274 / tmdm_diffusion_utils.py:110
         }
         build_a1(tile, y[tile], y0h[tile], gxv[tile]);
@@ -356,7 +357,7 @@ sampler_ws_kernel(const UpdSamplerParams p) {
 #pragma unroll
             for (int tile = 0; tile < 2; ++tile)
 #pragma unroll
-              for (int f = 0; f < F; ++f) zn[tile][f] = last ? 0.f : upd_draw(p, ix[tile], f, F, p.T - t);
+              for (int f = 0; f < F; ++f) zn[tile][f] = last ? 0.f : upd_draw_cached(p, ix[tile], f, F, p.T - t, zc[tile][f]);
             UPD_STAMP(5);
           }
         }

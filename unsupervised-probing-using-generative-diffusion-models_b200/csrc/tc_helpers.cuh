@@ -181,11 +181,17 @@ template <int N> __device__ __forceinline__ void tmem_st(uint32_t taddr, const u
 // fp16 hi/lo split of two consecutive K elements, packed as the A operand wants them in a TMEM
 // column: element 2c in bits [0,16), element 2c+1 in bits [16,32).
 __device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  __half2 h = __floats2half2_rn(a, b);
-  float2 hf = __half22float2(h);
-  __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<uint32_t*>(&h);
-  lo = *reinterpret_cast<uint32_t*>(&l);
+  // four instructions per pair: F2FP (pack hi), two FHADD (sm_100 mixed-precision add: fp32 + (-fp16), no unpack),
+  // F2FP (pack lo) -- the unpack-and-subtract form (HADD2.F32 + FADD per element) needs six
+  uint32_t h;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));
+  float la, lb;
+  asm("{ .reg .b16 h0, h1, n0, n1;\n\t"
+      "mov.b32 {h0,h1}, %2;\n\tneg.f16 n0, h0;\n\tneg.f16 n1, h1;\n\t"
+      "add.rn.f32.f16 %0, n0, %3;\n\tadd.rn.f32.f16 %1, n1, %4; }"
+      : "=f"(la), "=f"(lb) : "r"(h), "f"(a), "f"(b));
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(lb), "f"(la));
+  hi = h;
 }
 __device__ __forceinline__ float to_tf32(float x) {
   uint32_t u;

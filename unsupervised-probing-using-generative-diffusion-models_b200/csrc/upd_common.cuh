@@ -122,6 +122,24 @@ __device__ __forceinline__ float upd_gauss(uint64_t seed, uint64_t window, uint3
   return z0;
 }
 
+// Four N(0,1) draws from ONE Philox call, for the fused samplers: the draws number 4g .. 4g+3 of a trajectory element
+// (draw 0 = y_T, draw i = reverse step t = T - i) share the call keyed by the draw group g.  The stream stays a pure
+// function of (seed, global window, row, sample, element, draw), so it is still independent of how a sweep is tiled,
+// batched or sharded; a sampler that walks the steps in order pays a quarter of the Philox + Box-Muller work per draw.
+__device__ __forceinline__ float4 upd_gauss4(uint64_t seed, uint64_t window, uint32_t row, uint32_t sample, uint32_t elem,
+                                             uint32_t draw_group) {
+  uint32_t r[4];
+  upd_philox4x32_10(elem, sample, row, (draw_group & 0xFFu) | ((uint32_t)window << 8),
+                    (uint32_t)seed ^ (uint32_t)(window >> 24) ^ 0x9E3779B9u, (uint32_t)(seed >> 32), r);
+  float4 z;
+  upd_box_muller(r[0], r[1], z.x, z.y);
+  upd_box_muller(r[2], r[3], z.z, z.w);
+  return z;
+}
+__device__ __forceinline__ float upd_pick4(const float4& z, int i) {
+  return (i & 2) ? ((i & 1) ? z.w : z.z) : ((i & 1) ? z.y : z.x);
+}
+
 // softplus(z) = log1p(exp(z)), beta=1, threshold=20 (F.softplus defaults).
 // max(z,0) + ln2*lg2(1 + ex2(-|z|*log2e)): two MUFU ops; for z > 20 the correction is below
 // half an ulp of z, so the threshold branch of the reference is reproduced without a select.
