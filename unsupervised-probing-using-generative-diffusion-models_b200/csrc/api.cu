@@ -55,6 +55,12 @@ cudaError_t upd_launch_dts_attention_bwd(const float* q, long long q_stride, con
                                          long long kv_stride, int R, int H, int Lq, int S, float scale, const float* o,
                                          const float* lse, const float* d_o, float* dq, long long dq_stride, float* dk,
                                          float* dv, long long dkv_stride, cudaStream_t stream);
+cudaError_t upd_launch_dts_attention_tc(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
+                                        int R, int H, int Lq, int S, float scale, float* o, float* lse, cudaStream_t stream);
+cudaError_t upd_launch_dts_attention_tc_bwd(const float* q, long long q_stride, const float* k, const float* v,
+                                            long long kv_stride, int R, int H, int Lq, int S, float scale, const float* o,
+                                            const float* lse, const float* d_o, float* dq, long long dq_stride, float* dk,
+                                            float* dv, long long dkv_stride, cudaStream_t stream);
 cudaError_t upd_launch_fx_embed_split(const float* x, const float* w, const float* pe, long long rows, int L, int NF, int K,
                                       float* y, void* a3, cudaStream_t stream);
 cudaError_t upd_launch_dts_layernorm(const float* x, const float* gamma, const float* beta, long long rows, int D, float* y,
@@ -487,12 +493,23 @@ int upd_fx_attention(const float* q_dev, long long q_row_stride, const float* k_
                                      H, Lq, S, causal, scale, a3_dev, (cudaStream_t)stream));
 }
 
+// UPD_DTS_ATTN_FFMA=1: run the fp32 FFMA attention kernels even where the tcgen05 ones apply (comparison runs, tests).
+static bool dts_attention_ffma_forced() {
+  const char* e = getenv("UPD_DTS_ATTN_FFMA");
+  return e && e[0] == '1';
+}
+
 int upd_dts_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
                       long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale, float* o_dev,
                       float* lse_dev, void* stream) {
   if (!q_dev || !k_dev || !v_dev || !o_dev || R <= 0 || H <= 0 || Lq <= 0 || S <= 0) return UPD_ERR_BAD_ARG;
   if (head_dim != 16 || (long long)R * H > 0x7fffffffLL) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
+  if (!dts_attention_ffma_forced()) {       // tcgen05 kernel; sequences beyond its limits fall through to the FFMA kernel
+    cudaError_t e = upd_launch_dts_attention_tc(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev,
+                                                lse_dev, (cudaStream_t)stream);
+    if (e != cudaErrorInvalidValue) UPD_FINISH(e);
+  }
   UPD_FINISH(upd_launch_dts_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev, lse_dev,
                                       nullptr, nullptr, 0, 0, (cudaStream_t)stream));
 }
@@ -516,6 +533,12 @@ int upd_dts_attention_bwd(const float* q_dev, long long q_row_stride, const floa
     return UPD_ERR_BAD_ARG;
   if (head_dim != 16 || (long long)R * H > 0x7fffffffLL) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
+  if (!dts_attention_ffma_forced()) {
+    cudaError_t e = upd_launch_dts_attention_tc_bwd(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev,
+                                                    lse_dev, do_dev, dq_dev, dq_row_stride, dk_dev, dv_dev, dkv_row_stride,
+                                                    (cudaStream_t)stream);
+    if (e != cudaErrorInvalidValue) UPD_FINISH(e);
+  }
   UPD_FINISH(upd_launch_dts_attention_bwd(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev,
                                           lse_dev, do_dev, dq_dev, dq_row_stride, dk_dev, dv_dev, dkv_row_stride,
                                           (cudaStream_t)stream));
