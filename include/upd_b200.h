@@ -242,7 +242,11 @@ int upd_dts_layernorm_bwd(const float* x_dev, const float* dy_dev, const float* 
  *   q_dev + (r*Lq+i)*q_row_stride floats, head h at + h*16; k_dev / v_dev likewise over (r*S + j) with kv_row_stride, so
  *   Q|K|V may be one fused projection buffer.  lse_dev [R*H, Lq] (may be NULL in the forward) keeps the base-2
  *   log-sum-exp the backward needs; _bwd writes dq / dk / dv with the same addressing (dq_row_stride, dkv_row_stride).
- *   Limits: head_dim == 16; (S + Lq) * 136 bytes of shared memory. */
+ *   Runs on tcgen05 tensor cores (csrc/dts_attention_tc.cu: fp16 hi/lo operands, fp32 accumulation in TMEM; the backward
+ *   scales each (row, head) tile of do_dev by a power of two, so cotangents of any magnitude keep fp32-grade accuracy)
+ *   for S <= 224 (forward) / S, Lq <= 224 (backward); longer sequences run the fp32 FFMA kernels (csrc/dts_attention.cu;
+ *   also with the environment variable UPD_DTS_ATTN_FFMA=1).
+ *   Limits: head_dim == 16; (S + Lq) * 136 bytes of shared memory on the FFMA path. */
 int upd_dts_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
                       long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale, float* o_dev,
                       float* lse_dev, void* stream);

@@ -137,11 +137,18 @@ def test_full_loop_runs_and_is_distributionally_sane():
     assert float(outs.var(dim=-1).mean()) > 0
 
 
-@pytest.mark.parametrize("Lq,S,cross", [(200, 200, False), (48, 48, False), (200, 120, True), (33, 70, True)])
-def test_fused_attention_forward_backward_against_autograd(Lq, S, cross):
-    """upd_dts_attention(_bwd) vs materialised-score attention differentiated by torch autograd (float64)."""
+@pytest.mark.parametrize("Lq,S,cross,gmag,ffma", [
+    (200, 200, False, 1.0, False), (48, 48, False, 1.0, False), (200, 120, True, 1.0, False), (33, 70, True, 1.0, False),
+    (200, 200, False, 1e-6, False),      # refinement-gradient sized cotangent: the backward's power-of-two scaling of dO
+    (224, 129, True, 3e4, False),        # largest tile of the tcgen05 kernels, two ragged row blocks, large cotangent
+    (260, 260, False, 1.0, False),       # beyond the tcgen05 limits: the FFMA kernels take over
+    (200, 200, False, 1e-6, True)])      # the FFMA kernels forced at the working shape
+def test_fused_attention_forward_backward_against_autograd(Lq, S, cross, gmag, ffma, monkeypatch):
+    """upd_dts_attention(_bwd) -- tcgen05 kernels, FFMA kernels beyond their limits -- vs materialised-score attention
+    differentiated by torch autograd (float64)."""
     import math
     from updgm_b200.diffusionts import FusedAttention
+    monkeypatch.setenv("UPD_DTS_ATTN_FFMA", "1" if ffma else "0")
     torch.manual_seed(Lq + S)
     R, H, hs = 5, 4, 16
     d = H * hs
@@ -159,7 +166,8 @@ def test_fused_attention_forward_backward_against_autograd(Lq, S, cross):
     att = torch.softmax(heads(q64) @ heads(k64).transpose(-1, -2) / math.sqrt(hs), -1)
     ref = (att @ heads(v64)).transpose(1, 2).reshape(R, Lq, d)
     assert _rel(out.detach(), ref.detach()) < 2e-5
-    w = torch.randn(R, Lq, d, device=DEV)
+    w = torch.randn(R, Lq, d, device=DEV) * gmag
+    w[0, :, :16] = 0.0                                    # an all-zero dO tile (row 0, head 0)
     grads = torch.autograd.grad((out * w).sum(), [qb] if not cross else [qb, kvb])
     refs = torch.autograd.grad((ref * w.double()).sum(), [qb] if not cross else [qb, kvb])
     for g, r in zip(grads, refs):

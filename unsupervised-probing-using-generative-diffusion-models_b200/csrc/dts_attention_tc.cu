@@ -35,6 +35,7 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "sampler_math.cuh"
 #include "tc_helpers.cuh"
 
 namespace {
@@ -136,42 +137,64 @@ __device__ __forceinline__ void mma3(uint32_t d, uint32_t a, uint64_t b_hi, uint
 }
 
 // ================================================ forward ==============================================================
-__global__ void __launch_bounds__(128, 2) dts_attn_tc_fwd_kernel(const DtsTcParams p) {
+constexpr int FWD_THREADS = 256;                           // two warps per TMEM lane quadrant (each half of the key groups)
+
+// Combined T-form of mult * X^T: rows 0..15 = hi parts, rows 16..31 = lo parts (a B operand with N = 32 that yields
+// [A hi(X)^T | A lo(X)^T] in one MMA; its first 16 rows alone are the N = 16 operand hi(X)^T):
+// elem(c', s) at (s/8)*512 + c'*16 + (s%8)*2.
+__device__ __forceinline__ void stage_tform32(const float* __restrict__ src, long long stride, int n, int NP, float mult,
+                                              unsigned char* dst) {
+  for (int i = threadIdx.x; i < NP * 2; i += blockDim.x) {
+    const int c = i & 15, s8 = i >> 4;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int s = s8 * 8 + j;
+      x[j] = s < n ? src[(long long)s * stride + c] * mult : 0.0f;
+    }
+    uint4 h, l;
+    tc::split_f16x2(x[0], x[1], h.x, l.x); tc::split_f16x2(x[2], x[3], h.y, l.y);
+    tc::split_f16x2(x[4], x[5], h.z, l.z); tc::split_f16x2(x[6], x[7], h.w, l.w);
+    const uint32_t off = (uint32_t)s8 * 512u + (uint32_t)c * 16u;
+    *reinterpret_cast<uint4*>(dst + off) = h;
+    *reinterpret_cast<uint4*>(dst + off + 256u) = l;
+  }
+}
+
+__global__ void __launch_bounds__(FWD_THREADS, 2) dts_attn_tc_fwd_kernel(const DtsTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ TcSync sync;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ float pm[2][128], ps[2][128];                  // partial row max / row sum of the two column halves
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2, row = quad * 32 + lane;
   const int rh = blockIdx.x, r = rh / p.H, h = rh - r * p.H;
   const int S = p.S, SP = (S + 15) & ~15, NIT = SP >> 4;
   unsigned char* k_hi = smem;
   unsigned char* k_lo = k_hi + nform_bytes(SP);
-  unsigned char* vt_hi = k_lo + nform_bytes(SP);
-  unsigned char* vt_lo = vt_hi + 32u * SP;
-  float* spad = reinterpret_cast<float*>(vt_lo + 32u * SP);   // [SP] 0, -inf for the padding keys
+  unsigned char* vt = k_lo + nform_bytes(SP);               // combined T-form, 64 * SP bytes
   if (tid == 0) { tc::mbar_init(tc::smem_u32(&sync.mma_bar), 1); tc::fence_mbar_init(); }
   if (warp == 0) tc::tmem_alloc<256>(tc::smem_u32(&sync.tmem_base));
   const float* kb = p.k + (long long)r * S * p.kv_stride + h * HS;
   const float* vb = p.v + (long long)r * S * p.kv_stride + h * HS;
   stage_nform(kb, p.kv_stride, S, SP, 1.0f, k_hi, k_lo);
-  stage_tform(vb, p.kv_stride, S, SP, 1.0f, vt_hi, vt_lo);
-  for (int s = tid; s < SP; s += 128) spad[s] = s < S ? 0.0f : -INFINITY;
+  stage_tform32(vb, p.kv_stride, S, SP, 1.0f, vt);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = sync.tmem_base;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
-  const uint32_t q_cols = tmem_base + lane_sel;             // [0,16): Q operand
-  const uint32_t o_cols = q_cols + 16u;                     // [16,32): O accumulator
-  const uint32_t s_cols = q_cols + 32u;                     // [32, 32+SP): scores, then the P operand
+  const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+  const uint32_t o_cols = lane_base;                        // [0,16): Q operand, then [0,32): O accumulator [hi*hi | small terms]
+  const uint32_t s_cols = lane_base + 32u;                  // [32, 32+SP): scores, then the P operand
   const uint32_t bar = tc::smem_u32(&sync.mma_bar);
   const float qs = p.scale * LOG2E;
   const int d = p.H * HS;
   uint32_t parity = 0;
 
   for (int q0 = 0; q0 < p.Lq; q0 += 128) {
-    const int l = q0 + tid;
+    const int l = q0 + row;
     const bool valid = l < p.Lq;
-    {
+    if (part == 0) {
       const float* qr = p.q + ((long long)r * p.Lq + (valid ? l : 0)) * p.q_stride + h * HS;
       float4 qv[4];
 #pragma unroll
@@ -182,9 +205,9 @@ __global__ void __launch_bounds__(128, 2) dts_attn_tc_fwd_kernel(const DtsTcPara
         tc::split_f16x2(qv[c].x * qs, qv[c].y * qs, o[2 * c], o[8 + 2 * c]);
         tc::split_f16x2(qv[c].z * qs, qv[c].w * qs, o[2 * c + 1], o[8 + 2 * c + 1]);
       }
-      tc::tmem_st16(q_cols, o);
+      tc::tmem_st16(o_cols, o);
+      tc::wait_st();
     }
-    tc::wait_st();
     tc::fence_before_sync();
     __syncthreads();
     if (tid == 0) {                                         // S = Q K^T
@@ -198,63 +221,75 @@ __global__ void __launch_bounds__(128, 2) dts_attn_tc_fwd_kernel(const DtsTcPara
     parity ^= 1u;
     tc::fence_after_sync();
 
+    // ---- row max over this warp's groups (part, part + 2, ..); padding keys exist only in the last group ----
     float m = -INFINITY;
-    for (int g = 0; g < NIT; ++g) {
+    for (int g = part; g < NIT; g += 2) {
       uint32_t ra[16];
       tc::tmem_ld16(s_cols + 16u * g, ra);
       tc::wait_ld();
+      if (16 * g + 16 > S) {
 #pragma unroll
-      for (int j = 0; j < 16; j += 4) {
-        const float4 d4 = *reinterpret_cast<const float4*>(spad + 16 * g + j);
-        m = fmaxf(fmaxf(m, fmaxf(__uint_as_float(ra[j]) + d4.x, __uint_as_float(ra[j + 1]) + d4.y)),
-                  fmaxf(__uint_as_float(ra[j + 2]) + d4.z, __uint_as_float(ra[j + 3]) + d4.w));
+        for (int j = 0; j < 16; ++j) if (16 * g + j < S) m = fmaxf(m, __uint_as_float(ra[j]));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          m = fmaxf(fmaxf(m, fmaxf(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1]))),
+                    fmaxf(__uint_as_float(ra[j + 2]), __uint_as_float(ra[j + 3])));
       }
     }
-    float sum = 0.0f;
-    {
-      uint32_t ra[16], rb[16], o[16];
-      tc::tmem_ld16(s_cols, ra);
-      for (int g = 0; g < NIT; ++g) {
-        uint32_t (&cur)[16] = (g & 1) ? rb : ra;
-        uint32_t (&nxt)[16] = (g & 1) ? ra : rb;
-        tc::wait_ld();
-        if (g + 1 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 1), nxt);
+    pm[part][row] = m;
+    __syncthreads();
+    m = fmaxf(pm[0][row], pm[1][row]);
+    // ---- p = 2^(s - m) in place as the fp16 hi/lo operand of O = P V, partial row sums ----
+    float2 sum2 = make_float2(0.f, 0.f);
+    const float2 nm2 = sm::splat(-m);
+    for (int g = part; g < NIT; g += 2) {
+      uint32_t ra[16], o[16];
+      tc::tmem_ld16(s_cols + 16u * g, ra);
+      tc::wait_ld();
+      const bool ragged = 16 * g + 16 > S;
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float2 d2 = *reinterpret_cast<const float2*>(spad + 16 * g + j);
-          const float e0 = ex2f((__uint_as_float(cur[j]) + d2.x) - m);
-          const float e1 = ex2f((__uint_as_float(cur[j + 1]) + d2.y) - m);
-          sum += e0 + e1;
-          tc::split_f16x2(e0, e1, o[j / 2], o[8 + j / 2]);
-        }
-        tc::tmem_st16(s_cols + 16u * g, o);
+      for (int j = 0; j < 16; j += 2) {
+        const float2 x = sm::fadd2(make_float2(__uint_as_float(ra[j]), __uint_as_float(ra[j + 1])), nm2);
+        float2 e = make_float2(ex2f(x.x), ex2f(x.y));
+        if (ragged) { e.x = 16 * g + j < S ? e.x : 0.0f; e.y = 16 * g + j + 1 < S ? e.y : 0.0f; }
+        sum2 = sm::fadd2(sum2, e);
+        tc::split_f16x2(e.x, e.y, o[j / 2], o[8 + j / 2]);
       }
+      tc::tmem_st16(s_cols + 16u * g, o);
     }
+    ps[part][row] = sum2.x + sum2.y;
     tc::wait_st();
     tc::fence_before_sync();
     __syncthreads();
-    if (tid == 0) {                                         // O = P V
+    if (tid == 0) {                                         // O = P V: hi * [hi | lo] (N = 32), lo * hi (N = 16) per 16 keys
       tc::fence_after_sync();
-      const uint32_t id = idesc_f16(HS);
-      for (int j = 0; j < NIT; ++j)
-        mma3(tmem_base + 16u, tmem_base + 32u + 16u * j, tc::smem_desc(tc::smem_u32(vt_hi) + (uint32_t)j * 512u, 256u, 128u),
-             tc::smem_desc(tc::smem_u32(vt_lo) + (uint32_t)j * 512u, 256u, 128u), id, j > 0);
+      const uint32_t id32 = idesc_f16(32), id16 = idesc_f16(16);
+      for (int j = 0; j < NIT; ++j) {
+        const uint64_t b = tc::smem_desc(tc::smem_u32(vt) + (uint32_t)j * 1024u, 512u, 128u);
+        const uint32_t a = tmem_base + 32u + 16u * j;
+        tc::mma_f16_ts(tmem_base, a, b, id32, j > 0);
+        tc::mma_f16_ts(tmem_base + 16u, a + 8u, b, id16, true);
+      }
       tc::mma_commit(bar);
     }
     tc::mbar_wait(bar, parity);
     parity ^= 1u;
     tc::fence_after_sync();
-    {
-      uint32_t ro[16];
-      tc::tmem_ld16(o_cols, ro);
+    if (part == 0) {
+      uint32_t big[16], small[16];
+      tc::tmem_ld16(o_cols, big);
+      tc::tmem_ld16(o_cols + 16u, small);
       tc::wait_ld();
       if (valid) {
+        const float sum = ps[0][row] + ps[1][row];
         const float inv = 1.0f / sum;
         float* op = p.o + ((long long)r * p.Lq + l) * d + h * HS;
 #pragma unroll
         for (int c = 0; c < HS; c += 4)
-          *reinterpret_cast<float4*>(op + c) = make_float4(__uint_as_float(ro[c]) * inv, __uint_as_float(ro[c + 1]) * inv,
-                                                           __uint_as_float(ro[c + 2]) * inv, __uint_as_float(ro[c + 3]) * inv);
+          *reinterpret_cast<float4*>(op + c) =
+              make_float4((__uint_as_float(small[c]) + __uint_as_float(big[c])) * inv, (__uint_as_float(small[c + 1]) + __uint_as_float(big[c + 1])) * inv,
+                          (__uint_as_float(small[c + 2]) + __uint_as_float(big[c + 2])) * inv, (__uint_as_float(small[c + 3]) + __uint_as_float(big[c + 3])) * inv);
         if (p.lse) p.lse[(long long)rh * p.Lq + l] = m + log2f(sum);
       }
     }
@@ -279,33 +314,11 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)acc) : "memory");
 }
 
-// Combined T-form of mult * X^T: rows 0..15 = hi parts, rows 16..31 = lo parts (a B operand with N = 32 that yields
-// [A hi(X)^T | A lo(X)^T] in one MMA; its first 16 rows alone are the N = 16 operand hi(X)^T):
-// elem(c', s) at (s/8)*512 + c'*16 + (s%8)*2.
-__device__ __forceinline__ void stage_tform32(const float* __restrict__ src, long long stride, int n, int NP, float mult,
-                                              unsigned char* dst) {
-  for (int i = threadIdx.x; i < NP * 2; i += blockDim.x) {
-    const int c = i & 15, s8 = i >> 4;
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int s = s8 * 8 + j;
-      x[j] = s < n ? src[(long long)s * stride + c] * mult : 0.0f;
-    }
-    uint4 h, l;
-    tc::split_f16x2(x[0], x[1], h.x, l.x); tc::split_f16x2(x[2], x[3], h.y, l.y);
-    tc::split_f16x2(x[4], x[5], h.z, l.z); tc::split_f16x2(x[6], x[7], h.w, l.w);
-    const uint32_t off = (uint32_t)s8 * 512u + (uint32_t)c * 16u;
-    *reinterpret_cast<uint4*>(dst + off) = h;
-    *reinterpret_cast<uint4*>(dst + off + 256u) = l;
-  }
-}
-
 struct BwdPass {
   uint32_t x_hi, x_lo, g_hi, g_lo, lbo_r;                  // row operands: N-forms in shared memory (A of the first stage)
   uint32_t yn_hi, yn_lo, ygn_hi, ygn_lo, lbo_c; int NPc;   // column operands (B of the first stage)
   uint32_t t1, t2;                                         // combined T-forms: out1 = A1 t1, out2 = dS t2 (keys as rows only)
-  const float *colL, *colD;                                // per-column lse / D
+  const float* colLD; int ncols;                           // keys as rows: (-lse, -D) per column (query); else: valid columns (keys)
 };
 
 // First stage of one chunk (columns c0 .. c0 + nc): S = X Yn^T, dP = G Ygn^T, both operands from shared memory.
@@ -348,11 +361,12 @@ __device__ __forceinline__ void bwd_second_stage(const BwdPass& a, int j0, int n
 }
 
 // One block of 128 rows against all columns, chunk by chunk.  KEYS = rows are keys (out1 = p^T dO needs p as an operand,
-// out2 = dS^T Q); else rows are queries (out1 = dS K).  rowL / rowD: this lane's lse / D (queries as rows), 0 otherwise;
-// rowL = +inf switches a padding row off.  On return the accumulators are complete (the caller reads them).
+// out2 = dS^T Q); else rows are queries (out1 = dS K).  nrowL / nrowD: minus this lane's lse / D (queries as rows; -inf
+// switches a padding row off), unused otherwise.  On return the accumulators are complete (the caller reads them).
 template <bool KEYS>
-__device__ __forceinline__ void bwd_block(const BwdPass& a, int row0, float rowL, float rowD, uint32_t tmem_base, uint32_t bar,
+__device__ __forceinline__ void bwd_block(const BwdPass& a, int row0, float nrowL, float nrowD, uint32_t tmem_base, uint32_t bar,
                                           uint32_t& parity) {
+  const float2 nrowL2 = sm::splat(nrowL), nrowD2 = sm::splat(nrowD);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int quad = warp & 3, part = warp >> 2;
   const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
@@ -374,19 +388,33 @@ __device__ __forceinline__ void bwd_block(const BwdPass& a, int row0, float rowL
       tc::tmem_ld16(lane_base + COL_S + 16u * g, rs);
       tc::tmem_ld16(lane_base + COL_P + 16u * g, rp);
       tc::wait_ld();
+      const int col0 = 16 * (g0 + g);
+      if (KEYS) {                                           // columns are queries: (-lse, -D) per column from shared memory
 #pragma unroll
-      for (int j = 0; j < 16; j += 2) {
-        const float2 cl = *reinterpret_cast<const float2*>(a.colL + 16 * (g0 + g) + j);
-        const float2 cd = *reinterpret_cast<const float2*>(a.colD + 16 * (g0 + g) + j);
-        const float p0 = ex2f((__uint_as_float(rs[j]) - rowL) - cl.x);
-        const float p1 = ex2f((__uint_as_float(rs[j + 1]) - rowL) - cl.y);
-        const float d0 = p0 * ((__uint_as_float(rp[j]) - rowD) - cd.x);
-        const float d1 = p1 * ((__uint_as_float(rp[j + 1]) - rowD) - cd.y);
-        tc::split_f16x2(d0, d1, ods[j / 2], ods[8 + j / 2]);
-        if (KEYS) tc::split_f16x2(p0, p1, op[j / 2], op[8 + j / 2]);
+        for (int j = 0; j < 16; j += 2) {
+          const float4 c = *reinterpret_cast<const float4*>(a.colLD + 2 * (col0 + j));    // (-L0, -D0, -L1, -D1)
+          const float2 x = sm::fadd2(make_float2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), make_float2(c.x, c.z));
+          const float2 pp = make_float2(ex2f(x.x), ex2f(x.y));
+          const float2 t = sm::fadd2(make_float2(__uint_as_float(rp[j]), __uint_as_float(rp[j + 1])), make_float2(c.y, c.w));
+          const float2 ds = sm::fmul2(pp, t);
+          tc::split_f16x2(ds.x, ds.y, ods[j / 2], ods[8 + j / 2]);
+          tc::split_f16x2(pp.x, pp.y, op[j / 2], op[8 + j / 2]);
+        }
+        tc::tmem_st16(lane_base + COL_S + 16u * g, ods);
+        tc::tmem_st16(lane_base + COL_P + 16u * g, op);
+      } else {                                              // columns are keys: per-lane (-lse, -D); padding keys in the last group
+        const bool ragged = col0 + 16 > a.ncols;
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float2 x = sm::fadd2(make_float2(__uint_as_float(rs[j]), __uint_as_float(rs[j + 1])), nrowL2);
+          float2 pp = make_float2(ex2f(x.x), ex2f(x.y));
+          if (ragged) { pp.x = col0 + j < a.ncols ? pp.x : 0.0f; pp.y = col0 + j + 1 < a.ncols ? pp.y : 0.0f; }
+          const float2 t = sm::fadd2(make_float2(__uint_as_float(rp[j]), __uint_as_float(rp[j + 1])), nrowD2);
+          const float2 ds = sm::fmul2(pp, t);
+          tc::split_f16x2(ds.x, ds.y, ods[j / 2], ods[8 + j / 2]);
+        }
+        tc::tmem_st16(lane_base + COL_S + 16u * g, ods);
       }
-      tc::tmem_st16(lane_base + COL_S + 16u * g, ods);
-      if (KEYS) tc::tmem_st16(lane_base + COL_P + 16u * g, op);
     }
     tc::wait_st();
     tc::fence_before_sync();
@@ -432,10 +460,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) dts_attn_tc_bwd_kernel(const D
   unsigned char* kt = take(64u * SP);
   unsigned char* qt = take(64u * LP);
   unsigned char* gt = take(64u * LP);
-  float* sL = reinterpret_cast<float*>(take(4u * LP));      // lse per query (+inf for padding)
-  float* sD = reinterpret_cast<float*>(take(4u * LP));      // D = dO . O per query, in scaled units
-  float* zL = reinterpret_cast<float*>(take(4u * SP));      // per key: 0, +inf for padding
-  float* zD = reinterpret_cast<float*>(take(4u * SP));      // zeros
+  float* sLD = reinterpret_cast<float*>(take(8u * LP));     // per query: (-lse (-inf for padding), -D in scaled units), D = dO . O
   if (tid == 0) { tc::mbar_init(tc::smem_u32(&sync.mma_bar), 1); tc::fence_mbar_init(); }
   if (warp == 0) tc::tmem_alloc<256>(tc::smem_u32(&sync.tmem_base));
 
@@ -457,10 +482,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) dts_attn_tc_bwd_kernel(const D
         amax = fmaxf(amax, fmaxf(fmaxf(fabsf(g4.x), fabsf(g4.y)), fmaxf(fabsf(g4.z), fabsf(g4.w))));
       }
     }
-    sD[i] = dsum;
-    sL[i] = i < Lq ? p.lse[(long long)rh * Lq + i] : INFINITY;
+    sLD[2 * i] = i < Lq ? -p.lse[(long long)rh * Lq + i] : -INFINITY;
+    sLD[2 * i + 1] = -dsum;
   }
-  for (int j = tid; j < SP; j += BWD_THREADS) { zL[j] = j < S ? 0.0f : INFINITY; zD[j] = 0.0f; }
   // K, V and Q do not depend on the scale of dO: stage them while the reduction's loads are in flight
   const float qs = p.scale * LOG2E;
   stage_nform(kb, p.kv_stride, S, SP, 1.0f, kn_hi, kn_lo);
@@ -482,7 +506,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) dts_attn_tc_bwd_kernel(const D
     e = max(-120, min(120, e));
   }
   const float gs = ldexpf(1.0f, e), gs_inv = ldexpf(1.0f, -e);
-  for (int i = tid; i < LP; i += BWD_THREADS) sD[i] *= gs;    // same thread wrote it
+  for (int i = tid; i < LP; i += BWD_THREADS) sLD[2 * i + 1] *= gs;    // same thread wrote it
   stage_nform(gb, d, Lq, LP, gs, gn_hi, gn_lo);
   stage_tform32(gb, d, Lq, LP, gs, gt);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -503,11 +527,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) dts_attn_tc_bwd_kernel(const D
     a.yn_hi = tc::smem_u32(kn_hi); a.yn_lo = tc::smem_u32(kn_lo); a.ygn_hi = tc::smem_u32(vn_hi); a.ygn_lo = tc::smem_u32(vn_lo);
     a.lbo_c = nform_lbo(SP); a.NPc = SP;
     a.t1 = tc::smem_u32(kt); a.t2 = 0;
-    a.colL = zL; a.colD = zD;
+    a.colLD = nullptr; a.ncols = S;
     for (int row0 = 0; row0 < Lq; row0 += 128) {
       const int i = row0 + quad * 32 + lane;
       const bool valid = i < Lq;
-      bwd_block<false>(a, row0, valid ? sL[i] : INFINITY, valid ? sD[i] : 0.0f, tmem_base, bar, parity);
+      bwd_block<false>(a, row0, valid ? sLD[2 * i] : -INFINITY, valid ? sLD[2 * i + 1] : 0.0f, tmem_base, bar, parity);
       if (part == 0) {
         uint32_t big[16], small[16];
         tc::tmem_ld16(lane_base + COL_OUT1, big);
@@ -527,7 +551,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) dts_attn_tc_bwd_kernel(const D
     a.yn_hi = tc::smem_u32(qn_hi); a.yn_lo = tc::smem_u32(qn_lo); a.ygn_hi = tc::smem_u32(gn_hi); a.ygn_lo = tc::smem_u32(gn_lo);
     a.lbo_c = nform_lbo(LP); a.NPc = LP;
     a.t1 = tc::smem_u32(gt); a.t2 = tc::smem_u32(qt);
-    a.colL = sL; a.colD = sD;
+    a.colLD = sLD; a.ncols = Lq;
     for (int row0 = 0; row0 < S; row0 += 128) {
       const int j = row0 + quad * 32 + lane;
       bwd_block<true>(a, row0, 0.0f, 0.0f, tmem_base, bar, parity);
@@ -555,7 +579,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 
 // the first-stage A operand of the last row block reads up to 128 rows past row0: keep that inside the allocation
 size_t bwd_smem_bytes(int SP, int LP) {
   return (size_t)4 * (2 * ((size_t)SP * 16 + 16)) + (size_t)4 * (2 * ((size_t)LP * 16 + 16)) + (size_t)64 * SP +
-         (size_t)2 * 64 * LP + (size_t)8 * LP + (size_t)8 * SP + 4096;
+         (size_t)2 * 64 * LP + (size_t)8 * LP + 4096;
 }
 
 }  // namespace
@@ -569,10 +593,10 @@ cudaError_t upd_launch_dts_attention_tc(const float* q, long long q_stride, cons
   DtsTcParams p = {};
   p.q = q; p.q_stride = q_stride; p.k = k; p.v = v; p.kv_stride = kv_stride; p.R = R; p.H = H; p.Lq = Lq; p.S = S;
   p.scale = scale; p.o = o; p.lse = lse;
-  const size_t smem = (size_t)2 * (2 * ((size_t)SP * 16 + 16)) + (size_t)2 * 32 * SP + (size_t)4 * SP;
+  const size_t smem = (size_t)2 * (2 * ((size_t)SP * 16 + 16)) + (size_t)64 * SP;
   cudaError_t e = cudaFuncSetAttribute(dts_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  dts_attn_tc_fwd_kernel<<<(unsigned)(R * H), 128, smem, stream>>>(p);
+  dts_attn_tc_fwd_kernel<<<(unsigned)(R * H), FWD_THREADS, smem, stream>>>(p);
   return cudaGetLastError();
 }
 
