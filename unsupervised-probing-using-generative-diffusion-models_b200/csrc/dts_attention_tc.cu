@@ -6,30 +6,38 @@
 // chain of tcgen05.mma with fp32 accumulation in TMEM on error-compensated fp16 hi/lo operands (hi*hi + lo*hi + hi*lo,
 // ~22 mantissa bits per factor -- the same encoding as the fused sampler and fx_attention.cu).  One CTA per (row, head).
 //
-// FORWARD (128 threads, thread i = query i of a block of 128 = TMEM lane i, two CTAs per SM):
-//   S = Q K^T (3 MMAs, N = keys padded to 16) -> row max / ex2 / row sum inside the thread's TMEM lane -> un-normalised
-//   P re-encoded IN PLACE as the A operand of O = P V (3 MMAs per 16 keys, N = 16) -> O / sum and the base-2
+// FORWARD (256 threads = two warps per TMEM lane quadrant, two CTAs per SM; thread (quadrant, lane) = query row of a block of
+// 128, the two warps of a quadrant take alternate groups of 16 keys):
+//   S = Q K^T (3 MMAs, N = keys padded to 16) -> partial row max, exchanged through shared memory -> 2^(s - max) and
+//   partial row sums; un-normalised P re-encoded IN PLACE as the A operand of O = P V -> O / sum and the base-2
 //   log-sum-exp (saved for the backward) to global memory.
 //
-// BACKWARD (512 threads = 4 warps per TMEM lane quadrant, one CTA per SM).  Like the FFMA kernel it replaces
-// (dts_attention.cu) it never reduces across rows: probabilities are recomputed once with queries as rows (dQ) and once
-// with keys as rows (dK, dV), so every output row is private to one TMEM lane.  A pass over a block of 128 rows:
-//     S  = X  Yn^T     (X = scaled Q | K rows,  Yn = K | scaled Q of all columns)      3 MMAs, N = columns
-//     dP = G  Ygn^T    (G = dO | V rows,        Ygn = V | dO)                          3 MMAs
-//     p  = ex2(S - lse_query),  dS = p (dP - D_query)          16 warps, each a quarter of the 16-column groups,
-//                                                              dS (and p) re-encoded in place as fp16 hi/lo A operands
-//     query rows:  dQ = dS K            key rows:  dV = p^T dO,  dK = dS^T Q           3 MMAs per 16 columns, N = 16
+// BACKWARD (256 threads, two CTAs per SM).  Like the FFMA kernel it replaces (dts_attention.cu) it never reduces across
+// rows: probabilities are recomputed once with queries as rows (dQ) and once with keys as rows (dK, dV), so every output
+// row is private to one TMEM lane.  A pass over a block of 128 rows walks the columns in chunks of <= 96 (TMEM: 64
+// accumulator columns + 2 x 96 = 256 per CTA, so that two heads are in flight per SM and one CTA's elementwise phase
+// overlaps the other's MMAs):
+//     S  = X  Yn^T     (X = scaled Q | K rows,  Yn = K | scaled Q of the chunk's columns)   3 MMAs, both operands in
+//     dP = G  Ygn^T    (G = dO | V rows,        Ygn = V | dO)                               3 MMAs  shared memory
+//     p  = 2^(S - lse_query),  dS = p (dP - D_query)      packed fp32x2 math; dS (and p) re-encoded in place as fp16
+//                                                         hi/lo A operands
+//     query rows:  dQ += dS K          key rows:  dV += p^T dO,  dK += dS^T Q               2 MMAs per 16 columns and output
 //   (lse, D = dO.O per query: per-lane scalars when queries are rows, broadcast from shared memory when they are
 //   columns.)  dO is tiny (1e-6 in the refinement loop, below fp16's normal range), and every gradient is linear in it:
 //   the CTA scales its dO tile by a power of two so that max|dO| lands in [4, 8) and un-scales the three outputs.
 //
+// Small-N MMAs.  The contractions over keys / queries have N = 16 outputs; a tcgen05.mma costs ~50 clk however small N is
+// (measured: 39 N = 16 MMAs per 2000 clk, with dependent and with independent accumulators alike), so the hi*hi and hi*lo
+// passes share ONE N = 32 instruction on a combined [hi | lo] operand and only lo*hi needs its own: 2 instead of 3.
+//
 // Operand forms in shared memory (K-major, no swizzle, core matrix = 8 rows x 16 bytes):
-//   N-form of X [n x 16]  (B operand with N = n, K = 16):  elem(s, c) at (c/8)*LBO + s*16 + (c%8)*2, LBO = NP*16 + 16
-//                          (the 16 spare bytes spread a quarter-warp's stores over the banks); one row = the two 16-byte
-//                          words groups a TMEM A operand row needs, so row operands are copied from it
-//   T-form of X^T [16 x n] (B operand with N = 16, K = n):  elem(c, s) at (s/8)*256 + c*16 + (s%8)*2
-// Limits: keys S <= 224 (forward), S and Lq <= 224 (backward: TMEM holds S and dP side by side); beyond that the host
-// entry points run the FFMA kernels of dts_attention.cu.
+//   N-form of X [n x 16]  (B operand with N = n, K = 16; also the A operand of a 128-row block):
+//                          elem(s, c) at (c/8)*LBO + s*16 + (c%8)*2, LBO = NP*16 + 16 (the 16 spare bytes spread a
+//                          quarter-warp's stores over the banks)
+//   combined T-form of X^T [32 x n] (B operand with N = 32 | 16, K = n): rows 0..15 hi, rows 16..31 lo,
+//                          elem(c', s) at (s/8)*512 + c'*16 + (s%8)*2
+// Limits: keys S <= 224 (forward), S and Lq <= 224 (backward); beyond that the host entry points run the FFMA kernels of
+// dts_attention.cu.
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -73,59 +81,72 @@ __device__ __forceinline__ float ex2f(float x) {
 __device__ __forceinline__ uint32_t nform_lbo(int NP) { return (uint32_t)NP * 16u + 16u; }
 __device__ __forceinline__ uint32_t nform_bytes(int NP) { return 2u * nform_lbo(NP); }
 
-// N-form of mult * X[n x 16] (rows >= n are zero), hi and lo parts.
-__device__ __forceinline__ void stage_nform(const float* __restrict__ src, long long stride, int n, int NP, float mult,
-                                            unsigned char* hi, unsigned char* lo) {
-  const uint32_t LBO = nform_lbo(NP);
-  for (int i = threadIdx.x; i < NP * 2; i += blockDim.x) {
-    const int s = i >> 1, c8 = i & 1;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-    if (s < n) {
-      a = *reinterpret_cast<const float4*>(src + (long long)s * stride + c8 * 8);
-      b = *reinterpret_cast<const float4*>(src + (long long)s * stride + c8 * 8 + 4);
+// Staging is split into a LOAD half (all global loads of a phase are issued before any is consumed: a CTA pays one
+// memory round trip per phase, not one per loop iteration -- the first version spent a third of the backward kernel in
+// long-scoreboard stalls) and a STORE half (convert, write the operand form).  Both kernels run 256 threads and
+// NP <= 224, so a thread has at most two tasks per matrix.
+constexpr int STG_THREADS = 256, STG_TASKS = 2;
+
+// N-form tasks: (row s, 8 consecutive channels c8) -> one 16-byte core-matrix row each for hi and lo.
+struct NTasks { float4 a[STG_TASKS], b[STG_TASKS]; };
+__device__ __forceinline__ void load_ntasks(const float* __restrict__ src, long long stride, int n, int NP, NTasks& t) {
+#pragma unroll
+  for (int u = 0; u < STG_TASKS; ++u) {
+    const int i = threadIdx.x + u * STG_THREADS, s = i >> 1, c8 = i & 1;
+    t.a[u] = t.b[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < NP * 2 && s < n) {
+      t.a[u] = *reinterpret_cast<const float4*>(src + (long long)s * stride + c8 * 8);
+      t.b[u] = *reinterpret_cast<const float4*>(src + (long long)s * stride + c8 * 8 + 4);
     }
-    uint4 h, l;
-    tc::split_f16x2(a.x * mult, a.y * mult, h.x, l.x); tc::split_f16x2(a.z * mult, a.w * mult, h.y, l.y);
-    tc::split_f16x2(b.x * mult, b.y * mult, h.z, l.z); tc::split_f16x2(b.z * mult, b.w * mult, h.w, l.w);
-    const uint32_t off = (uint32_t)c8 * LBO + (uint32_t)s * 16u;
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+}
+// N-form of mult * X[n x 16] (rows >= n are zero), hi and lo parts.
+__device__ __forceinline__ void store_nform(const NTasks& t, int NP, float mult, unsigned char* hi, unsigned char* lo) {
+  const uint32_t LBO = nform_lbo(NP);
+#pragma unroll
+  for (int u = 0; u < STG_TASKS; ++u) {
+    const int i = threadIdx.x + u * STG_THREADS, s = i >> 1, c8 = i & 1;
+    if (i < NP * 2) {
+      const float4 a = t.a[u], b = t.b[u];
+      uint4 h, l;
+      tc::split_f16x2(a.x * mult, a.y * mult, h.x, l.x); tc::split_f16x2(a.z * mult, a.w * mult, h.y, l.y);
+      tc::split_f16x2(b.x * mult, b.y * mult, h.z, l.z); tc::split_f16x2(b.z * mult, b.w * mult, h.w, l.w);
+      const uint32_t off = (uint32_t)c8 * LBO + (uint32_t)s * 16u;
+      *reinterpret_cast<uint4*>(hi + off) = h;
+      *reinterpret_cast<uint4*>(lo + off) = l;
+    }
   }
 }
 
-// T-form of mult * X^T [16 x n] (columns >= n are zero).
-__device__ __forceinline__ void stage_tform(const float* __restrict__ src, long long stride, int n, int NP, float mult,
-                                            unsigned char* hi, unsigned char* lo) {
-  for (int i = threadIdx.x; i < NP * 2; i += blockDim.x) {
-    const int c = i & 15, s8 = i >> 4;
-    float x[8];
+// T-form tasks: (channel c, 8 consecutive rows s8) -> one 16-byte row of X^T each for hi and lo.
+struct TTasks { float x[STG_TASKS][8]; };
+__device__ __forceinline__ void load_ttasks(const float* __restrict__ src, long long stride, int n, int NP, TTasks& t) {
+#pragma unroll
+  for (int u = 0; u < STG_TASKS; ++u) {
+    const int i = threadIdx.x + u * STG_THREADS, c = i & 15, s8 = i >> 4;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int s = s8 * 8 + j;
-      x[j] = s < n ? src[(long long)s * stride + c] * mult : 0.0f;
+      t.x[u][j] = (i < NP * 2 && s < n) ? src[(long long)s * stride + c] : 0.0f;
     }
-    uint4 h, l;
-    tc::split_f16x2(x[0], x[1], h.x, l.x); tc::split_f16x2(x[2], x[3], h.y, l.y);
-    tc::split_f16x2(x[4], x[5], h.z, l.z); tc::split_f16x2(x[6], x[7], h.w, l.w);
-    const uint32_t off = (uint32_t)s8 * 256u + (uint32_t)c * 16u;
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    *reinterpret_cast<uint4*>(lo + off) = l;
   }
 }
-
-// Row r of an N-form -> the 16 TMEM words of an A operand K-slice (hi words 0..7, lo words 8..15); zeros past NP.
-__device__ __forceinline__ void row_operand(const unsigned char* hi, const unsigned char* lo, int NP, int r, uint32_t (&o)[16]) {
-  if (r < NP) {
-    const uint32_t LBO = nform_lbo(NP);
-    const uint4 h0 = *reinterpret_cast<const uint4*>(hi + (uint32_t)r * 16u);
-    const uint4 h1 = *reinterpret_cast<const uint4*>(hi + LBO + (uint32_t)r * 16u);
-    const uint4 l0 = *reinterpret_cast<const uint4*>(lo + (uint32_t)r * 16u);
-    const uint4 l1 = *reinterpret_cast<const uint4*>(lo + LBO + (uint32_t)r * 16u);
-    o[0] = h0.x; o[1] = h0.y; o[2] = h0.z; o[3] = h0.w; o[4] = h1.x; o[5] = h1.y; o[6] = h1.z; o[7] = h1.w;
-    o[8] = l0.x; o[9] = l0.y; o[10] = l0.z; o[11] = l0.w; o[12] = l1.x; o[13] = l1.y; o[14] = l1.z; o[15] = l1.w;
-  } else {
+// Combined T-form of mult * X^T: rows 0..15 = hi parts, rows 16..31 = lo parts (a B operand with N = 32 that yields
+// [A hi(X)^T | A lo(X)^T] in one MMA; its first 16 rows alone are the N = 16 operand hi(X)^T):
+// elem(c', s) at (s/8)*512 + c'*16 + (s%8)*2.
+__device__ __forceinline__ void store_tform32(const TTasks& t, int NP, float mult, unsigned char* dst) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) o[j] = 0u;
+  for (int u = 0; u < STG_TASKS; ++u) {
+    const int i = threadIdx.x + u * STG_THREADS, c = i & 15, s8 = i >> 4;
+    if (i < NP * 2) {
+      const float* x = t.x[u];
+      uint4 h, l;
+      tc::split_f16x2(x[0] * mult, x[1] * mult, h.x, l.x); tc::split_f16x2(x[2] * mult, x[3] * mult, h.y, l.y);
+      tc::split_f16x2(x[4] * mult, x[5] * mult, h.z, l.z); tc::split_f16x2(x[6] * mult, x[7] * mult, h.w, l.w);
+      const uint32_t off = (uint32_t)s8 * 512u + (uint32_t)c * 16u;
+      *reinterpret_cast<uint4*>(dst + off) = h;
+      *reinterpret_cast<uint4*>(dst + off + 256u) = l;
+    }
   }
 }
 
@@ -138,28 +159,6 @@ __device__ __forceinline__ void mma3(uint32_t d, uint32_t a, uint64_t b_hi, uint
 
 // ================================================ forward ==============================================================
 constexpr int FWD_THREADS = 256;                           // two warps per TMEM lane quadrant (each half of the key groups)
-
-// Combined T-form of mult * X^T: rows 0..15 = hi parts, rows 16..31 = lo parts (a B operand with N = 32 that yields
-// [A hi(X)^T | A lo(X)^T] in one MMA; its first 16 rows alone are the N = 16 operand hi(X)^T):
-// elem(c', s) at (s/8)*512 + c'*16 + (s%8)*2.
-__device__ __forceinline__ void stage_tform32(const float* __restrict__ src, long long stride, int n, int NP, float mult,
-                                              unsigned char* dst) {
-  for (int i = threadIdx.x; i < NP * 2; i += blockDim.x) {
-    const int c = i & 15, s8 = i >> 4;
-    float x[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int s = s8 * 8 + j;
-      x[j] = s < n ? src[(long long)s * stride + c] * mult : 0.0f;
-    }
-    uint4 h, l;
-    tc::split_f16x2(x[0], x[1], h.x, l.x); tc::split_f16x2(x[2], x[3], h.y, l.y);
-    tc::split_f16x2(x[4], x[5], h.z, l.z); tc::split_f16x2(x[6], x[7], h.w, l.w);
-    const uint32_t off = (uint32_t)s8 * 512u + (uint32_t)c * 16u;
-    *reinterpret_cast<uint4*>(dst + off) = h;
-    *reinterpret_cast<uint4*>(dst + off + 256u) = l;
-  }
-}
 
 __global__ void __launch_bounds__(FWD_THREADS, 2) dts_attn_tc_fwd_kernel(const DtsTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -176,8 +175,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) dts_attn_tc_fwd_kernel(const D
   if (warp == 0) tc::tmem_alloc<256>(tc::smem_u32(&sync.tmem_base));
   const float* kb = p.k + (long long)r * S * p.kv_stride + h * HS;
   const float* vb = p.v + (long long)r * S * p.kv_stride + h * HS;
-  stage_nform(kb, p.kv_stride, S, SP, 1.0f, k_hi, k_lo);
-  stage_tform32(vb, p.kv_stride, S, SP, 1.0f, vt);
+  {
+    NTasks tk;
+    TTasks tv;
+    load_ntasks(kb, p.kv_stride, S, SP, tk);
+    load_ttasks(vb, p.kv_stride, S, SP, tv);
+    store_nform(tk, SP, 1.0f, k_hi, k_lo);
+    store_tform32(tv, SP, 1.0f, vt);
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
   tc::fence_before_sync();
   __syncthreads();
@@ -469,46 +474,71 @@ __global__ void __launch_bounds__(BWD_THREADS, 2) dts_attn_tc_bwd_kernel(const D
   const float* vb = p.v + (long long)r * S * p.kv_stride + h * HS;
   const float* gb = p.d_o + (long long)r * Lq * d + h * HS;
   const float* ob = p.o + (long long)r * Lq * d + h * HS;
-  // ---- D = dO . O per query and max |dO| of the tile ----
-  float amax = 0.0f;
-  for (int i = tid; i < LP; i += BWD_THREADS) {
-    float dsum = 0.0f;
-    if (i < Lq) {
-#pragma unroll
-      for (int c = 0; c < HS; c += 4) {
-        const float4 g4 = *reinterpret_cast<const float4*>(gb + (long long)i * d + c);
-        const float4 o4 = *reinterpret_cast<const float4*>(ob + (long long)i * d + c);
-        dsum = fmaf(g4.x, o4.x, dsum); dsum = fmaf(g4.y, o4.y, dsum); dsum = fmaf(g4.z, o4.z, dsum); dsum = fmaf(g4.w, o4.w, dsum);
-        amax = fmaxf(amax, fmaxf(fmaxf(fabsf(g4.x), fabsf(g4.y)), fmaxf(fabsf(g4.z), fabsf(g4.w))));
-      }
-    }
-    sLD[2 * i] = i < Lq ? -p.lse[(long long)rh * Lq + i] : -INFINITY;
-    sLD[2 * i + 1] = -dsum;
-  }
-  // K, V and Q do not depend on the scale of dO: stage them while the reduction's loads are in flight
+  float gs, gs_inv;
   const float qs = p.scale * LOG2E;
-  stage_nform(kb, p.kv_stride, S, SP, 1.0f, kn_hi, kn_lo);
-  stage_nform(vb, p.kv_stride, S, SP, 1.0f, vn_hi, vn_lo);
-  stage_nform(qb, p.q_stride, Lq, LP, qs, qn_hi, qn_lo);
-  stage_tform32(kb, p.kv_stride, S, SP, 1.0f, kt);
-  stage_tform32(qb, p.q_stride, Lq, LP, qs, qt);
+  float amax = 0.0f;
+  {
+    // phase 1: every element of K, V, Q, dO, O once (N-form tasks), all loads in flight together
+    NTasks tk, tv, tq, tg, to;
+    load_ntasks(kb, p.kv_stride, S, SP, tk);
+    load_ntasks(vb, p.kv_stride, S, SP, tv);
+    load_ntasks(qb, p.q_stride, Lq, LP, tq);
+    load_ntasks(gb, d, Lq, LP, tg);
+    load_ntasks(ob, d, Lq, LP, to);
+    float lse_u[STG_TASKS];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-  if (lane == 0) red[warp] = amax;
-  __syncthreads();
-  amax = red[0];
+    for (int u = 0; u < STG_TASKS; ++u) {
+      const int i = (tid + u * STG_THREADS) >> 1;
+      lse_u[u] = i < Lq ? p.lse[(long long)rh * Lq + i] : INFINITY;
+    }
+    store_nform(tk, SP, 1.0f, kn_hi, kn_lo);
+    store_nform(tv, SP, 1.0f, vn_hi, vn_lo);
+    store_nform(tq, LP, qs, qn_hi, qn_lo);
+    // D = dO . O per query (a row = two tasks of neighbouring lanes) and max |dO| of the tile
 #pragma unroll
-  for (int w = 1; w < BWD_THREADS / 32; ++w) amax = fmaxf(amax, red[w]);
-  // power of two that brings max|dO| into [4, 8); 1 for an all-zero (or non-finite) tile
-  int e = 0;
-  if (amax > 0.0f && amax < INFINITY) {
-    e = 2 - ilogbf(amax);
-    e = max(-120, min(120, e));
+    for (int u = 0; u < STG_TASKS; ++u) {
+      const float4 ga = tg.a[u], gb4 = tg.b[u], oa = to.a[u], ob4 = to.b[u];
+      float dsum = ga.x * oa.x;
+      dsum = fmaf(ga.y, oa.y, dsum); dsum = fmaf(ga.z, oa.z, dsum); dsum = fmaf(ga.w, oa.w, dsum);
+      dsum = fmaf(gb4.x, ob4.x, dsum); dsum = fmaf(gb4.y, ob4.y, dsum); dsum = fmaf(gb4.z, ob4.z, dsum); dsum = fmaf(gb4.w, ob4.w, dsum);
+      dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+      amax = fmaxf(amax, fmaxf(fmaxf(fmaxf(fabsf(ga.x), fabsf(ga.y)), fmaxf(fabsf(ga.z), fabsf(ga.w))),
+                               fmaxf(fmaxf(fabsf(gb4.x), fabsf(gb4.y)), fmaxf(fabsf(gb4.z), fabsf(gb4.w)))));
+      const int t = tid + u * STG_THREADS, i = t >> 1;
+      if (t < LP * 2 && (t & 1) == 0) { sLD[2 * i] = -lse_u[u]; sLD[2 * i + 1] = -dsum; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0) red[warp] = amax;
+    __syncthreads();
+    amax = red[0];
+#pragma unroll
+    for (int w = 1; w < BWD_THREADS / 32; ++w) amax = fmaxf(amax, red[w]);
+    // power of two that brings max|dO| into [4, 8); 1 for an all-zero (or non-finite) tile
+    int e = 0;
+    if (amax > 0.0f && amax < INFINITY) {
+      e = 2 - ilogbf(amax);
+      e = max(-120, min(120, e));
+    }
+    gs = ldexpf(1.0f, e);
+    gs_inv = ldexpf(1.0f, -e);
+    store_nform(tg, LP, gs, gn_hi, gn_lo);
+#pragma unroll
+    for (int u = 0; u < STG_TASKS; ++u) {
+      const int t = tid + u * STG_THREADS;
+      if (t < LP * 2 && (t & 1) == 0) sLD[2 * (t >> 1) + 1] *= gs;          // same thread wrote it
+    }
   }
-  const float gs = ldexpf(1.0f, e), gs_inv = ldexpf(1.0f, -e);
-  for (int i = tid; i < LP; i += BWD_THREADS) sLD[2 * i + 1] *= gs;    // same thread wrote it
-  stage_nform(gb, d, Lq, LP, gs, gn_hi, gn_lo);
-  stage_tform32(gb, d, Lq, LP, gs, gt);
+  {
+    // phase 2: the transposed forms (the tiles were just read: L1 / L2 hits)
+    TTasks xk, xq, xg;
+    load_ttasks(kb, p.kv_stride, S, SP, xk);
+    load_ttasks(qb, p.q_stride, Lq, LP, xq);
+    load_ttasks(gb, d, Lq, LP, xg);
+    store_tform32(xk, SP, 1.0f, kt);
+    store_tform32(xq, LP, qs, qt);
+    store_tform32(xg, LP, gs, gt);
+  }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   tc::fence_before_sync();
   __syncthreads();
