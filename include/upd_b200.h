@@ -230,9 +230,12 @@ int upd_dts_fourier_topk_bwd(const float* gseason_dev, const int* idx_dev, long 
  *   (diffusionts_transformer.py:215, 287) forward and input-gradient backward: y = LayerNorm(x) * gamma + beta over the
  *   last axis (eps 1e-5); gamma_dev / beta_dev [D] (AdaLN: 1 + scale[t] and shift[t], the step is shared by all rows).
  *   stats_dev [rows, 2] = (mean, rstd), written by the forward (may be NULL) and read by the backward, which returns
- *   dx only (the weights are constants during sampling).  D in {32,64,96,128,192,256,384,512,1024}. */
+ *   dx only (the weights are constants during sampling).  D in {32,64,96,128,192,256,384,512,1024}.
+ *   a3_dev (may be NULL): additionally emit the fp16 split operand [rows, 3D + 8] = [hi | lo | hi | 1 1 0..] that upd_gemm3
+ *   consumes, so that a dense layer reading y needs no separate upd_fx_split pass; y_dev may then be NULL (the fp32 y is
+ *   not written at all).  With a3_dev: D a multiple of 64 in {64,...,512,1024}. */
 int upd_dts_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, long long rows, int D,
-                      float* y_dev, float* stats_dev, void* stream);
+                      float* y_dev, float* stats_dev, void* a3_dev, void* stream);
 int upd_dts_layernorm_bwd(const float* x_dev, const float* dy_dev, const float* gamma_dev, const float* stats_dev,
                           long long rows, int D, float* dx_dev, void* stream);
 
@@ -246,10 +249,11 @@ int upd_dts_layernorm_bwd(const float* x_dev, const float* dy_dev, const float* 
  *   scales each (row, head) tile of do_dev by a power of two, so cotangents of any magnitude keep fp32-grade accuracy)
  *   for S <= 224 (forward) / S, Lq <= 224 (backward); longer sequences run the fp32 FFMA kernels (csrc/dts_attention.cu;
  *   also with the environment variable UPD_DTS_ATTN_FFMA=1).
+ *   a3_dev (forward, may be NULL): additionally emit the split operand [R*Lq, 3*H*16 + 8] of the out-projection GEMM.
  *   Limits: head_dim == 16; (S + Lq) * 136 bytes of shared memory on the FFMA path. */
 int upd_dts_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
                       long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale, float* o_dev,
-                      float* lse_dev, void* stream);
+                      float* lse_dev, void* a3_dev, void* stream);
 int upd_dts_attention_bwd(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
                           long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale,
                           const float* o_dev, const float* lse_dev, const float* do_dev, float* dq_dev,

@@ -16,7 +16,7 @@ SYMBOLS = (
     "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_dts_attention", "upd_dts_attention_bwd", "upd_dts_layernorm", "upd_dts_layernorm_bwd", "upd_stg_posterior", "upd_nsx_step", "upd_stg_gated_aggregate", "upd_stg_tcn_ln", "upd_stg_tcn_ln_cat", "upd_fx_split", "upd_gemm3", "upd_fx_add_ln_split", "upd_fx_attention", "upd_fx_attention_hs16", "upd_fx_embed_split",
 )
 
-ABI_VERSION = 6     # = UPD_ABI_VERSION of the csrc/ this binding was written against (argument lists below)
+ABI_VERSION = 7     # = UPD_ABI_VERSION of the csrc/ this binding was written against (argument lists below)
 KIND_NSDIFF, KIND_TMDM = 0, 1
 IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X2, IMPL_TCGEN05_WS = 0, 1, 2, 4
 _fp = ctypes.POINTER(ctypes.c_float)
@@ -84,11 +84,11 @@ def lib():
     L.upd_dts_fourier_topk_bwd.restype = ctypes.c_int
     L.upd_dts_fourier_topk_bwd.argtypes = [vp, vp, ll, ll, i, i, i, i, i, vp, vp]
     L.upd_dts_layernorm.restype = ctypes.c_int
-    L.upd_dts_layernorm.argtypes = [vp, vp, vp, ll, i, vp, vp, vp]
+    L.upd_dts_layernorm.argtypes = [vp, vp, vp, ll, i, vp, vp, vp, vp]
     L.upd_dts_layernorm_bwd.restype = ctypes.c_int
     L.upd_dts_layernorm_bwd.argtypes = [vp, vp, vp, vp, ll, i, vp, vp]
     L.upd_dts_attention.restype = ctypes.c_int
-    L.upd_dts_attention.argtypes = [vp, ll, vp, vp, ll, i, i, i, i, i, f32, vp, vp, vp]
+    L.upd_dts_attention.argtypes = [vp, ll, vp, vp, ll, i, i, i, i, i, f32, vp, vp, vp, vp]
     L.upd_dts_attention_bwd.restype = ctypes.c_int
     L.upd_dts_attention_bwd.argtypes = [vp, ll, vp, vp, ll, i, i, i, i, i, f32, vp, vp, vp, vp, ll, vp, vp, ll, vp]
     L.upd_nsx_step.restype = ctypes.c_int

@@ -56,7 +56,8 @@ cudaError_t upd_launch_dts_attention_bwd(const float* q, long long q_stride, con
                                          const float* lse, const float* d_o, float* dq, long long dq_stride, float* dk,
                                          float* dv, long long dkv_stride, cudaStream_t stream);
 cudaError_t upd_launch_dts_attention_tc(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
-                                        int R, int H, int Lq, int S, float scale, float* o, float* lse, cudaStream_t stream);
+                                        int R, int H, int Lq, int S, float scale, float* o, float* lse, void* a3,
+                                        cudaStream_t stream);
 cudaError_t upd_launch_dts_attention_tc_bwd(const float* q, long long q_stride, const float* k, const float* v,
                                             long long kv_stride, int R, int H, int Lq, int S, float scale, const float* o,
                                             const float* lse, const float* d_o, float* dq, long long dq_stride, float* dk,
@@ -64,7 +65,7 @@ cudaError_t upd_launch_dts_attention_tc_bwd(const float* q, long long q_stride, 
 cudaError_t upd_launch_fx_embed_split(const float* x, const float* w, const float* pe, long long rows, int L, int NF, int K,
                                       float* y, void* a3, cudaStream_t stream);
 cudaError_t upd_launch_dts_layernorm(const float* x, const float* gamma, const float* beta, long long rows, int D, float* y,
-                                     float* stats, cudaStream_t stream);
+                                     float* stats, void* a3, cudaStream_t stream);
 cudaError_t upd_launch_dts_layernorm_bwd(const float* x, const float* dy, const float* gamma, const float* stats,
                                          long long rows, int D, float* dx, cudaStream_t stream);
 
@@ -501,17 +502,20 @@ static bool dts_attention_ffma_forced() {
 
 int upd_dts_attention(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
                       long long kv_row_stride, int R, int H, int Lq, int S, int head_dim, float scale, float* o_dev,
-                      float* lse_dev, void* stream) {
+                      float* lse_dev, void* a3_dev, void* stream) {
   if (!q_dev || !k_dev || !v_dev || !o_dev || R <= 0 || H <= 0 || Lq <= 0 || S <= 0) return UPD_ERR_BAD_ARG;
   if (head_dim != 16 || (long long)R * H > 0x7fffffffLL) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
   if (!dts_attention_ffma_forced()) {       // tcgen05 kernel; sequences beyond its limits fall through to the FFMA kernel
     cudaError_t e = upd_launch_dts_attention_tc(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev,
-                                                lse_dev, (cudaStream_t)stream);
+                                                lse_dev, a3_dev, (cudaStream_t)stream);
     if (e != cudaErrorInvalidValue) UPD_FINISH(e);
   }
-  UPD_FINISH(upd_launch_dts_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev, lse_dev,
-                                      nullptr, nullptr, 0, 0, (cudaStream_t)stream));
+  cudaError_t e = upd_launch_dts_attention(q_dev, q_row_stride, k_dev, v_dev, kv_row_stride, R, H, Lq, S, scale, o_dev, lse_dev,
+                                           nullptr, nullptr, 0, 0, (cudaStream_t)stream);
+  if (e == cudaSuccess && a3_dev)           // FFMA path: the out-projection's operand in a second pass
+    e = upd_launch_fx_split(o_dev, (long long)R * Lq, H * 16, 1, 1, 0, a3_dev, (cudaStream_t)stream);
+  UPD_FINISH(e);
 }
 
 int upd_fx_attention_hs16(const float* q_dev, long long q_row_stride, const float* k_dev, const float* v_dev,
@@ -552,10 +556,10 @@ int upd_fx_embed_split(const float* x_dev, const float* w_dev, const float* pe_d
 }
 
 int upd_dts_layernorm(const float* x_dev, const float* gamma_dev, const float* beta_dev, long long rows, int D,
-                      float* y_dev, float* stats_dev, void* stream) {
-  if (!x_dev || !gamma_dev || !beta_dev || !y_dev || rows <= 0) return UPD_ERR_BAD_ARG;
+                      float* y_dev, float* stats_dev, void* a3_dev, void* stream) {
+  if (!x_dev || !gamma_dev || !beta_dev || (!y_dev && !a3_dev) || rows <= 0) return UPD_ERR_BAD_ARG;
   UPD_DEVICE_OR_RETURN();
-  UPD_FINISH(upd_launch_dts_layernorm(x_dev, gamma_dev, beta_dev, rows, D, y_dev, stats_dev, (cudaStream_t)stream));
+  UPD_FINISH(upd_launch_dts_layernorm(x_dev, gamma_dev, beta_dev, rows, D, y_dev, stats_dev, a3_dev, (cudaStream_t)stream));
 }
 
 int upd_dts_layernorm_bwd(const float* x_dev, const float* dy_dev, const float* gamma_dev, const float* stats_dev,

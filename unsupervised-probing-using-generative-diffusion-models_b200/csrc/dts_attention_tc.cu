@@ -65,6 +65,7 @@ struct DtsTcParams {
   float scale;
   float* o;                                 // [R*Lq, H*16]
   float* lse;                               // [R*H, Lq] base-2 log-sum-exp of the scaled scores (may be null in the forward)
+  __half* a3;                               // forward, optional: split operand [R*Lq, 3*H*16 + 8] of the out-projection
   const float* d_o;                         // [R*Lq, H*16]
   float* dq; long long dq_stride;
   float* dk; float* dv; long long dkv_stride;
@@ -296,6 +297,20 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) dts_attn_tc_fwd_kernel(const D
               make_float4((__uint_as_float(small[c]) + __uint_as_float(big[c])) * inv, (__uint_as_float(small[c + 1]) + __uint_as_float(big[c + 1])) * inv,
                           (__uint_as_float(small[c + 2]) + __uint_as_float(big[c + 2])) * inv, (__uint_as_float(small[c + 3]) + __uint_as_float(big[c + 3])) * inv);
         if (p.lse) p.lse[(long long)rh * p.Lq + l] = m + log2f(sum);
+        if (p.a3) {                                          // the out-projection's operand, heads merged
+          __half* arow = p.a3 + ((long long)r * p.Lq + l) * (3 * d + 8) + h * HS;
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int c = 0; c < HS; c += 2)
+            tc::split_f16x2((__uint_as_float(small[c]) + __uint_as_float(big[c])) * inv,
+                            (__uint_as_float(small[c + 1]) + __uint_as_float(big[c + 1])) * inv, hi[c / 2], lo[c / 2]);
+          const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+          reinterpret_cast<uint4*>(arow)[0] = h0; reinterpret_cast<uint4*>(arow)[1] = h1;
+          reinterpret_cast<uint4*>(arow + d)[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          reinterpret_cast<uint4*>(arow + d)[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+          reinterpret_cast<uint4*>(arow + 2 * d)[0] = h0; reinterpret_cast<uint4*>(arow + 2 * d)[1] = h1;
+          if (h == 0) *reinterpret_cast<uint4*>(arow + 3 * d) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
+        }
       }
     }
     tc::fence_before_sync();                                 // this block's TMEM reads precede the next block's writes
@@ -616,13 +631,15 @@ size_t bwd_smem_bytes(int SP, int LP) {
 
 // cudaErrorInvalidValue = shape outside the tensor-core kernels' limits (the caller runs the FFMA kernels instead).
 cudaError_t upd_launch_dts_attention_tc(const float* q, long long q_stride, const float* k, const float* v, long long kv_stride,
-                                        int R, int H, int Lq, int S, float scale, float* o, float* lse, cudaStream_t stream) {
+                                        int R, int H, int Lq, int S, float scale, float* o, float* lse, void* a3,
+                                        cudaStream_t stream) {
   const int SP = (S + 15) & ~15;
+  if (a3 && (((H * HS) & 7) || !aligned16(a3))) return cudaErrorInvalidValue;
   if (SP > MAX_NP || (q_stride & 3) || (kv_stride & 3) || !aligned16(q) || !aligned16(k) || !aligned16(v) || !aligned16(o))
     return cudaErrorInvalidValue;
   DtsTcParams p = {};
   p.q = q; p.q_stride = q_stride; p.k = k; p.v = v; p.kv_stride = kv_stride; p.R = R; p.H = H; p.Lq = Lq; p.S = S;
-  p.scale = scale; p.o = o; p.lse = lse;
+  p.scale = scale; p.o = o; p.lse = lse; p.a3 = reinterpret_cast<__half*>(a3);
   const size_t smem = (size_t)2 * (2 * ((size_t)SP * 16 + 16)) + (size_t)64 * SP;
   cudaError_t e = cudaFuncSetAttribute(dts_attn_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

@@ -5,8 +5,11 @@
 // AdaLN modulation is a [d] vector).  The backward feeds the Langevin refinement gradient (DiffusionTS.py:384-399):
 //   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma      (weights are constants: no dgamma / dbeta)
 // One warp per row, d in {32,64,96,128,192,256,384,512,1024}; the library path was 3 launches forward and 4 backward per layer.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "tc_helpers.cuh"
 
 namespace {
 
@@ -41,6 +44,42 @@ __global__ void dts_ln_fwd_kernel(const float* __restrict__ x, const float* __re
   if (stats && lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
 }
 
+// The same forward, emitting the split operand [hi | lo | hi | 1 1 0..] (fp16, row pitch 3D + 8) of the dense layer that
+// consumes y (fx_encoder.gemm3): the fp32 y is optional -- when only a linear layer reads it, it never reaches HBM.
+// A lane owns pairs of neighbouring channels (c = 2 lane + 64 i) so that the fp16 halves are stored as 32-bit words.
+template <int NP>
+__global__ void dts_ln_fwd_a3_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     long long rows, int D, float* __restrict__ y, float* __restrict__ stats,
+                                     __half* __restrict__ a3) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float2 v[NP];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { v[i] = *reinterpret_cast<const float2*>(x + r * D + 2 * lane + 64 * i); s += v[i].x + v[i].y; }
+  const float mean = warp_sum(s) / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NP; ++i) { const float d0 = v[i].x - mean, d1 = v[i].y - mean; q = fmaf(d0, d0, q); q = fmaf(d1, d1, q); }
+  const float rstd = rsqrtf(warp_sum(q) / D + 1e-5f);
+  __half* row = a3 + r * (3LL * D + 8);
+#pragma unroll
+  for (int i = 0; i < NP; ++i) {
+    const int c = 2 * lane + 64 * i;
+    const float2 g = *reinterpret_cast<const float2*>(gamma + c), b = *reinterpret_cast<const float2*>(beta + c);
+    const float o0 = fmaf((v[i].x - mean) * rstd, g.x, b.x), o1 = fmaf((v[i].y - mean) * rstd, g.y, b.y);
+    if (y) *reinterpret_cast<float2*>(y + r * D + c) = make_float2(o0, o1);
+    uint32_t hi, lo;
+    tc::split_f16x2(o0, o1, hi, lo);
+    *reinterpret_cast<uint32_t*>(row + c) = hi;
+    *reinterpret_cast<uint32_t*>(row + D + c) = lo;
+    *reinterpret_cast<uint32_t*>(row + 2 * D + c) = hi;
+  }
+  if (lane == 0) *reinterpret_cast<uint4*>(row + 3 * D) = make_uint4(0x3C003C00u, 0u, 0u, 0u);   // bias columns: 1, 1, 0 x 6
+  if (stats && lane == 0) { stats[2 * r] = mean; stats[2 * r + 1] = rstd; }
+}
+
 template <int NL>
 __global__ void dts_ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ gamma,
                                   const float* __restrict__ stats, long long rows, int D, float* __restrict__ dx) {
@@ -67,9 +106,19 @@ __global__ void dts_ln_bwd_kernel(const float* __restrict__ x, const float* __re
 }  // namespace
 
 cudaError_t upd_launch_dts_layernorm(const float* x, const float* gamma, const float* beta, long long rows, int D, float* y,
-                                     float* stats, cudaStream_t stream) {
+                                     float* stats, void* a3, cudaStream_t stream) {
   const int wpb = 8;
   const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  if (a3) {
+    switch (D) {
+#define UPD_LN(NP) case 64 * NP: dts_ln_fwd_a3_kernel<NP><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, rows, D, y, stats, (__half*)a3); break;
+      UPD_LN(1) UPD_LN(2) UPD_LN(3) UPD_LN(4) UPD_LN(6) UPD_LN(8) UPD_LN(16)
+#undef UPD_LN
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
+  if (!y) return cudaErrorInvalidValue;
   switch (D) {
 #define UPD_LN(NL) case 32 * NL: dts_ln_fwd_kernel<NL><<<grid, wpb * 32, 0, stream>>>(x, gamma, beta, rows, D, y, stats); break;
     UPD_LN(1) UPD_LN(2) UPD_LN(3) UPD_LN(4) UPD_LN(6) UPD_LN(8) UPD_LN(12) UPD_LN(16) UPD_LN(32)

@@ -173,10 +173,11 @@ class FourierTopK(torch.autograd.Function):
 class FusedAttention(torch.autograd.Function):
     """softmax(q k^T / sqrt(hs)) v on projection buffers (upd_dts_attention / _bwd).  ``qbuf`` [R, Lq, *] holds q at
     column offset ``q_off``; ``kvbuf`` [R, S, *] holds k at ``k_off`` and v at ``v_off`` (the same tensor as qbuf for
-    self-attention).  Returns [R, Lq, d] with the heads merged."""
+    self-attention).  Returns [R, Lq, d] with the heads merged -- or, with ``proj = (w3, w, n_out)``, the out-projection
+    of that: the attention kernel then emits the projection GEMM's split operand itself (no upd_fx_split pass)."""
 
     @staticmethod
-    def forward(ctx, qbuf, kvbuf, q_off, k_off, v_off, n_heads, d):
+    def forward(ctx, qbuf, kvbuf, q_off, k_off, v_off, n_heads, d, proj=None):
         qbuf, kvbuf = qbuf.contiguous(), kvbuf.contiguous()
         R, Lq, S = qbuf.shape[0], qbuf.shape[1], kvbuf.shape[1]
         hs = d // n_heads
@@ -184,22 +185,28 @@ class FusedAttention(torch.autograd.Function):
         out = torch.empty((R, Lq, d), dtype=torch.float32, device=dev)
         need = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
         lse = torch.empty((R * n_heads, Lq), dtype=torch.float32, device=dev) if need else None
+        a3 = torch.empty((R * Lq, 3 * d + 8), dtype=torch.float16, device=dev) if proj is not None else None
         scale = 1.0 / math.sqrt(hs)
         kb = kvbuf.data_ptr()
         rc = _lib.lib().upd_dts_attention(
             ctypes.c_void_p(qbuf.data_ptr() + 4 * q_off), qbuf.shape[2], ctypes.c_void_p(kb + 4 * k_off),
             ctypes.c_void_p(kb + 4 * v_off), kvbuf.shape[2], R, n_heads, Lq, S, hs, scale, _lib.ptr(out), _lib.ptr(lse),
-            _lib.stream_ptr(dev))
+            _lib.ptr(a3), _lib.stream_ptr(dev))
         _lib.check(rc, "upd_dts_attention")
         if need:
             ctx.save_for_backward(qbuf, kvbuf, out, lse)
             ctx.meta = (q_off, k_off, v_off, n_heads, d, scale, qbuf.data_ptr() == kvbuf.data_ptr())
-        return out
+            ctx.w_proj = None if proj is None else proj[1]
+        if proj is None:
+            return out
+        return gemm3(a3, proj[0], proj[2]).reshape(R, Lq, proj[2])
 
     @staticmethod
     def backward(ctx, g):
         qbuf, kvbuf, out, lse = ctx.saved_tensors
         q_off, k_off, v_off, n_heads, d, scale, same = ctx.meta
+        if ctx.w_proj is not None:
+            g = (g.reshape(-1, g.shape[-1]) @ ctx.w_proj).reshape(out.shape)
         g = g.contiguous()
         R, Lq, S = qbuf.shape[0], qbuf.shape[1], kvbuf.shape[1]
         dev = g.device
@@ -212,7 +219,7 @@ class FusedAttention(torch.autograd.Function):
             _lib.ptr(lse), _lib.ptr(g), ctypes.c_void_p(dqbuf.data_ptr() + 4 * q_off), dqbuf.shape[2],
             ctypes.c_void_p(dkb + 4 * k_off), ctypes.c_void_p(dkb + 4 * v_off), dkvbuf.shape[2], _lib.stream_ptr(dev))
         _lib.check(rc, "upd_dts_attention_bwd")
-        return dqbuf, (None if same else dkvbuf), None, None, None, None, None
+        return dqbuf, (None if same else dkvbuf), None, None, None, None, None, None
 
 
 class FusedLayerNorm(torch.autograd.Function):
@@ -227,7 +234,7 @@ class FusedLayerNorm(torch.autograd.Function):
         need = ctx.needs_input_grad[0]
         stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if need else None
         rc = _lib.lib().upd_dts_layernorm(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), rows, d, _lib.ptr(y), _lib.ptr(stats),
-                                          _lib.stream_ptr(x.device))
+                                          None, _lib.stream_ptr(x.device))
         _lib.check(rc, "upd_dts_layernorm")
         if need:
             ctx.save_for_backward(x, gamma, stats)
@@ -261,6 +268,59 @@ class ConstLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return (g.reshape(-1, g.shape[-1]) @ ctx.w).reshape(ctx.shp), None, None, None
+
+
+class LayerNormLinear(torch.autograd.Function):
+    """ConstLinear(FusedLayerNorm(x)): the normalisation kernel emits the GEMM's split operand directly, the fp32
+    normalised tensor never exists (forward) -- upd_dts_layernorm with a3 + upd_gemm3; backward = dy W, then the
+    LayerNorm input gradient."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, w3, w, n_out):
+        x = x.contiguous()
+        d = x.shape[-1]
+        rows = x.numel() // d
+        need = ctx.needs_input_grad[0]
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device) if need else None
+        a3 = torch.empty((rows, 3 * d + 8), dtype=torch.float16, device=x.device)
+        rc = _lib.lib().upd_dts_layernorm(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(beta), rows, d, None, _lib.ptr(stats),
+                                          _lib.ptr(a3), _lib.stream_ptr(x.device))
+        _lib.check(rc, "upd_dts_layernorm")
+        if need:
+            ctx.save_for_backward(x, gamma, stats)
+            ctx.w = w
+        return gemm3(a3, w3, n_out).reshape(*x.shape[:-1], n_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, gamma, stats = ctx.saved_tensors
+        d = x.shape[-1]
+        gy = (g.reshape(-1, g.shape[-1]) @ ctx.w).contiguous()
+        dx = torch.empty_like(x)
+        rc = _lib.lib().upd_dts_layernorm_bwd(_lib.ptr(x), _lib.ptr(gy), _lib.ptr(gamma), _lib.ptr(stats), x.numel() // d, d,
+                                              _lib.ptr(dx), _lib.stream_ptr(x.device))
+        _lib.check(rc, "upd_dts_layernorm_bwd")
+        return dx, None, None, None, None, None
+
+
+class GeluLinear(torch.autograd.Function):
+    """ConstLinear(F.gelu(x)): the exact GELU is applied inside the operand split (upd_fx_split, act = 2)."""
+
+    @staticmethod
+    def forward(ctx, x, w3, w, n_out):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        y = gemm3(a3_split(x2, act=2), w3, n_out)
+        if ctx.needs_input_grad[0]:
+            ctx.save_for_backward(x2)
+            ctx.w, ctx.shp = w, shp
+        return y.reshape(*shp[:-1], n_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x2,) = ctx.saved_tensors
+        gh = g.reshape(-1, g.shape[-1]) @ ctx.w
+        return torch.ops.aten.gelu_backward(gh, x2).reshape(ctx.shp), None, None, None
 
 
 def _sinusoidal(t, dim):
@@ -378,17 +438,27 @@ class PreparedTransformer:
         att = torch.softmax((q @ k.transpose(-2, -1)) * (1.0 / math.sqrt(q.shape[-1])), dim=-1)
         return (att @ v).transpose(1, 2).reshape(q.shape[0], q.shape[2], self.d)
 
-    def _self_attn(self, a, w):
-        qkv = ConstLinear.apply(a, *w["qkv"])                                     # [R, c, 3d] = (q | k | v)
+    def _fusable(self):
+        return self.d // self.nh == 16 and self.d % 64 == 0 and self.device.type == "cuda"
+
+    def _self_attn(self, h, gamma, beta, w):
+        """attention(LayerNorm(h)): normalisation -> fused Q|K|V projection -> attention -> out-projection."""
+        if self._fusable():
+            qkv = LayerNormLinear.apply(h, gamma, beta, *w["qkv"])                # [R, c, 3d] = (q | k | v)
+            return FusedAttention.apply(qkv, qkv, 0, self.d, 2 * self.d, self.nh, self.d, w["o"])
+        qkv = ConstLinear.apply(FusedLayerNorm.apply(h, gamma, beta), *w["qkv"])
         if self.d // self.nh == 16:
             y = FusedAttention.apply(qkv, qkv, 0, self.d, 2 * self.d, self.nh, self.d)
         else:
             y = self._attend(*qkv.split(self.d, dim=-1))
         return ConstLinear.apply(y, *w["o"])
 
-    def _cross_attn(self, a, enc, w):
-        q = ConstLinear.apply(a, *w["q"])
+    def _cross_attn(self, h, gamma, beta, enc, w):
         kv = ConstLinear.apply(enc, *w["kv"])                                     # [R, c_enc, 2d] = (k | v)
+        if self._fusable():
+            q = LayerNormLinear.apply(h, gamma, beta, *w["q"])
+            return FusedAttention.apply(q, kv, 0, 0, self.d, self.nh, self.d, w["o"])
+        q = ConstLinear.apply(FusedLayerNorm.apply(h, gamma, beta), *w["q"])
         if self.d // self.nh == 16:
             y = FusedAttention.apply(q, kv, 0, 0, self.d, self.nh, self.d)
         else:
@@ -396,6 +466,8 @@ class PreparedTransformer:
         return ConstLinear.apply(y, *w["o"])
 
     def _mlp(self, x, w):
+        if self._fusable():
+            return GeluLinear.apply(LayerNormLinear.apply(x, w["ln2_w"], w["ln2_b"], *w["fc1"]), *w["fc2"])
         h = FusedLayerNorm.apply(x, w["ln2_w"], w["ln2_b"])
         return ConstLinear.apply(F.gelu(ConstLinear.apply(h, *w["fc1"])), *w["fc2"])
 
@@ -414,8 +486,7 @@ class PreparedTransformer:
         emb = self._conv3(x, self.emb_w, self.emb_b)
         h = emb + self.pe_enc
         for w in self.enc:
-            a = self._ada_ln(h, w["ada1"], t)
-            h = h + self._self_attn(a, w["attn"])
+            h = h + self._self_attn(h, w["ada1"][0][t], w["ada1"][1][t], w["attn"])
             h = h + self._mlp(h, w)
         enc = h
         h = emb + self.pe_dec
@@ -424,8 +495,8 @@ class PreparedTransformer:
         means = []
         NF2 = 2 * self.NF
         for w in self.dec:
-            h = h + self._self_attn(self._ada_ln(h, w["ada1"], t), w["attn1"])
-            h = h + self._cross_attn(self._ada_ln(h, w["ada1_1"], t), enc, w["attn2"])
+            h = h + self._self_attn(h, w["ada1"][0][t], w["ada1"][1][t], w["attn1"])
+            h = h + self._cross_attn(h, w["ada1_1"][0][t], w["ada1_1"][1][t], enc, w["attn2"])
             y = torch.matmul(w["fold_w"], h) + w["fold_b"][:, None]               # [R, 2NF+9, d]
             se = FourierTopK.apply(y, self.NF, self.low, seq, self.top_k)
             y9 = y[:, NF2:, :]
