@@ -1,4 +1,4 @@
-"""profiles/r01_families_*: launch shares and ncu --set full metrics of the DiffSTG / DiffusionTS kernels.
+"""profiles/<tag>_families_*: launch shares and ncu --set full metrics of the DiffSTG / DiffusionTS kernels.
 
     python profiles/make_family_summaries.py r01
 Inputs (gpurun_out/, produced on a B200):
@@ -20,7 +20,9 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 OWN = ("stg_tcn_ln_kernel", "stg_gated_aggregate_kernel", "stg_posterior_kernel", "gauss_fill_kernel", "nsx_step_kernel",
        "sigma_estimation_kernel", "fx_add_ln_split_small_kernel", "fx_embed_split_kernel",
        "dts_fourier_topk_fwd_kernel", "dts_fourier_topk_bwd_kernel", "dts_ddim_step_kernel", "dts_adagrad_kernel",
-       "dts_infill_kernel", "dts_attn_fwd_kernel", "dts_attn_bwd_kernel", "fx_split_kernel")
+       "dts_infill_kernel", "dts_attn_fwd_kernel", "dts_attn_bwd_kernel", "fx_split_kernel",
+       "dts_attn_tc_fwd_kernel", "dts_attn_tc_bwd_kernel", "dts_ln_fwd_a3_kernel", "dts_ln_fwd_kernel", "dts_ln_bwd_kernel",
+       "gemm3_pair_kernel", "gemm3_kernel", "stg_tcn_ln_cat_kernel")
 lines = [l for l in open("gpurun_out/%s_families_launches.csv" % tag) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 # split the launch list at the first DiffusionTS-only kernel: everything before belongs to DiffSTG

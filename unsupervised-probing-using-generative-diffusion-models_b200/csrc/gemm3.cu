@@ -115,6 +115,12 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
 }
+// The same with the TMA unit ADDING the tile to what C already holds (fp32 reduction in L2): out = addend + A3 W3^T with
+// the addend resident in C -- no thread ever loads it.
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
@@ -128,7 +134,7 @@ constexpr uint32_t EPI_STAGE_BYTES = 2 * 32 * 128;      // per epilogue warp: tw
 template <int BN>
 __device__ __forceinline__ void drain_accumulator(uint32_t src, float* __restrict__ C, const float* __restrict__ addend,
                                                   long long row, long long M, int n0, int n_out, const CUtensorMap* tma_c,
-                                                  unsigned char* stage, int lane) {
+                                                  bool reduce_add, unsigned char* stage, int lane) {
   int buf = 0;
 #pragma unroll 1
   for (int c = 0; c < BN; c += 32) {
@@ -146,7 +152,8 @@ __device__ __forceinline__ void drain_accumulator(uint32_t src, float* __restric
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tma_c, tc::smem_u32(stage + buf * (32 * 128)), n0 + c, (int)(row - lane));
+        if (reduce_add) tma_reduce_add_2d(tma_c, tc::smem_u32(stage + buf * (32 * 128)), n0 + c, (int)(row - lane));
+        else tma_store_2d(tma_c, tc::smem_u32(stage + buf * (32 * 128)), n0 + c, (int)(row - lane));
         tma_store_commit();
       }
       buf ^= 1;
@@ -270,7 +277,7 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
       tc::mbar_wait(tc::smem_u32(&acc_full[acc]), acc_phase);
       tc::fence_after_sync();
       const uint32_t src = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
-      drain_accumulator<BN>(src, C, addend, row, M, n0, n_out, use_tma_store ? &tma_c : nullptr,
+      drain_accumulator<BN>(src, C, addend, row, M, n0, n_out, use_tma_store ? &tma_c : nullptr, use_tma_store == 2,
                             epi_stage + (size_t)quad * EPI_STAGE_BYTES, lane);
       tc::fence_before_sync();
       __syncwarp();
@@ -420,7 +427,7 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
       tc::mbar_wait(tc::smem_u32(&acc_full[acc]), acc_phase);
       tc::fence_after_sync();
       const uint32_t src = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)acc * BN;
-      drain_accumulator<BN>(src, C, addend, row, M, n0, n_out, use_tma_store ? &tma_c : nullptr,
+      drain_accumulator<BN>(src, C, addend, row, M, n0, n_out, use_tma_store ? &tma_c : nullptr, use_tma_store == 2,
                             epi_stage + (size_t)quad * EPI_STAGE_BYTES, lane);
       tc::fence_before_sync();
       __syncwarp();
@@ -510,8 +517,13 @@ cudaError_t launch_cl(const CUtensorMap& ma, const CUtensorMap& mb, long long M,
   if (units < clusters) clusters = units;
   cfg.gridDim = dim3((unsigned)(clusters * CL));
   CUtensorMap mc = ma;                                              // placeholder when the direct-store path is taken
-  const int use_tma = (addend == nullptr && (n_out & 3) == 0 && make_map_c(&mc, out, M, n_out)) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, addend, M, n_out, (Kp + BK - 1) / BK, mb_, nb);
+  // 1 = staged TMA store; 2 = staged TMA reduce-add onto the addend, which is first copied into C unless it already is C
+  int use_tma = ((n_out & 3) == 0 && make_map_c(&mc, out, M, n_out)) ? (addend ? 2 : 1) : 0;
+  if (use_tma == 2 && addend != out) {
+    cudaError_t ce = cudaMemcpyAsync(out, addend, (size_t)M * n_out * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+    if (ce != cudaSuccess) return ce;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, use_tma ? nullptr : addend, M, n_out, (Kp + BK - 1) / BK, mb_, nb);
 }
 
 template <int BN>
@@ -545,8 +557,13 @@ cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, long long 
   if (units < clusters) clusters = units;
   cfg.gridDim = dim3((unsigned)(clusters * 2));
   CUtensorMap mc = ma;
-  const int use_tma = (addend == nullptr && (n_out & 3) == 0 && make_map_c(&mc, out, M, n_out)) ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, addend, M, n_out, (Kp + BK - 1) / BK, mb_, nb);
+  // 1 = staged TMA store; 2 = staged TMA reduce-add onto the addend, which is first copied into C unless it already is C
+  int use_tma = ((n_out & 3) == 0 && make_map_c(&mc, out, M, n_out)) ? (addend ? 2 : 1) : 0;
+  if (use_tma == 2 && addend != out) {
+    cudaError_t ce = cudaMemcpyAsync(out, addend, (size_t)M * n_out * sizeof(float), cudaMemcpyDeviceToDevice, stream);
+    if (ce != cudaSuccess) return ce;
+  }
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, use_tma ? nullptr : addend, M, n_out, (Kp + BK - 1) / BK, mb_, nb);
 }
 
 template <int BN>
@@ -578,7 +595,12 @@ cudaError_t upd_launch_gemm3(const void* a3, const void* w3, long long M, int Nw
   if ((Kp & 7) != 0 || (reinterpret_cast<uintptr_t>(a3) & 15) != 0 || (reinterpret_cast<uintptr_t>(w3) & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(out) & 15) != 0 || (addend && (reinterpret_cast<uintptr_t>(addend) & 15) != 0))
     return cudaErrorInvalidValue;
-  if (n_out <= 64) return launch<64>(a3, w3, M, Nw, n_out, Kp, out, addend, sms, stream);
-  if (n_out <= 128) return launch<128>(a3, w3, M, Nw, n_out, Kp, out, addend, sms, stream);
+  int bn = n_out <= 64 ? 64 : (n_out <= 128 ? 128 : 256);
+  if (const char* e = getenv("UPD_GEMM3_BN")) {                     // experiments: force the column block
+    const int f = atoi(e);
+    if (f == 64 || f == 128 || f == 256) bn = f;
+  }
+  if (bn == 64) return launch<64>(a3, w3, M, Nw, n_out, Kp, out, addend, sms, stream);
+  if (bn == 128) return launch<128>(a3, w3, M, Nw, n_out, Kp, out, addend, sms, stream);
   return launch<256>(a3, w3, M, Nw, n_out, Kp, out, addend, sms, stream);
 }

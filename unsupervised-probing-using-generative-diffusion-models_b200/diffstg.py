@@ -343,6 +343,7 @@ class PreparedUGnet:
         C = Td * c_out
         tc_ok = b["down_w3"] is not None
         front, sc = self._front(b, x, t, c_in, c_out, T_in, tc_ok)
+        sc_is_temp = sc is not None                                                             # else a view of the block's input
         if sc is None:                                                                          # identity shortcut
             sc = (torch.cat(x, dim=1) if isinstance(x, tuple) else x).reshape(N, c_out * T_in)
         if tc_ok:
@@ -354,7 +355,7 @@ class PreparedUGnet:
         agg = gated_aggregate(kqvs.contiguous(), rowptr, col, b["gnn_bias"], V, C)
         # up-sampling GEMM with the shortcut as its accumulator input: out = shortcut + agg W_up + bias
         if tc_ok:
-            up = gemm3(a3_split(agg), b["up_w3"], c_out * T_in, addend=sc.contiguous())          # bias inside the GEMM
+            up = gemm3(a3_split(agg), b["up_w3"], c_out * T_in, addend=sc.contiguous(), inplace=sc_is_temp)   # bias inside the GEMM
         else:
             up = torch.addmm(sc, agg, b["up_w"]) + b["up_b_full"]
         return up.view(N, c_out, T_in)

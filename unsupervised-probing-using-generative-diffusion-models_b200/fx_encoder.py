@@ -135,11 +135,16 @@ def add_ln_split(x2d, res2d, ln1, ln2=None, want_y=True, want_a3=True):
     return y, a3
 
 
-def gemm3(a3, w3, n_out, addend=None):
+def gemm3(a3, w3, n_out, addend=None, inplace=False):
     """One fp16 tensor-core GEMM, fp32 accumulate and output: [rows, 3K+8] x [N, 3K+8]^T (+ addend) -> [rows, n_out]
-    (upd_gemm3: the warp-specialised tcgen05 kernel of csrc/gemm3.cu)."""
+    (upd_gemm3: the warp-specialised tcgen05 kernel of csrc/gemm3.cu).  inplace: the result is accumulated onto
+    ``addend`` itself (a contiguous fp32 [rows, n_out] temporary of the caller) instead of onto a copy of it."""
     rows, kp = a3.shape
-    y = torch.empty((rows, n_out), dtype=torch.float32, device=a3.device)
+    if inplace and addend is not None and addend.is_contiguous() and addend.dtype == torch.float32 and \
+            tuple(addend.shape) == (rows, n_out):
+        y = addend
+    else:
+        y = torch.empty((rows, n_out), dtype=torch.float32, device=a3.device)
     if rows == 0:
         return y
     with torch.cuda.device(a3.device):
