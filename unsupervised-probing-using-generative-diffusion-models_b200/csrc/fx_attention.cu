@@ -2,7 +2,9 @@
 //     out = softmax(scale * (tau_b * Q K^T + delta_b)) V        (DSAttention of torch-timeseries 0.1.10 as called from
 //     models/Diffusion_model/NsDiff/mu_backbone.py:70-104; head size 64, sequences of 100..150 positions)
 // One CTA = one (batch row, head): K and V are staged once, then blocks of 128 queries run through it;
-// 128 threads, thread i = query row i of the block = TMEM lane i.
+// 256 threads = two warps per TMEM lane quadrant: thread (quadrant, lane) = query row of the block = TMEM lane, the two
+// warps of a quadrant take alternate 16-key groups of the score row (partial max / sum exchanged through shared memory)
+// and halves of the output columns -- round 1 ran one warp per quadrant and was bound by that warp's serial stream.
 //
 //   Q row -> fp16 hi/lo A operand in TMEM (scaled by tau*scale*log2e, so scores come out as base-2 exponents)
 //   K, V^T of this (b,h) -> shared memory as fp16 hi/lo B operands (K-major, no-swizzle core-matrix layout)
@@ -47,11 +49,15 @@ __device__ __forceinline__ uint32_t idesc_f16(int n) {      // D fp32, A/B fp16 
   return (1u << 4) | ((uint32_t)(n >> 3) << 17) | (8u << 24);
 }
 
+constexpr int FX_THREADS = 256;
+
 template <bool CAUSAL>
-__global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams p) {
+__global__ void __launch_bounds__(FX_THREADS, 2) fx_attention_kernel(const FxAttnParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ AttnSync sync;
-  const int tid = threadIdx.x, warp = tid >> 5;
+  __shared__ float pm[2][128], ps[2][128];                  // partial row max / row sum of the two warps of a quadrant
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2, row = quad * 32 + lane;
   const int bh = blockIdx.x, b = bh / p.H, h = bh - b * p.H;
   const int S = p.S, SP = (S + 15) & ~15, NIT = SP >> 4;
   // K [SP x 64]: elem(s,c) at (c/8)*KLBO + s*16 + (c%8)*2 with KLBO = SP*16 + 16: the extra 16 bytes between
@@ -71,20 +77,21 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
   // three HBM round trips here instead of one per iteration (the projections were just written: 2.5 GB, not in L2).
   //   K: task (s, 8 consecutive channels) -> one 16-byte core-matrix row each for hi and lo
   //   V: task (channel c, 8 consecutive keys) -> one 16-byte row of V^T; global reads coalesced over c
-  for (int s0 = tid; s0 < SP; s0 += 128)
+  for (int s0 = tid; s0 < SP; s0 += FX_THREADS)
     sdelta[s0] = s0 < S ? (p.delta ? p.delta[(long long)b * p.delta_pitch + s0] * LOG2E : 0.0f) : -INFINITY;
   const float* kb = p.k + (long long)b * S * p.kv_stride + h * DK;
   const float* vb = p.v + (long long)b * S * p.kv_stride + h * DK;
-  for (int bt = 0; bt < NIT; bt += 4) {
+  const int NST = (NIT + 1) >> 1;                             // staging iterations of 256 tasks
+  for (int bt = 0; bt < NST; bt += 4) {
     float4 ka[4], kc[4];
     float vx[4][8];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int it = bt + u;
-      const int i = tid + 128 * it;
+      const int i = tid + FX_THREADS * it;
       const int s = i >> 3, c8 = i & 7;
       ka[u] = kc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (it < NIT && s < S) {
+      if (it < NST && s < S) {
         ka[u] = *reinterpret_cast<const float4*>(kb + (long long)s * p.kv_stride + c8 * 8);
         kc[u] = *reinterpret_cast<const float4*>(kb + (long long)s * p.kv_stride + c8 * 8 + 4);
       }
@@ -92,15 +99,15 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int sv = s8 * 8 + j;
-        vx[u][j] = (it < NIT && sv < S) ? vb[(long long)sv * p.kv_stride + c] : 0.0f;
+        vx[u][j] = (it < NST && sv < S) ? vb[(long long)sv * p.kv_stride + c] : 0.0f;
       }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int it = bt + u;
-      if (it >= NIT) break;
-      const int i = tid + 128 * it;
-      {
+      if (it >= NST) break;
+      const int i = tid + FX_THREADS * it;
+      if (i < SP * 8) {
         const int s = i >> 3, c8 = i & 7;
         uint4 hi, lo;
         tc::split_f16x2(ka[u].x, ka[u].y, hi.x, lo.x); tc::split_f16x2(ka[u].z, ka[u].w, hi.y, lo.y);
@@ -109,7 +116,7 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
         *reinterpret_cast<uint4*>(k_hi + off) = hi;
         *reinterpret_cast<uint4*>(k_lo + off) = lo;
       }
-      {
+      if (i < SP * 8) {
         const int s8 = i >> 6, c = i & 63;
         uint4 hi, lo;
         tc::split_f16x2(vx[u][0], vx[u][1], hi.x, lo.x); tc::split_f16x2(vx[u][2], vx[u][3], hi.y, lo.y);
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem_base = sync.tmem_base;
-  const uint32_t lane_sel = (uint32_t)(warp * 32) << 16;
+  const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
   const uint32_t q_cols = tmem_base + lane_sel;             // columns [0,64): Q operand, later the O accumulator
   const uint32_t s_cols = q_cols + 64u;                     // columns [64, 64+SP): scores, then P operand
   const uint32_t bar = tc::smem_u32(&sync.mma_bar);
@@ -134,16 +141,17 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
   uint32_t parity = 0;
 
   for (int q0 = 0; q0 < p.Lq; q0 += 128) {                  // query blocks share the staged K / V
-    // ---- this thread's query row -> TMEM (hi words [16j,16j+8), lo words [16j+8,16j+16) per K-slice j) ----
-    const int l = q0 + tid;
+    const int l = q0 + row;
     const bool valid = l < p.Lq;
+    // ---- the query row -> TMEM (hi words [16j,16j+8), lo words [16j+8,16j+16) per K-slice j): each warp of the
+    // quadrant writes two of the four K-slices ----
     {
-      const float* qr = p.q + ((long long)b * p.Lq + (valid ? l : 0)) * p.q_stride + h * DK;
-      float4 qv[DK / 4];
+      const float* qr = p.q + ((long long)b * p.Lq + (valid ? l : 0)) * p.q_stride + h * DK + 32 * part;
+      float4 qv[8];
 #pragma unroll
-      for (int c = 0; c < DK / 4; ++c) qv[c] = valid ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int c = 0; c < 8; ++c) qv[c] = valid ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < DK / 16; ++j) {
+      for (int j = 0; j < 2; ++j) {
         uint32_t o[16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
           tc::split_f16x2(a.x * qs, a.y * qs, o[2 * c], o[8 + 2 * c]);
           tc::split_f16x2(a.z * qs, a.w * qs, o[2 * c + 1], o[8 + 2 * c + 1]);
         }
-        tc::tmem_st16(q_cols + 16u * j, o);
+        tc::tmem_st16(q_cols + 16u * (2 * part + j), o);
       }
     }
     tc::wait_st();
@@ -175,71 +183,51 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
     parity ^= 1u;
     tc::fence_after_sync();
 
-    // ---- softmax over this thread's row.  Scores are base-2 exponents (Q was pre-scaled); delta (and the -inf of
-    // the padding keys) comes from shared memory as a broadcast.  TMEM loads run one 16-column group ahead. ----
+    // ---- softmax over the row, this warp's 16-key groups (part, part + 2, ..).  Scores are base-2 exponents (Q was
+    // pre-scaled); delta (and the -inf of the padding keys) comes from shared memory as a broadcast. ----
     const int s_end = CAUSAL ? min(S, l + 1) : S;            // causal: keys >= s_end are masked
     float m = -INFINITY;
-    {
-      uint32_t ra[16], rb[16];
-      tc::tmem_ld16(s_cols, ra);
-      for (int g = 0; g < NIT; g += 2) {
-        tc::wait_ld();
-        if (g + 1 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 1), rb);
+    for (int g = part; g < NIT; g += 2) {
+      uint32_t ra[16];
+      tc::tmem_ld16(s_cols + 16u * g, ra);
+      tc::wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 d4 = *reinterpret_cast<const float4*>(sdelta + 16 * g + j);
-          float x0 = __uint_as_float(ra[j]) + d4.x, x1 = __uint_as_float(ra[j + 1]) + d4.y;
-          float x2 = __uint_as_float(ra[j + 2]) + d4.z, x3 = __uint_as_float(ra[j + 3]) + d4.w;
-          if (CAUSAL) {
-            const int s = 16 * g + j;
-            x0 = s < s_end ? x0 : -INFINITY; x1 = s + 1 < s_end ? x1 : -INFINITY;
-            x2 = s + 2 < s_end ? x2 : -INFINITY; x3 = s + 3 < s_end ? x3 : -INFINITY;
-          }
-          m = fmaxf(fmaxf(m, fmaxf(x0, x1)), fmaxf(x2, x3));
+      for (int j = 0; j < 16; j += 4) {
+        const float4 d4 = *reinterpret_cast<const float4*>(sdelta + 16 * g + j);
+        float x0 = __uint_as_float(ra[j]) + d4.x, x1 = __uint_as_float(ra[j + 1]) + d4.y;
+        float x2 = __uint_as_float(ra[j + 2]) + d4.z, x3 = __uint_as_float(ra[j + 3]) + d4.w;
+        if (CAUSAL) {
+          const int s = 16 * g + j;
+          x0 = s < s_end ? x0 : -INFINITY; x1 = s + 1 < s_end ? x1 : -INFINITY;
+          x2 = s + 2 < s_end ? x2 : -INFINITY; x3 = s + 3 < s_end ? x3 : -INFINITY;
         }
-        if (g + 1 < NIT) {
-          tc::wait_ld();
-          if (g + 2 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 2), ra);
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 d4 = *reinterpret_cast<const float4*>(sdelta + 16 * (g + 1) + j);
-            float x0 = __uint_as_float(rb[j]) + d4.x, x1 = __uint_as_float(rb[j + 1]) + d4.y;
-            float x2 = __uint_as_float(rb[j + 2]) + d4.z, x3 = __uint_as_float(rb[j + 3]) + d4.w;
-            if (CAUSAL) {
-              const int s = 16 * (g + 1) + j;
-              x0 = s < s_end ? x0 : -INFINITY; x1 = s + 1 < s_end ? x1 : -INFINITY;
-              x2 = s + 2 < s_end ? x2 : -INFINITY; x3 = s + 3 < s_end ? x3 : -INFINITY;
-            }
-            m = fmaxf(fmaxf(m, fmaxf(x0, x1)), fmaxf(x2, x3));
-          }
-        }
+        m = fmaxf(fmaxf(m, fmaxf(x0, x1)), fmaxf(x2, x3));
       }
     }
+    pm[part][row] = m;
+    __syncthreads();
+    m = fmaxf(pm[0][row], pm[1][row]);
     float sum = 0.0f;
-    {
-      uint32_t ra[16], rb[16], o[16];
-      tc::tmem_ld16(s_cols, ra);
-      for (int g = 0; g < NIT; ++g) {
-        uint32_t (&cur)[16] = (g & 1) ? rb : ra;
-        uint32_t (&nxt)[16] = (g & 1) ? ra : rb;
-        tc::wait_ld();
-        if (g + 1 < NIT) tc::tmem_ld16(s_cols + 16u * (g + 1), nxt);
+    for (int g = part; g < NIT; g += 2) {
+      uint32_t cur[16], o[16];
+      tc::tmem_ld16(s_cols + 16u * g, cur);
+      tc::wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float2 d2 = *reinterpret_cast<const float2*>(sdelta + 16 * g + j);
-          float e0, e1;
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"((__uint_as_float(cur[j]) + d2.x) - m));
-          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"((__uint_as_float(cur[j + 1]) + d2.y) - m));
-          if (CAUSAL) {
-            const int s = 16 * g + j;
-            e0 = s < s_end ? e0 : 0.0f; e1 = s + 1 < s_end ? e1 : 0.0f;
-          }
-          sum += e0 + e1;
-          tc::split_f16x2(e0, e1, o[j / 2], o[8 + j / 2]);
+      for (int j = 0; j < 16; j += 2) {
+        const float2 d2 = *reinterpret_cast<const float2*>(sdelta + 16 * g + j);
+        float e0, e1;
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"((__uint_as_float(cur[j]) + d2.x) - m));
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"((__uint_as_float(cur[j + 1]) + d2.y) - m));
+        if (CAUSAL) {
+          const int s = 16 * g + j;
+          e0 = s < s_end ? e0 : 0.0f; e1 = s + 1 < s_end ? e1 : 0.0f;
         }
-        tc::tmem_st16(s_cols + 16u * g, o);
+        sum += e0 + e1;
+        tc::split_f16x2(e0, e1, o[j / 2], o[8 + j / 2]);
       }
+      tc::tmem_st16(s_cols + 16u * g, o);
     }
+    ps[part][row] = sum;
     tc::wait_st();
     tc::fence_before_sync();
     __syncthreads();
@@ -260,36 +248,37 @@ __global__ void __launch_bounds__(128, 2) fx_attention_kernel(const FxAttnParams
     parity ^= 1u;
     tc::fence_after_sync();
 
-    // ---- O / sum -> split operand of the out-projection, heads merged ----
-    const float inv = 1.0f / sum;
-    __half* row = p.a3 + ((long long)b * p.Lq + (valid ? l : 0)) * (3 * Kd + 8) + h * DK;
+    // ---- O / sum -> split operand of the out-projection, heads merged; each warp of the quadrant writes 32 of the
+    // head's 64 columns ----
+    const float inv = 1.0f / (ps[0][row] + ps[1][row]);
+    __half* arow = p.a3 + ((long long)b * p.Lq + (valid ? l : 0)) * (3 * Kd + 8) + h * DK + 32 * part;
     {
-      uint32_t r[DK / 16][16];
+      uint32_t r[2][16];
 #pragma unroll
-      for (int g = 0; g < DK / 16; ++g) tc::tmem_ld16(q_cols + 16u * g, r[g]);
+      for (int g = 0; g < 2; ++g) tc::tmem_ld16(q_cols + 16u * (2 * part + g), r[g]);
       tc::wait_ld();
       if (valid) {
 #pragma unroll
-        for (int g = 0; g < DK / 16; ++g) {
+        for (int g = 0; g < 2; ++g) {
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int j = 0; j < 16; j += 2)
             tc::split_f16x2(__uint_as_float(r[g][j]) * inv, __uint_as_float(r[g][j + 1]) * inv, hi[j / 2], lo[j / 2]);
-          uint4* d_hi = reinterpret_cast<uint4*>(row + 16 * g);
-          uint4* d_lo = reinterpret_cast<uint4*>(row + Kd + 16 * g);
-          uint4* d_h2 = reinterpret_cast<uint4*>(row + 2 * Kd + 16 * g);
+          uint4* d_hi = reinterpret_cast<uint4*>(arow + 16 * g);
+          uint4* d_lo = reinterpret_cast<uint4*>(arow + Kd + 16 * g);
+          uint4* d_h2 = reinterpret_cast<uint4*>(arow + 2 * Kd + 16 * g);
           const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
           d_hi[0] = h0; d_hi[1] = h1;
           d_lo[0] = make_uint4(lo[0], lo[1], lo[2], lo[3]); d_lo[1] = make_uint4(lo[4], lo[5], lo[6], lo[7]);
           d_h2[0] = h0; d_h2[1] = h1;
         }
-        if (h == 0)                                          // bias columns of the operand: 1, 1, 0 x 6
+        if (h == 0 && part == 0)                             // bias columns of the operand: 1, 1, 0 x 6
           *reinterpret_cast<uint4*>(p.a3 + ((long long)b * p.Lq + l) * (3 * Kd + 8) + 3 * Kd) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
       }
     }
     tc::fence_before_sync();                                 // this block's TMEM reads precede the next block's writes
+    __syncthreads();                                         // (both warps of a quadrant: the next Q write covers other columns)
   }
-  __syncthreads();
   if (warp == 0) tc::tmem_dealloc<256>(tmem_base);
 }
 
@@ -312,11 +301,11 @@ cudaError_t upd_launch_fx_attention(const float* q, long long q_stride, const fl
   if (causal) {
     e = cudaFuncSetAttribute(fx_attention_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fx_attention_kernel<true><<<(unsigned)(B * H), 128, smem, stream>>>(p);
+    fx_attention_kernel<true><<<(unsigned)(B * H), FX_THREADS, smem, stream>>>(p);
   } else {
     e = cudaFuncSetAttribute(fx_attention_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    fx_attention_kernel<false><<<(unsigned)(B * H), 128, smem, stream>>>(p);
+    fx_attention_kernel<false><<<(unsigned)(B * H), FX_THREADS, smem, stream>>>(p);
   }
   return cudaGetLastError();
 }
