@@ -186,3 +186,42 @@ def test_fused_layernorm_forward_backward():
     (g,) = torch.autograd.grad((y * w).sum(), x)
     (gr,) = torch.autograd.grad((ref * w.double()).sum(), x)
     assert _rel(g, gr) < 1e-5
+
+
+@pytest.mark.parametrize("d", [64, 128])
+def test_fused_producers_of_the_split_operand_against_autograd(d):
+    """LayerNormLinear (normalisation kernel emits the GEMM operand), GeluLinear (GELU inside the split) and the projected
+    FusedAttention (attention kernel emits the out-projection's operand) vs the same chains of library ops in float64."""
+    import math
+    from updgm_b200.diffusionts import FusedAttention, GeluLinear, LayerNormLinear
+    from updgm_b200.fx_encoder import _W3Cache
+    torch.manual_seed(d)
+    R, L, H = 3, 70, d // 16
+    lin1, lin2 = torch.nn.Linear(d, 3 * d).to(DEV), torch.nn.Linear(3 * d, d).to(DEV)
+    w3a, w3b = _W3Cache().get([(lin1.weight, lin1.bias)]), _W3Cache().get([(lin2.weight, lin2.bias)])
+    gam, bet = torch.rand(d, device=DEV) + 0.5, torch.randn(d, device=DEV)
+    x = torch.randn(R, L, d, device=DEV, requires_grad=True)
+    # LayerNorm -> Linear -> GELU -> Linear
+    y = GeluLinear.apply(LayerNormLinear.apply(x, gam, bet, w3a, lin1.weight.detach(), 3 * d), w3b, lin2.weight.detach(), d)
+    x64 = x.detach().double().requires_grad_(True)
+    h64 = torch.nn.functional.layer_norm(x64, (d,), gam.double(), bet.double()) @ lin1.weight.double().t() + lin1.bias.double()
+    ref = torch.nn.functional.gelu(h64) @ lin2.weight.double().t() + lin2.bias.double()
+    assert _rel(y.detach(), ref.detach()) < 2e-5
+    w = torch.randn_like(y) * 1e-6
+    (g,) = torch.autograd.grad((y * w).sum(), x)
+    (gr,) = torch.autograd.grad((ref * w.double()).sum(), x64)
+    assert _rel(g, gr) < 2e-5, _rel(g, gr)
+    # attention with the out-projection folded in
+    lin_o = torch.nn.Linear(d, d).to(DEV)
+    w3o = _W3Cache().get([(lin_o.weight, lin_o.bias)])
+    qb = torch.randn(R, L, 3 * d, device=DEV, requires_grad=True)
+    y = FusedAttention.apply(qb, qb, 0, d, 2 * d, H, d, (w3o, lin_o.weight.detach(), d))
+    q64 = qb.detach().double().requires_grad_(True)
+    heads = lambda t: t.reshape(R, -1, H, 16).transpose(1, 2)
+    att = torch.softmax(heads(q64[..., :d]) @ heads(q64[..., d:2 * d]).transpose(-1, -2) / 4.0, -1)
+    ref = (att @ heads(q64[..., 2 * d:])).transpose(1, 2).reshape(R, L, d) @ lin_o.weight.double().t() + lin_o.bias.double()
+    assert _rel(y.detach(), ref.detach()) < 2e-5
+    w = torch.randn_like(y)
+    (g,) = torch.autograd.grad((y * w).sum(), qb)
+    (gr,) = torch.autograd.grad((ref * w.double()).sum(), q64)
+    assert _rel(g, gr) < 2e-5, _rel(g, gr)

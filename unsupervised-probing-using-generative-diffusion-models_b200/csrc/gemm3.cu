@@ -185,7 +185,7 @@ template <int BN, int CL>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
              const __grid_constant__ CUtensorMap tma_c, int use_tma_store, float* __restrict__ C,
-             const float* __restrict__ addend, long long M, int n_out, int num_k_blocks, long long num_m_blocks,
+             const float* __restrict__ addend, long long M, int n_out, int num_k_blocks, int tail_ksteps, long long num_m_blocks,
              int num_n_blocks) {
   using K = Cfg<BN>;
   constexpr int STAGES = K::STAGES;
@@ -257,7 +257,8 @@ gemm3_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ 
           const uint32_t sa = tc::smem_u32(smem + (size_t)r.stage * K::STAGE_BYTES);
           const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) mma_f16_ss(d, da + 2u * k, db + 2u * k, IDESC, (kb | k) != 0);
+          const int nk = kb + 1 < num_k_blocks ? BK / 16 : tail_ksteps;     // Kp = 3K + 8: the last block holds 8 columns
+          for (int k = 0; k < nk; ++k) mma_f16_ss(d, da + 2u * k, db + 2u * k, IDESC, (kb | k) != 0);
           if (CL == 1) tc::mma_commit(tc::smem_u32(&empty[r.stage]));       // slot free once these MMAs have read it
           else mma_commit_mc(tc::smem_u32(&empty[r.stage]), MASK);           // ... in this CTA AND for the peer's producer
           r.advance<STAGES>();
@@ -346,7 +347,7 @@ template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm3_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                   const __grid_constant__ CUtensorMap tma_c, int use_tma_store, float* __restrict__ C,
-                  const float* __restrict__ addend, long long M, int n_out, int num_k_blocks, long long num_m_blocks,
+                  const float* __restrict__ addend, long long M, int n_out, int num_k_blocks, int tail_ksteps, long long num_m_blocks,
                   int num_n_blocks) {
   using K = PairCfg<BN>;
   constexpr int STAGES = K::STAGES;
@@ -409,7 +410,8 @@ gemm3_pair_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_consta
           const uint32_t sa = tc::smem_u32(smem + (size_t)r.stage * K::STAGE_BYTES);
           const uint64_t da = smem_desc_sw128(sa), db = smem_desc_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) mma_f16_ss_pair(d, da + 2u * k, db + 2u * k, IDESC, (kb | k) != 0);
+          const int nk = kb + 1 < num_k_blocks ? BK / 16 : tail_ksteps;     // Kp = 3K + 8: the last block holds 8 columns
+          for (int k = 0; k < nk; ++k) mma_f16_ss_pair(d, da + 2u * k, db + 2u * k, IDESC, (kb | k) != 0);
           mma_commit_pair(tc::smem_u32(&empty[r.stage]), 3);                // frees the slot in both CTAs
           r.advance<STAGES>();
         }
@@ -523,7 +525,8 @@ cudaError_t launch_cl(const CUtensorMap& ma, const CUtensorMap& mb, long long M,
     cudaError_t ce = cudaMemcpyAsync(out, addend, (size_t)M * n_out * sizeof(float), cudaMemcpyDeviceToDevice, stream);
     if (ce != cudaSuccess) return ce;
   }
-  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, use_tma ? nullptr : addend, M, n_out, (Kp + BK - 1) / BK, mb_, nb);
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, use_tma ? nullptr : addend, M, n_out, (Kp + BK - 1) / BK,
+                            ((Kp - ((Kp + BK - 1) / BK - 1) * BK) + 15) / 16, mb_, nb);
 }
 
 template <int BN>
@@ -563,7 +566,8 @@ cudaError_t launch_pair(const CUtensorMap& ma, const CUtensorMap& mb, long long 
     cudaError_t ce = cudaMemcpyAsync(out, addend, (size_t)M * n_out * sizeof(float), cudaMemcpyDeviceToDevice, stream);
     if (ce != cudaSuccess) return ce;
   }
-  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, use_tma ? nullptr : addend, M, n_out, (Kp + BK - 1) / BK, mb_, nb);
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, use_tma, out, use_tma ? nullptr : addend, M, n_out, (Kp + BK - 1) / BK,
+                            ((Kp - ((Kp + BK - 1) / BK - 1) * BK) + 15) / 16, mb_, nb);
 }
 
 template <int BN>
@@ -596,6 +600,10 @@ cudaError_t upd_launch_gemm3(const void* a3, const void* w3, long long M, int Nw
       (reinterpret_cast<uintptr_t>(out) & 15) != 0 || (addend && (reinterpret_cast<uintptr_t>(addend) & 15) != 0))
     return cudaErrorInvalidValue;
   int bn = n_out <= 64 ? 64 : (n_out <= 128 ? 128 : 256);
+  if (bn == 256) {                     // a ragged last column block: 128-wide blocks when they cut the padding (> 25 %)
+    const int p256 = (n_out + 255) / 256 * 256, p128 = (n_out + 127) / 128 * 128;
+    if (p128 < p256 && 4 * (p256 - n_out) > n_out) bn = 128;
+  }
   if (const char* e = getenv("UPD_GEMM3_BN")) {                     // experiments: force the column block
     const int f = atoi(e);
     if (f == 64 || f == 128 || f == 256) bn = f;
