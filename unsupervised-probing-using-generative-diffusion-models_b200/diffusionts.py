@@ -270,6 +270,21 @@ class ConstLinear(torch.autograd.Function):
         return (g.reshape(-1, g.shape[-1]) @ ctx.w).reshape(ctx.shp), None, None, None
 
 
+class OperandLinear(torch.autograd.Function):
+    """ConstLinear on a split operand the caller already holds (``a3 = a3_split(x)``, shared by several layers that read
+    the same activation -- the six decoder blocks' K|V projections of the encoder output).  ``x`` only ties the result to
+    the autograd graph."""
+
+    @staticmethod
+    def forward(ctx, x, a3, w3, w, n_out):
+        ctx.w, ctx.shp = w, x.shape
+        return gemm3(a3, w3, n_out).reshape(*x.shape[:-1], n_out)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g.reshape(-1, g.shape[-1]) @ ctx.w).reshape(ctx.shp), None, None, None, None
+
+
 class LayerNormLinear(torch.autograd.Function):
     """ConstLinear(FusedLayerNorm(x)): the normalisation kernel emits the GEMM's split operand directly, the fp32
     normalised tensor never exists (forward) -- upd_dts_layernorm with a3 + upd_gemm3; backward = dy W, then the
@@ -453,8 +468,11 @@ class PreparedTransformer:
             y = self._attend(*qkv.split(self.d, dim=-1))
         return ConstLinear.apply(y, *w["o"])
 
-    def _cross_attn(self, h, gamma, beta, enc, w):
-        kv = ConstLinear.apply(enc, *w["kv"])                                     # [R, c_enc, 2d] = (k | v)
+    def _cross_attn(self, h, gamma, beta, enc, w, enc_a3=None):
+        if enc_a3 is not None:
+            kv = OperandLinear.apply(enc, enc_a3, *w["kv"])                       # [R, c_enc, 2d] = (k | v)
+        else:
+            kv = ConstLinear.apply(enc, *w["kv"])
         if self._fusable():
             q = LayerNormLinear.apply(h, gamma, beta, *w["q"])
             return FusedAttention.apply(q, kv, 0, 0, self.d, self.nh, self.d, w["o"])
@@ -489,6 +507,7 @@ class PreparedTransformer:
             h = h + self._self_attn(h, w["ada1"][0][t], w["ada1"][1][t], w["attn"])
             h = h + self._mlp(h, w)
         enc = h
+        enc_a3 = a3_split(enc.detach().reshape(-1, d).contiguous()) if self._fusable() else None   # one split for all decoder blocks
         h = emb + self.pe_dec
         season = None
         trend = None
@@ -496,7 +515,7 @@ class PreparedTransformer:
         NF2 = 2 * self.NF
         for w in self.dec:
             h = h + self._self_attn(h, w["ada1"][0][t], w["ada1"][1][t], w["attn1"])
-            h = h + self._cross_attn(h, w["ada1_1"][0][t], w["ada1_1"][1][t], enc, w["attn2"])
+            h = h + self._cross_attn(h, w["ada1_1"][0][t], w["ada1_1"][1][t], enc, w["attn2"], enc_a3)
             y = torch.matmul(w["fold_w"], h) + w["fold_b"][:, None]               # [R, 2NF+9, d]
             se = FourierTopK.apply(y, self.NF, self.low, seq, self.top_k)
             y9 = y[:, NF2:, :]
