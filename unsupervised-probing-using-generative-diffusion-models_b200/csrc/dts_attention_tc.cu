@@ -176,6 +176,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) dts_attn_tc_fwd_kernel(const D
   if (warp == 0) tc::tmem_alloc<256>(tc::smem_u32(&sync.tmem_base));
   const float* kb = p.k + (long long)r * S * p.kv_stride + h * HS;
   const float* vb = p.v + (long long)r * S * p.kv_stride + h * HS;
+  float4 qv0[4];                                            // the first query block's rows, requested with the K / V tiles
+  {
+    const bool v0 = part == 0 && row < p.Lq;
+    const float* qr = p.q + ((long long)r * p.Lq + (v0 ? row : 0)) * p.q_stride + h * HS;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) qv0[c] = v0 ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   {
     NTasks tk;
     TTasks tv;
@@ -203,8 +210,13 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) dts_attn_tc_fwd_kernel(const D
     if (part == 0) {
       const float* qr = p.q + ((long long)r * p.Lq + (valid ? l : 0)) * p.q_stride + h * HS;
       float4 qv[4];
+      if (q0 == 0) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) qv[c] = valid ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 4; ++c) qv[c] = qv0[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) qv[c] = valid ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       uint32_t o[16];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {

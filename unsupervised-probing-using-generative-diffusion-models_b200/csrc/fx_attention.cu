@@ -77,6 +77,15 @@ __global__ void __launch_bounds__(FX_THREADS, 2) fx_attention_kernel(const FxAtt
   // three HBM round trips here instead of one per iteration (the projections were just written: 2.5 GB, not in L2).
   //   K: task (s, 8 consecutive channels) -> one 16-byte core-matrix row each for hi and lo
   //   V: task (channel c, 8 consecutive keys) -> one 16-byte row of V^T; global reads coalesced over c
+  // the first query block's rows are requested before the K / V staging, so that a CTA pays ONE memory round trip
+  // before its first MMA instead of two (a CTA lives ~5 k clk, a round trip is ~1.5 k)
+  float4 qv0[8];
+  {
+    const bool v0 = row < p.Lq;
+    const float* qr = p.q + ((long long)b * p.Lq + (v0 ? row : 0)) * p.q_stride + h * DK + 32 * part;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) qv0[c] = v0 ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int s0 = tid; s0 < SP; s0 += FX_THREADS)
     sdelta[s0] = s0 < S ? (p.delta ? p.delta[(long long)b * p.delta_pitch + s0] * LOG2E : 0.0f) : -INFINITY;
   const float* kb = p.k + (long long)b * S * p.kv_stride + h * DK;
@@ -148,8 +157,13 @@ __global__ void __launch_bounds__(FX_THREADS, 2) fx_attention_kernel(const FxAtt
     {
       const float* qr = p.q + ((long long)b * p.Lq + (valid ? l : 0)) * p.q_stride + h * DK + 32 * part;
       float4 qv[8];
+      if (q0 == 0) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) qv[c] = valid ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int c = 0; c < 8; ++c) qv[c] = qv0[c];
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) qv[c] = valid ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         uint32_t o[16];
