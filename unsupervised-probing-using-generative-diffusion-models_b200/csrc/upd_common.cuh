@@ -111,7 +111,7 @@ __device__ __forceinline__ void upd_box_muller(uint32_t a, uint32_t b, float& z0
 // N(0,1) for (global window, row-in-window, sample, position, feature, draw).  Counter layout:
 //   c0 = position*F + feature, c1 = sample, c2 = row-in-window, c3 = draw | (window_lo << 8);
 //   key = seed ^ (window_hi...).  One Philox call per scalar keeps the stream independent of how
-//   the sweep is tiled; its cost is noise next to the 514 softplus of the same row-step.
+//   the sweep is tiled; its cost is noise next to the 386 softplus of the same row-step.
 __device__ __forceinline__ float upd_gauss(uint64_t seed, uint64_t window, uint32_t row, uint32_t sample,
                                            uint32_t elem, uint32_t draw) {
   uint32_t r[4];

@@ -103,7 +103,6 @@ class _NsDiffBase(nn.Module):
         self.scaler = net_param["scaler_type"]
         self.register_buffer("scaler_mean", torch.zeros(self.dataset_nf))
         self.register_buffer("scaler_std", torch.zeros(self.dataset_nf))
-        # three-tile rotation kernel where it is the faster one (several features: +6.5 %, csrc/sampler_tc3w.cu)
         self.sampler_impl = kernels.IMPL_TCGEN05      # the library picks the kernel for (kind, F, T), include/upd_b200.h
         self._packed = None
         self._packed_key = None
