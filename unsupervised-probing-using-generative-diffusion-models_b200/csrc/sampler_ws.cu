@@ -55,6 +55,12 @@ struct __align__(8) WsSync {
   uint32_t pad;
 };
 
+#ifndef UPD_WS_NO_SETMAXNREG
+template <int F> struct WS_SETMAXNREG { static constexpr bool value = (F == 1); };
+#else
+template <int F> struct WS_SETMAXNREG { static constexpr bool value = false; };
+#endif
+
 template <int KIND, int F>
 struct WsShape {
   static constexpr bool NS = (KIND == 0);
@@ -167,6 +173,11 @@ sampler_ws_kernel(const UpdSamplerParams p) {
 
   if (warp < EPI_WARPS) {
     // =========================================== epilogue warps ===========================================
+    // Register re-allocation between the roles (F = 1): the kernel is compiled for 96 registers per thread (640 threads);
+    // the four epilogue warpgroups take 104 and the row warpgroup gives back down to 64 (512 x 104 + 128 x 64 = 640 x 96).
+    // Measured: 4.03 -> 4.21 G row-steps/s at F = 1 (the epilogue's spills go away, the posterior chain fits in 64);
+    // at F = 2 the row warps' per-feature state spills at 64 registers and the kernel loses 8 %, so it stays off there.
+    if constexpr (WS_SETMAXNREG<F>::value) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int quad = warp & 3, cq = warp >> 2;
     const int trow = quad * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
@@ -256,6 +267,7 @@ sampler_ws_kernel(const UpdSamplerParams p) {
     }
   } else {
     // ============================================== row warps ==============================================
+    if constexpr (WS_SETMAXNREG<F>::value) asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     const int quad = warp - EPI_WARPS;                               // = warp % 4: this warp's TMEM lane quadrant
     const int trow = quad * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(quad * 32) << 16;
