@@ -176,7 +176,8 @@ sampler_ws_kernel(const UpdSamplerParams p) {
     // Register re-allocation between the roles (F = 1): the kernel is compiled for 96 registers per thread (640 threads);
     // the four epilogue warpgroups take 104 and the row warpgroup gives back down to 64 (512 x 104 + 128 x 64 = 640 x 96).
     // Measured: 4.03 -> 4.21 G row-steps/s at F = 1 (the epilogue's spills go away, the posterior chain fits in 64);
-    // at F = 2 the row warps' per-feature state spills at 64 registers and the kernel loses 8 %, so it stays off there.
+    // at F = 2 the row warps' per-feature state spills at 64 registers and the kernel loses 8 % (2 % without their noise
+    // cache), so it stays off there.
     if constexpr (WS_SETMAXNREG<F>::value) asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int quad = warp & 3, cq = warp >> 2;
     const int trow = quad * 32 + lane;
