@@ -715,7 +715,7 @@ def run_diffstg_evaluation_cache(model, timeseries_datas, pred_len, graph_data, 
 def _reduce_elements(pred_future_list, scale=None, want_mean=False):
     """List of [B,O,F,K] elements (any strides) -> per-window statistics on the GPU, one launch per run of
     equal-shaped elements.  Returns dict of CPU tensors mpv [W], pred_mean [W], mpv_f [W,F] (+ mean)."""
-    dev = torch.device("cuda")
+    dev = scale.device if scale is not None else torch.device("cuda", torch.cuda.current_device())   # the scaler table lives on the model's device
     outs = {"mpv": [], "pred_mean": [], "mpv_f": [], "mean": []}
     i, n = 0, len(pred_future_list)
     while i < n:
@@ -757,7 +757,10 @@ def _scaler_table(model):
         return None
     if not hasattr(model, "scaler_mean") or not hasattr(model, "scaler_std"):
         return None
-    return torch.stack([model.scaler_mean.detach().float().cpu(), model.scaler_std.detach().float().cpu()]).cuda().contiguous()
+    dev = _model_device(model)                      # the model's device, which need not be the current one
+    if dev.type != "cuda":
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return torch.stack([model.scaler_mean.detach().float().cpu(), model.scaler_std.detach().float().cpu()]).to(dev).contiguous()
 
 
 def _feature_inverse_transform(pred_future, model=None):
