@@ -23,7 +23,7 @@ LIB_NAME = "libupd_b200.so"
 LIB_PATH = os.path.join(PKG_DIR, LIB_NAME)
 BUILD_DIR = os.path.join(PKG_DIR, "build")
 SOURCES = ["api.cu", "sampler_simt.cu", "sampler_tc.cu", "sampler_ws.cu", "mpv_reduce.cu", "sigma_est.cu",
-           "infill_steps.cu", "stg_steps.cu", "fx_fused.cu", "gemm3.cu", "fx_attention.cu", "dts_attention.cu", "dts_attention_tc.cu", "dts_norm.cu"]
+           "infill_steps.cu", "stg_steps.cu", "stg_tcn_mma.cu", "fx_fused.cu", "gemm3.cu", "fx_attention.cu", "dts_attention.cu", "dts_attention_tc.cu", "dts_norm.cu"]
 HEADERS = ["upd_common.cuh", "sampler_params.cuh", "sampler_math.cuh", "sampler_epi.cuh", "tc_helpers.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

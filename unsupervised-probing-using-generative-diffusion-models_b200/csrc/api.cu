@@ -40,7 +40,8 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
                                            long long N, int V, int C, int relu, float* out, int sms, cudaStream_t stream);
 cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
-                                  void* a3, const float* wsc, float* sc_out, const float* x2, int CI2, cudaStream_t stream);
+                                  void* a3, const float* wsc, float* sc_out, const float* x2, int CI2, int sms,
+                                  cudaStream_t stream);
 cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, int L, int act, void* a3, cudaStream_t stream);
 cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const float* g1, const float* b1,
                                        const float* g2, const float* b2, long long rows, int K, float* y, void* a3,
@@ -420,7 +421,7 @@ int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev,
   if ((C != 4 && C != 8 && C != 16) || CI < 1 || (T & 1) != 0) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_tcn_ln(x_dev, w1_dev, b1_dev, w2_dev, b2_dev, gamma_dev, beta_dev, N, CI, C, T, hn_dev, a3_dev,
-                                   wsc_dev, sc_dev, nullptr, 0, (cudaStream_t)stream));
+                                   wsc_dev, sc_dev, nullptr, 0, sms, (cudaStream_t)stream));
 }
 
 int upd_stg_tcn_ln_cat(const float* x_dev, int CI1, const float* x2_dev, int CI2, const float* w1_dev, const float* b1_dev,
@@ -432,7 +433,7 @@ int upd_stg_tcn_ln_cat(const float* x_dev, int CI1, const float* x2_dev, int CI2
   if ((C != 4 && C != 8 && C != 16) || (T & 1) != 0) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_tcn_ln(x_dev, w1_dev, b1_dev, w2_dev, b2_dev, gamma_dev, beta_dev, N, CI1 + CI2, C, T, hn_dev,
-                                   a3_dev, wsc_dev, sc_dev, x2_dev, CI2, (cudaStream_t)stream));
+                                   a3_dev, wsc_dev, sc_dev, x2_dev, CI2, sms, (cudaStream_t)stream));
 }
 
 int upd_gram_centered(const float* traj_dev, int n_win, int K, int D, double* gram_dev, void* stream) {

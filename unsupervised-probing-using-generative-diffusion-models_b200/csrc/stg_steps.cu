@@ -349,9 +349,15 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
   return cudaGetLastError();
 }
 
+cudaError_t upd_launch_stg_tcn_mma(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
+                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
+                                   void* a3, const float* wsc, float* sc_out, const float* x2, int CI1, int sms,
+                                   cudaStream_t stream);
+
 cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
-                                  void* a3, const float* wsc, float* sc_out, const float* x2, int CI2, cudaStream_t stream) {
+                                  void* a3, const float* wsc, float* sc_out, const float* x2, int CI2, int sms,
+                                  cudaStream_t stream) {
   if ((x2 == nullptr) != (CI2 == 0) || CI2 < 0 || CI2 >= CI || (reinterpret_cast<uintptr_t>(x2) & 15) != 0) return cudaErrorInvalidValue;
   int threads = ((T + 3) / 4 + 31) / 32 * 32;          // one segment of 4*threads positions at a time
   if (threads > 128) threads = 128;
@@ -368,6 +374,13 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
   if ((wsc == nullptr) != (sc_out == nullptr) || (reinterpret_cast<uintptr_t>(sc_out) & 15) != 0) return cudaErrorInvalidValue;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorInvalidValue;
+  // Tensor-core kernel (csrc/stg_tcn_mma.cu) for rows of up to 512 positions with T % 4 == 0; the FFMA kernel below keeps
+  // the other shapes (T % 4 == 2, long segmented rows).  UPD_TCN_IMPL=ffma forces the FFMA kernel (measurement / tests).
+  static const bool ffma_env = getenv("UPD_TCN_IMPL") && getenv("UPD_TCN_IMPL")[0] == 'f';
+  if (!ffma_env) {
+    cudaError_t e = upd_launch_stg_tcn_mma(x, w1, b1, w2, b2, gamma, beta, N, CI, C, T, hn, a3, wsc, sc_out, x2, CI - CI2, sms, stream);
+    if (e != cudaErrorNotSupported) return e;
+  }
   const int rpc = N >= 8192 ? 8 : 1;                   // rows per CTA: amortises the weight staging on big launches
   const unsigned grid = (unsigned)((N + rpc - 1) / rpc);
 #define UPD_TCN_LAUNCH(CC, XX)                                                                                         \
