@@ -12,16 +12,18 @@
 // other kernels use: x = hi + lo (fp16 each; values below fp16's normal range keep an absolute error of 2^-25), three
 // MMAs per tile (lo*hi + hi*lo + hi*hi); ~1e-6 of the output rms against the fp32 library convolution.
 //
-// The split is done ONCE per element, on the way into shared memory: a shared-memory word pair holds the packed fp16
-// hi parts and the packed lo parts of two adjacent channels at one position -- exactly one A-fragment register each --
-// so the inner loop is 8-byte shared loads and MMAs only (the first version split tf32 operands in the loop: 46 warp
-// instructions per position, 11 % of them MMAs).
+// The split is done ONCE per element, on the way into shared memory, into an fp16 hi plane and an fp16 lo plane laid out
+// position-major ([position][channel], 16-byte chunks of 8 channels, XOR-swizzled by the position so that any 8
+// consecutive positions hit 8 different bank groups).  A tap is then only a row offset, and ONE ldmatrix.x4 per plane
+// delivers the four A-fragment registers of a 16 x 16 tile in the order the MMA wants them: the inner loop is two
+// ldmatrix + one 16-byte weight load per six MMAs.  (History, profiles/r02_tcn_*: tf32 operands split inside the loop,
+// 46 warp instructions per position, 11 % MMAs, 1.25x over the FFMA kernel; fp16 {hi, lo} word pairs per channel pair,
+// 8-byte loads, 38 instructions per position -- a third of them register moves that gather the fragments -- 2.15x.)
 //
 // One CTA (4 warps) walks rows n = blockIdx.x, + gridDim.x, ...:
-//   load x[n], split -> shared [c_in / 2][TP] (4 zero halo columns in front: both convolutions are causal, zero-padded)
-//   phase 1: every warp takes pairs of 16-position tiles; A fragments = four 8-byte shared loads per K-slice (row pitch
-//            = 4 mod 16 pairs: conflict-free), B fragments = one 16-byte load per lane of the pre-split weights; the
-//            accumulator fragment of a thread IS a channel pair at one position: h1 is split and stored the same way
+//   load x[n], split -> shared planes (4 zero halo rows in front: both convolutions are causal and zero-padded)
+//   phase 1: every warp takes pairs of 16-position tiles; the accumulator fragment of a thread IS a channel pair at two
+//            positions: h1 is split and stored into its own hi / lo planes with 4-byte stores (conflict-free)
 //   phase 2: the same on h1; LayerNorm over the channels of a position = the thread's own columns + two shuffles over the
 //            four lanes that share a row; result -> shared staging
 //   copy-out: coalesced stores of the fp32 row, or of the fp16 split operand [hi | lo | hi | 1 1 0..] of the
@@ -39,6 +41,7 @@ namespace {
 constexpr int TCN_WARPS = 4;
 constexpr int TCN_THREADS = TCN_WARPS * 32;
 constexpr int MT = 2;                        // position tiles a warp holds at once (B fragments are reused across them)
+constexpr int HALO = 4;                      // zero rows in front of position 0
 
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile(
@@ -46,12 +49,29 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr) : "memory");
+  r[2] = 0u;
+  r[3] = 0u;
+}
 
 // {packed fp16 hi parts, packed fp16 lo parts} of two values adjacent in K (the even one in the low half)
 __device__ __forceinline__ uint2 split_pair(float a, float b) {
   uint2 r;
   tc::split_f16x2(a, b, r.x, r.y);
   return r;
+}
+
+// 16-byte chunk (8 channels) `c` of position row `row` in a plane of NC chunks per row
+template <int NC>
+__device__ __forceinline__ int swz(int c, int row) {
+  if (NC == 2) return c ^ ((row >> 2) & 1);
+  if (NC == 4) return c ^ ((row >> 1) & 3);
+  return c;
 }
 
 // acc[m] += A[m] * B over one K-slice of 16, three passes, small terms first.  w = {hi(b0), hi(b1), lo(b0), lo(b1)}
@@ -64,23 +84,19 @@ __device__ __forceinline__ void mma3(float (&acc)[MT][4], const uint32_t (&ahi)[
   for (int m = 0; m < MT; ++m) mma_f16(acc[m], ahi[m], w.x, w.y);
 }
 
-// A fragments (hi / lo) of MT position tiles for one K-slice: src [channel pairs][TP] of {hi, lo} words, position p at
-// column p + 4; p0 points at (first pair of the slice + tig, column P0 + g + tap + 2).  HALF: only the first 8 channels of
-// the slice exist (the other fragment registers are zero).
-template <bool HALF>
-__device__ __forceinline__ void load_a(const uint2* __restrict__ p0, int TP, uint32_t (&ahi)[MT][4], uint32_t (&alo)[MT][4]) {
+// A fragments (hi / lo) of MT position tiles; off = this lane's byte offset inside a plane for the slice's first tile
+// (row, swizzled chunk -- tile bases are multiples of 16 rows, which the swizzle does not see), PITCH = bytes per row.
+// NC == 1: the plane holds 8 channels only (the upper half of the fragment is zero).
+template <int NC>
+__device__ __forceinline__ void load_a(uint32_t hi_plane, uint32_t lo_plane, uint32_t off, uint32_t (&ahi)[MT][4], uint32_t (&alo)[MT][4]) {
 #pragma unroll
   for (int m = 0; m < MT; ++m) {
-    const uint2* p = p0 + 16 * m;
-    const uint2 v0 = p[0], v1 = p[8];
-    ahi[m][0] = v0.x; alo[m][0] = v0.y;
-    ahi[m][1] = v1.x; alo[m][1] = v1.y;
-    if (HALF) {
-      ahi[m][2] = alo[m][2] = ahi[m][3] = alo[m][3] = 0u;
+    if (NC == 1) {
+      ldsm_x2(ahi[m], hi_plane + off + m * 16 * 16);
+      ldsm_x2(alo[m], lo_plane + off + m * 16 * 16);
     } else {
-      const uint2 v2 = p[4 * TP], v3 = p[4 * TP + 8];
-      ahi[m][2] = v2.x; alo[m][2] = v2.y;
-      ahi[m][3] = v3.x; alo[m][3] = v3.y;
+      ldsm_x4(ahi[m], hi_plane + off + m * 16 * (16 * NC));
+      ldsm_x4(alo[m], lo_plane + off + m * 16 * (16 * NC));
     }
   }
 }
@@ -103,24 +119,31 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
     const float* __restrict__ x2, int CI1) {
   constexpr int NT = (C + 7) / 8;            // n-tiles of 8 output channels
   constexpr int CP = NT * 8;                 // c_out padded
-  constexpr bool HALF2 = (C <= 8);           // phase 2 reads 8 channels of h1
-  constexpr int XPAIRS = HALF1 ? 4 : 8 * KS; // channel pairs of x held in shared memory
-  constexpr int HPAIRS = HALF2 ? 4 : 8;
+  constexpr int NCX = HALF1 ? 1 : 2 * KS;    // 16-byte chunks (8 channels) per position row of the x planes
+  constexpr int NCH = (C <= 8) ? 1 : 2;      // ... of the h1 planes
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int pairs = (T + 16 * MT - 1) / (16 * MT);              // pairs of 16-position tiles in a row
   const int TPAD = pairs * 16 * MT;
-  const int TP = TPAD + 4;                   // pitch in {hi, lo} word pairs, = 4 mod 16: conflict-free 8-byte fragment loads
+  const int ROWS = TPAD + HALO;
   const int TPO = TPAD + 4;                  // staging pitch in floats, = 4 mod 32: conflict-free fragment stores
-  uint2* sx = reinterpret_cast<uint2*>(smem_raw);               // [XPAIRS][TP]
-  uint2* sh = sx + XPAIRS * TP;              // [HPAIRS][TP]
-  float* so = reinterpret_cast<float*>(sh + HPAIRS * TP);       // [CP][TPO]
-  uint4* sw1 = reinterpret_cast<uint4*>(so + CP * TPO);         // [3][KS][NT][32]
+  // x planes and the fp32 output staging share one region (the planes are dead once phase 1 is done); the raw fp32 row of
+  // the NEXT unit of work arrives by cp.async into its own buffer while this one is being computed
+  const int XPL = ROWS * NCX * 16;           // bytes of one x plane
+  const int XREG = (2 * XPL > CP * TPO * 4) ? 2 * XPL : CP * TPO * 4;
+  unsigned char* sxh = smem_raw;             // [ROWS][NCX * 16 B] hi plane of x
+  unsigned char* sxl = sxh + XPL;
+  float* so = reinterpret_cast<float*>(smem_raw);               // [CP][TPO], aliases the x planes
+  unsigned char* shh = smem_raw + XREG;      // [ROWS][NCH * 16 B] hi plane of h1
+  unsigned char* shl = shh + ROWS * NCH * 16;
+  float* sraw = reinterpret_cast<float*>(shl + ROWS * NCH * 16);   // [CI][T] fp32, as in global memory
+  uint4* sw1 = reinterpret_cast<uint4*>(sraw + CI * T);         // [3][KS][NT][32]
   uint4* sw2 = sw1 + 3 * KS * NT * 32;       // [3][NT][32]
   uint4* swsc = sw2 + 3 * NT * 32;           // [KS][NT][32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+  const uint32_t xh_a = tc::smem_u32(sxh), xl_a = tc::smem_u32(sxl), hh_a = tc::smem_u32(shh), hl_a = tc::smem_u32(shl);
 
-  // ---- once per CTA: zero the activation buffers (halo, tail and padding rows stay zero), split the weights ----
-  for (int i = tid; i < (XPAIRS + HPAIRS) * TP; i += TCN_THREADS) sx[i] = make_uint2(0u, 0u);
+  // ---- once per CTA: zero the activation planes (halo, tail and padding channels stay zero), split the weights ----
+  for (int i = tid; i < (XREG + ROWS * NCH * 32) / 16; i += TCN_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0u, 0u, 0u, 0u);
   for (int i = tid; i < 3 * KS * NT * 32; i += TCN_THREADS) {
     const int l = i & 31, nt = (i >> 5) % NT, s = (i >> 5) / NT, ks = s % KS, tap = s / KS;
     sw1[i] = pack_b<C>(w1, CI, 3, tap, nt, ks * 16, l);
@@ -149,41 +172,73 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
     }
   const int Q = T >> 2;                      // float4 groups per channel row (T % 4 == 0)
   const int K = C * T;
-  const int items = ((CI + 1) >> 1) * Q;     // (channel pair, group of 4 positions) units of the x load
-  __syncthreads();                           // the zero fill is complete before the first row lands on top of it
+  // ldmatrix row addresses of this lane (matrix j = lane / 8, row r = lane % 8 of it) per tap and K-slice, and the h1 store
+  // offsets of its accumulator fragment, relative to a tile base
+  uint32_t aoff1[3][KS], aoff2[3], hoff[NT][2];
+  {
+    const int j = lane >> 3, r = lane & 7;
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      const int row = r + 8 * (j & 1) + tap + HALO - 2;
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) aoff1[tap][ks] = (uint32_t)(row * (16 * NCX) + swz<NCX>(NCX == 1 ? 0 : 2 * ks + (j >> 1), row) * 16);
+      aoff2[tap] = (uint32_t)(row * (16 * NCH) + swz<NCH>(NCH == 1 ? 0 : (j >> 1), row) * 16);
+    }
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = g + 8 * h + HALO;
+        hoff[nt][h] = (uint32_t)(row * (16 * NCH) + swz<NCH>(nt, row) * 16 + tig * 4);
+      }
+  }
+  const uint32_t raw_a = tc::smem_u32(sraw);
+  // raw fp32 row of unit n -> shared, asynchronously (16-byte cp.async, a warp per channel, lanes along the positions)
+  auto prefetch = [&](long long n) {
+    const float* xr = x + n * (long long)CI1 * T;
+    const float* xr2 = x2 ? x2 + n * (long long)(CI - CI1) * T - (long long)CI1 * T : xr;   // indexed by the channel of the concatenation
+    for (int ch = warp; ch < CI; ch += TCN_WARPS) {
+      const float* src = (ch < CI1 ? xr : xr2) + ch * T;
+      for (int q = lane; q < Q; q += 32)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_a + (uint32_t)(ch * T + 4 * q) * 4u), "l"(src + 4 * q) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if ((long long)blockIdx.x < N) prefetch(blockIdx.x);
+  __syncthreads();                           // the zero fill is complete
 
   for (long long n = blockIdx.x; n < N; n += gridDim.x) {
-    // ---- x[n] -> split -> shared: all global loads of a batch are issued before the first is consumed ----
-    const float* xr = x + n * (long long)CI1 * T;
-    const float* xr2 = x2 ? x2 + n * (long long)(CI - CI1) * T : nullptr;
-    constexpr int U = 4;
-    for (int i0 = tid; i0 < items; i0 += TCN_THREADS * U) {
-      float4 va[U], vb[U];
-      int dst[U];
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                         // the raw row is visible; the previous row's copy-out has left the staging
+    // ---- split -> x planes: a lane owns one position and 8 channels (conflict-free 4-byte reads of the raw row, one
+    //      16-byte store per plane).  The planes are rewritten completely (padding channels, tail and halo rows are
+    //      zeros): the output staging of the previous row lived in the same memory. ----
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = i0 + u * TCN_THREADS;
-        dst[u] = -1;
-        va[u] = vb[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (i < items) {
-          const int cp = i / Q, q = i - cp * Q, c0 = 2 * cp, c1 = c0 + 1;
-          dst[u] = cp * TP + 4 + 4 * q;
-          va[u] = __ldg(reinterpret_cast<const float4*>((c0 < CI1 ? xr + (long long)c0 * T : xr2 + (long long)(c0 - CI1) * T) + 4 * q));
-          if (c1 < CI)
-            vb[u] = __ldg(reinterpret_cast<const float4*>((c1 < CI1 ? xr + (long long)c1 * T : xr2 + (long long)(c1 - CI1) * T) + 4 * q));
+    for (int o = 0; o < NCX; ++o) {
+      const int nch = CI - 8 * o;            // channels of this octet that exist (<= 0: padding)
+      for (int p = (warp << 5) + lane; p < TPAD; p += TCN_WARPS * 32) {
+        float v[8];
+        const float* rp = sraw + 8 * o * T + p;
+        if (p < T && nch >= 8) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = rp[j * T];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = (j < nch && p < T) ? rp[j * T] : 0.0f;
         }
+        const uint2 e0 = split_pair(v[0], v[1]), e1 = split_pair(v[2], v[3]), e2 = split_pair(v[4], v[5]), e3 = split_pair(v[6], v[7]);
+        const int row = p + HALO;
+        const int off = row * (NCX * 16) + swz<NCX>(o, row) * 16;
+        *reinterpret_cast<uint4*>(sxh + off) = make_uint4(e0.x, e1.x, e2.x, e3.x);
+        *reinterpret_cast<uint4*>(sxl + off) = make_uint4(e0.y, e1.y, e2.y, e3.y);
       }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (dst[u] >= 0) {
-          const uint2 e0 = split_pair(va[u].x, vb[u].x), e1 = split_pair(va[u].y, vb[u].y);
-          const uint2 e2 = split_pair(va[u].z, vb[u].z), e3 = split_pair(va[u].w, vb[u].w);
-          uint4* d = reinterpret_cast<uint4*>(sx + dst[u]);
-          d[0] = make_uint4(e0.x, e0.y, e1.x, e1.y);
-          d[1] = make_uint4(e2.x, e2.y, e3.x, e3.y);
-        }
+    }
+    if (tid < HALO * NCX) {
+      *reinterpret_cast<uint4*>(sxh + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
+      *reinterpret_cast<uint4*>(sxl + tid * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
     __syncthreads();
+    if (n + gridDim.x < N) prefetch(n + gridDim.x);      // in flight during both phases and the copy-out
     // ---- phase 1: h1 = conv3(x) + b1 (and the 1x1 shortcut from the tap-2 fragments) ----
     for (int pi = warp; pi < pairs; pi += TCN_WARPS) {
       const int P0 = pi * 16 * MT;
@@ -196,13 +251,12 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
           acc[nt][m][1] = acc[nt][m][3] = b1r[nt][1];
           scv[nt][m][0] = scv[nt][m][1] = scv[nt][m][2] = scv[nt][m][3] = 0.0f;
         }
-      const uint2* pa = sx + tig * TP + P0 + g + 2;
 #pragma unroll
       for (int tap = 0; tap < 3; ++tap)
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
           uint32_t ahi[MT][4], alo[MT][4];
-          load_a<HALF1>(pa + ks * 8 * TP + tap, TP, ahi, alo);
+          load_a<NCX>(xh_a, xl_a, aoff1[tap][ks] + (uint32_t)(P0 * (16 * NCX)), ahi, alo);
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) mma3(acc[nt], ahi, alo, sw1[((tap * KS + ks) * NT + nt) * 32 + lane]);
           if (tap == 2 && wsc) {
@@ -210,14 +264,17 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
             for (int nt = 0; nt < NT; ++nt) mma3(scv[nt], ahi, alo, swsc[(ks * NT + nt) * 32 + lane]);
           }
         }
-      // the accumulator fragment holds channel pair nt*4 + tig at positions g and g + 8: h1 in the operand layout
+      // the accumulator fragment holds channels nt*8 + 2*tig, +1 at positions g and g + 8: h1 in the operand layout
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt)
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          uint2* d = sh + (nt * 4 + tig) * TP + 4 + P0 + 16 * m + g;
-          d[0] = split_pair(acc[nt][m][0], acc[nt][m][1]);
-          d[8] = split_pair(acc[nt][m][2], acc[nt][m][3]);
+          const uint2 ea = split_pair(acc[nt][m][0], acc[nt][m][1]), eb = split_pair(acc[nt][m][2], acc[nt][m][3]);
+          const uint32_t tb = (uint32_t)((P0 + 16 * m) * (16 * NCH));
+          *reinterpret_cast<uint32_t*>(shh + tb + hoff[nt][0]) = ea.x;
+          *reinterpret_cast<uint32_t*>(shl + tb + hoff[nt][0]) = ea.y;
+          *reinterpret_cast<uint32_t*>(shh + tb + hoff[nt][1]) = eb.x;
+          *reinterpret_cast<uint32_t*>(shl + tb + hoff[nt][1]) = eb.y;
         }
       if (wsc) {
         float* so_g = sc_out + n * (long long)K;
@@ -244,11 +301,10 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
           acc[nt][m][0] = acc[nt][m][2] = b2r[nt][0];
           acc[nt][m][1] = acc[nt][m][3] = b2r[nt][1];
         }
-      const uint2* pa = sh + tig * TP + P0 + g + 2;
 #pragma unroll
       for (int tap = 0; tap < 3; ++tap) {
         uint32_t ahi[MT][4], alo[MT][4];
-        load_a<HALF2>(pa + tap, TP, ahi, alo);
+        load_a<NCH>(hh_a, hl_a, aoff2[tap] + (uint32_t)(P0 * (16 * NCH)), ahi, alo);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) mma3(acc[nt], ahi, alo, sw2[(tap * NT + nt) * 32 + lane]);
       }
@@ -287,38 +343,37 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
         }
     }
     __syncthreads();
-    // ---- copy-out ----
+    // ---- copy-out: a warp per channel row, lanes along the positions ----
     if (a3 == nullptr) {
       float* out = hn + n * (long long)K;
-      for (int i = tid; i < C * Q; i += TCN_THREADS) {
-        const int c = i / Q, q = i - c * Q;
-        *reinterpret_cast<float4*>(out + c * T + 4 * q) = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
-      }
+      for (int c = warp; c < C; c += TCN_WARPS)
+        for (int q = lane; q < Q; q += 32)
+          *reinterpret_cast<float4*>(out + c * T + 4 * q) = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
     } else {
       // the row as the split operand [hi | lo | hi | 1 1 0..] (K = C*T) of the fp16 tensor-core GEMM that follows
       __half* row = a3 + n * (long long)(3 * K + 8);
-      for (int i = tid; i < C * Q; i += TCN_THREADS) {
-        const int c = i / Q, q = i - c * Q;
-        const float4 v = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
-        const uint2 e01 = split_pair(v.x, v.y), e23 = split_pair(v.z, v.w);
-        const uint2 hi = make_uint2(e01.x, e23.x), lo = make_uint2(e01.y, e23.y);
-        const int col = c * T + 4 * q;
-        *reinterpret_cast<uint2*>(row + col) = hi;
-        *reinterpret_cast<uint2*>(row + K + col) = lo;
-        *reinterpret_cast<uint2*>(row + 2 * K + col) = hi;
-      }
+      for (int c = warp; c < C; c += TCN_WARPS)
+        for (int q = lane; q < Q; q += 32) {
+          const float4 v = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
+          const uint2 e01 = split_pair(v.x, v.y), e23 = split_pair(v.z, v.w);
+          const uint2 hi = make_uint2(e01.x, e23.x), lo = make_uint2(e01.y, e23.y);
+          __half* d = row + c * T + 4 * q;
+          *reinterpret_cast<uint2*>(d) = hi;
+          *reinterpret_cast<uint2*>(d + K) = lo;
+          *reinterpret_cast<uint2*>(d + 2 * K) = hi;
+        }
       if (tid == 0) *reinterpret_cast<uint4*>(row + 3 * K) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
     }
-    // the next row's x load touches sx only; phase 1 (writes sh) and phase 2 (writes so) start behind its barriers
   }
 }
 
 template <int C, int KS, bool HALF1>
-size_t tcn_mma_smem(int T) {
+size_t tcn_mma_smem(int CI, int T) {
   constexpr int NT = (C + 7) / 8, CP = NT * 8;
-  constexpr int XPAIRS = HALF1 ? 4 : 8 * KS, HPAIRS = (C <= 8) ? 4 : 8;
-  const int pairs = (T + 16 * MT - 1) / (16 * MT), TPAD = pairs * 16 * MT, TP = TPAD + 4, TPO = TPAD + 4;
-  return sizeof(uint2) * (size_t)(XPAIRS + HPAIRS) * TP + sizeof(float) * (size_t)CP * TPO +
+  constexpr int NCX = HALF1 ? 1 : 2 * KS, NCH = (C <= 8) ? 1 : 2;
+  const int pairs = (T + 16 * MT - 1) / (16 * MT), TPAD = pairs * 16 * MT, ROWS = TPAD + HALO, TPO = TPAD + 4;
+  const size_t xpl = (size_t)ROWS * NCX * 32, st = sizeof(float) * (size_t)CP * TPO;
+  return (xpl > st ? xpl : st) + (size_t)ROWS * NCH * 32 + sizeof(float) * (size_t)CI * T +
          sizeof(uint4) * 32 * ((size_t)3 * KS * NT + 3 * NT + KS * NT);
 }
 
@@ -326,7 +381,7 @@ template <int C, int KS, bool HALF1>
 cudaError_t launch_tcn_mma(const float* x, const float* w1, const float* b1, const float* w2, const float* b2,
                            const float* gamma, const float* beta, long long N, int CI, int T, float* hn, void* a3,
                            const float* wsc, float* sc_out, const float* x2, int CI1, int sms, cudaStream_t stream) {
-  const size_t smem = tcn_mma_smem<C, KS, HALF1>(T);
+  const size_t smem = tcn_mma_smem<C, KS, HALF1>(CI, T);
   if (smem > 110 * 1024) return cudaErrorNotSupported;      // below two CTAs per SM the FFMA kernel's segmented walk is the better fit
   auto kern = stg_tcn_mma_kernel<C, KS, HALF1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -360,6 +415,10 @@ cudaError_t upd_launch_stg_tcn_mma(const float* x, const float* w1, const float*
                                    void* a3, const float* wsc, float* sc_out, const float* x2, int CI1, int sms,
                                    cudaStream_t stream) {
   if ((T & 3) != 0 || T < 4 || T > 512 || CI < 1 || CI > 32) return cudaErrorNotSupported;
+  // measured against the FFMA kernel (profiles/r02_tcn_mma.txt): 2.0-2.5x on the 16-channel blocks, 1.2x at 8 -> 8 channels,
+  // level at 4 -> 8 and slower at c_out = 4 (one n-tile is half empty and the MMAs are a minor part of the pass)
+  static const bool force = getenv("UPD_TCN_IMPL") && getenv("UPD_TCN_IMPL")[0] == 'm';
+  if (!force && (C < 8 || CI < 8)) return cudaErrorNotSupported;
   switch (C) {
     case 4: return dispatch_ci<4>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, hn, a3, wsc, sc_out, x2, CI1, sms, stream);
     case 8: return dispatch_ci<8>(x, w1, b1, w2, b2, gamma, beta, N, CI, T, hn, a3, wsc, sc_out, x2, CI1, sms, stream);
