@@ -298,10 +298,20 @@ int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const 
  *   shortcut bias + t_conv(emb(step)); b2_dev [C]; gamma/beta [C].  Exactly one of hn_dev (fp32) and a3_dev (the row as the
  *   fp16 split operand [N, 3*C*T+8] of the down-sampling GEMM, see the f(x) section) is written; the other is NULL.  wsc_dev [C, CI] / sc_dev [N, C, T] (both or neither): the block's 1x1 shortcut W_sc x
  *   (ugnet.py:129) evaluated in the same pass.  Limits: C in {4, 8, 16}, T even (any length: a row is walked in
- *   segments of 512 positions; T % 4 != 0 takes scalar global accesses). */
+ *   segments of 512 positions; T % 4 != 0 takes scalar global accesses).  Rows of T % 4 == 0, T <= 512 positions with
+ *   C >= 8 and 8 <= CI <= 32 run on the warp-MMA kernel (csrc/stg_tcn_mma.cu: fp16 hi/lo split operands, fp32 accumulate,
+ *   ~1e-6 of the output rms from the fp32 FFMA kernel that keeps every other shape). */
 int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
                    const float* gamma_dev, const float* beta_dev, long long N, int CI, int C, int T, float* hn_dev,
                    void* a3_dev, const float* wsc_dev, float* sc_dev, void* stream);
+
+/* upd_stg_conv1d -- replaces the narrow convolutions of UGnet along the time axis: DownSample's Conv2d(c, c, (1,3), (1,2), (0,1))
+ *   (models/Diffusion_model/DiffSTG/ugnet.py:152), UpSample's ConvTranspose2d(c, c, (1,4), (1,2), (0,1)) (:171) and the 1x1
+ *   x_proj / out.0 projections (:245-246).  x_dev [N, CI, Tin] -> y_dev [N, CO, Tout] with
+ *   Tout = (Tin + 2 pad - K) / stride + 1 (transposed == 0, w_dev [CO, CI, K]) or (Tin - 1) stride - 2 pad + K
+ *   (transposed == 1, w_dev [CI, CO, K] as nn.ConvTranspose2d stores it); b_dev [CO] or NULL.  Limit: CI*K*CO <= 12288. */
+int upd_stg_conv1d(const float* x_dev, const float* w_dev, const float* b_dev, long long N, int CI, int CO, int Tin, int K,
+                   int stride, int pad, int transposed, float* y_dev, void* stream);
 
 /* upd_stg_tcn_ln_cat -- upd_stg_tcn_ln on the channel concatenation cat(x_dev [N, CI1, T], x2_dev [N, CI2, T]) of the
  *   U-Net's up path (`x = torch.cat((x, s), dim=1)`, models/Diffusion_model/DiffSTG/ugnet.py:288-289), read from the two

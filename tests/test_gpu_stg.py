@@ -207,3 +207,23 @@ def test_fused_tcn_kernel_reads_a_skip_concatenation_in_place(C, CI1, CI2, T, N)
     _lib.check(L.upd_stg_tcn_ln_cat(_lib.ptr(x1), CI1, _lib.ptr(x2), CI2, *tail, N, C, T, None, _lib.ptr(a3), None, None, st), "d")
     assert torch.equal(hn, ref_hn) and torch.equal(sc, ref_sc) and torch.equal(a3, ref_a3)
     assert L.upd_stg_tcn_ln_cat(_lib.ptr(x1), CI1, None, CI2, *tail, N, C, T, _lib.ptr(hn), None, None, None, st) == 1   # bad arg
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("CI,CO,T,k,stride,pad,transposed", [(1, 4, 400, 1, 1, 0, False), (4, 1, 400, 1, 1, 0, False), (8, 8, 400, 3, 2, 1, False),
+                                                            (8, 8, 200, 4, 2, 1, True), (16, 16, 50, 4, 2, 1, True), (12, 20, 37, 3, 2, 1, False),
+                                                            (3, 5, 9, 4, 2, 1, True)])
+def test_narrow_convolution_kernel_against_library_ops(CI, CO, T, k, stride, pad, transposed):
+    """upd_stg_conv1d == F.conv1d / F.conv_transpose1d (fp32, TF32 off): x_proj / out.0 / DownSample / UpSample shapes."""
+    import torch.nn.functional as F
+    from updgm_b200.diffstg import conv1d_time
+    torch.manual_seed(CI * 100 + CO)
+    N = 300
+    x = torch.randn(N, CI, T, device=DEV)
+    w = torch.randn(*((CI, CO, k) if transposed else (CO, CI, k)), device=DEV) * 0.3
+    b = torch.randn(CO, device=DEV)
+    with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+        ref = (F.conv_transpose1d if transposed else F.conv1d)(x, w, b, stride=stride, padding=pad)
+    out = conv1d_time(x, w, b, k, stride=stride, pad=pad, transposed=transposed)
+    assert tuple(out.shape) == tuple(ref.shape)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)

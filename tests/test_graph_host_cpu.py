@@ -49,6 +49,11 @@ class _StandInLib:
             out.copy_(y0)
         return 0
 
+    def upd_stg_conv1d(self, x, w, b, N, CI, CO, Tin, k, stride, pad, transposed, y, st):
+        fn = F.conv_transpose1d if transposed else F.conv1d
+        y.copy_(fn(x, w, b, stride=stride, padding=pad))
+        return 0
+
     def upd_stg_posterior(self, xt, pred, z, n, a, b, c, out, st):
         a, b, c = (torch.tensor(v, dtype=torch.float32) for v in (a, b, c))
         out.copy_(a * (xt - b * pred) + c * (z if z is not None else pred))

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_build.build_library())
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.lib().upd_abi_version() == _lib.ABI_VERSION == 7
+    assert _lib.lib().upd_abi_version() == _lib.ABI_VERSION == 8
     assert _lib.lib().upd_error_string(2) == b"unsupported shape"
 
 

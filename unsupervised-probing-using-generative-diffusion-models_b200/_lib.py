@@ -13,10 +13,10 @@ SYMBOLS = (
     "upd_error_string", "upd_last_cuda_error", "upd_abi_version", "upd_denoiser_pack_bytes", "upd_denoiser_pack",
     "upd_nsdiff_sample", "upd_tmdm_sample", "upd_mpv_scratch_bytes", "upd_mpv_reduce", "upd_gram_centered", "upd_prediction_error", "upd_sigma_estimation",
     "upd_dts_ddim_step", "upd_dts_adagrad_step", "upd_dts_infill", "upd_gauss_fill",
-    "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_dts_attention", "upd_dts_attention_bwd", "upd_dts_layernorm", "upd_dts_layernorm_bwd", "upd_stg_posterior", "upd_nsx_step", "upd_stg_gated_aggregate", "upd_stg_tcn_ln", "upd_stg_tcn_ln_cat", "upd_fx_split", "upd_gemm3", "upd_fx_add_ln_split", "upd_fx_attention", "upd_fx_attention_hs16", "upd_fx_embed_split",
+    "upd_dts_fourier_topk", "upd_dts_fourier_topk_bwd", "upd_dts_attention", "upd_dts_attention_bwd", "upd_dts_layernorm", "upd_dts_layernorm_bwd", "upd_stg_posterior", "upd_nsx_step", "upd_stg_gated_aggregate", "upd_stg_tcn_ln", "upd_stg_tcn_ln_cat", "upd_stg_conv1d", "upd_fx_split", "upd_gemm3", "upd_fx_add_ln_split", "upd_fx_attention", "upd_fx_attention_hs16", "upd_fx_embed_split",
 )
 
-ABI_VERSION = 7     # = UPD_ABI_VERSION of the csrc/ this binding was written against (argument lists below)
+ABI_VERSION = 8     # = UPD_ABI_VERSION of the csrc/ this binding was written against (argument lists below)
 KIND_NSDIFF, KIND_TMDM = 0, 1
 IMPL_TCGEN05, IMPL_SIMT, IMPL_TCGEN05_X2, IMPL_TCGEN05_WS = 0, 1, 2, 4
 _fp = ctypes.POINTER(ctypes.c_float)
@@ -113,6 +113,8 @@ def lib():
     L.upd_stg_tcn_ln.argtypes = [vp, vp, vp, vp, vp, vp, vp, ll, i, i, i, vp, vp, vp, vp, vp]
     L.upd_stg_tcn_ln_cat.restype = ctypes.c_int
     L.upd_stg_tcn_ln_cat.argtypes = [vp, i, vp, i, vp, vp, vp, vp, vp, vp, ll, i, i, vp, vp, vp, vp, vp]
+    L.upd_stg_conv1d.restype = ctypes.c_int
+    L.upd_stg_conv1d.argtypes = [vp, vp, vp, ll, i, i, i, i, i, i, i, vp, vp]
     _LIB = L
     return L
 

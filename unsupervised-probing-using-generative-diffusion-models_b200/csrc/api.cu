@@ -42,6 +42,8 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
                                   const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
                                   void* a3, const float* wsc, float* sc_out, const float* x2, int CI2, int sms,
                                   cudaStream_t stream);
+cudaError_t upd_launch_stg_conv1d(const float* x, const float* w, const float* b, long long N, int CI, int CO, int Tin, int Tout,
+                                   int K, int stride, int pad, int transposed, float* y, cudaStream_t stream);
 cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, int L, int act, void* a3, cudaStream_t stream);
 cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const float* g1, const float* b1,
                                        const float* g2, const float* b2, long long rows, int K, float* y, void* a3,
@@ -434,6 +436,19 @@ int upd_stg_tcn_ln_cat(const float* x_dev, int CI1, const float* x2_dev, int CI2
   UPD_DEVICE_OR_RETURN();
   UPD_FINISH(upd_launch_stg_tcn_ln(x_dev, w1_dev, b1_dev, w2_dev, b2_dev, gamma_dev, beta_dev, N, CI1 + CI2, C, T, hn_dev,
                                    a3_dev, wsc_dev, sc_dev, x2_dev, CI2, sms, (cudaStream_t)stream));
+}
+
+int upd_stg_conv1d(const float* x_dev, const float* w_dev, const float* b_dev, long long N, int CI, int CO, int Tin, int K,
+                   int stride, int pad, int transposed, float* y_dev, void* stream) {
+  if (!x_dev || !w_dev || !y_dev || N <= 0 || CI < 1 || CO < 1 || Tin < 1 || K < 1 || stride < 1 || pad < 0)
+    return UPD_ERR_BAD_ARG;
+  const int Tout = transposed ? (Tin - 1) * stride - 2 * pad + K : (Tin + 2 * pad - K) / stride + 1;
+  if (Tout < 1) return UPD_ERR_BAD_ARG;
+  if ((long long)CI * K * CO > 12288) return UPD_ERR_UNSUPPORTED;
+  UPD_DEVICE_OR_RETURN();
+  (void)sms;
+  UPD_FINISH(upd_launch_stg_conv1d(x_dev, w_dev, b_dev, N, CI, CO, Tin, Tout, K, stride, pad, transposed, y_dev,
+                                   (cudaStream_t)stream));
 }
 
 int upd_gram_centered(const float* traj_dev, int n_win, int K, int D, double* gram_dev, void* stream) {

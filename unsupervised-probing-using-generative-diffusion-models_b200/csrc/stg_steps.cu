@@ -320,6 +320,53 @@ __global__ void nsx_step_kernel(const float* __restrict__ e, const float* __rest
   }
 }
 
+
+// Narrow convolutions of the U-Net along the time axis (ugnet.py:152 DownSample Conv2d (1,3)/(1,2)/(0,1), :171 UpSample
+// ConvTranspose2d (1,4)/(1,2)/(0,1), :245-246 the 1x1 x_proj / out.0): x [N, CI, Tin] -> y [N, CO, Tout], a handful of
+// channels, so a thread owns one output position and up to 8 output channels; weights broadcast from shared memory.
+//   transposed == 0:  y[co][t] = b[co] + sum_ci sum_k w[co][ci][k] * x[ci][t*stride + k - pad]
+//   transposed == 1:  y[co][t] = b[co] + sum_ci sum_k w[ci][co][k] * x[ci][(t + pad - k) / stride]   (where divisible)
+// HBM / L2-bound (a few FMAs per byte).  These were cuDNN implicit-GEMM / dgrad / magma launches (10 % of a DiffSTG step).
+__global__ void __launch_bounds__(128) stg_conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                         const float* __restrict__ b, int CI, int CO, int Tin, int Tout,
+                                                         int K, int stride, int pad, int transposed, float* __restrict__ y) {
+  extern __shared__ float sw[];                       // [CI][K][CO]: channels-out contiguous
+  for (int i = threadIdx.x; i < CI * K * CO; i += blockDim.x) {
+    const int co = i % CO, r = i / CO, k = r % K, ci = r / K;
+    sw[i] = transposed ? w[(ci * CO + co) * K + k] : w[(co * CI + ci) * K + k];
+  }
+  __syncthreads();
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= Tout) return;
+  const long long n = blockIdx.y;
+  const float* xr = x + n * (long long)CI * Tin;
+  float* yr = y + n * (long long)CO * Tout;
+  for (int c0 = 0; c0 < CO; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = (b && c0 + j < CO) ? b[c0 + j] : 0.0f;
+    for (int ci = 0; ci < CI; ++ci)
+      for (int k = 0; k < K; ++k) {
+        int src;
+        if (!transposed) {
+          src = t * stride + k - pad;
+        } else {
+          const int u = t + pad - k;
+          src = (u >= 0 && u % stride == 0) ? u / stride : -1;
+        }
+        if (src < 0 || src >= Tin) continue;
+        const float xv = __ldg(xr + ci * Tin + src);
+        const float* wk = sw + (ci * K + k) * CO + c0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (c0 + j < CO) acc[j] = fmaf(wk[j], xv, acc[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      if (c0 + j < CO) yr[(c0 + j) * Tout + t] = acc[j];
+  }
+}
+
 inline unsigned stream_grid(long long n, int block, int sms) {
   long long g = (n + block - 1) / block;
   long long cap = (long long)sms * 16;
@@ -346,6 +393,20 @@ cudaError_t upd_launch_nsx_step(const float* e, const float* w4, const float* b4
 cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr, const int* col, const float* bias,
                                            long long N, int V, int C, int relu, float* out, int sms, cudaStream_t stream) {
   stg_gated_aggregate_kernel<<<stream_grid(N * C, 256, sms), 256, 0, stream>>>(kqvs, rowptr, col, bias, N, V, C, relu, out);
+  return cudaGetLastError();
+}
+
+cudaError_t upd_launch_stg_conv1d(const float* x, const float* w, const float* b, long long N, int CI, int CO, int Tin, int Tout,
+                                   int K, int stride, int pad, int transposed, float* y, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * (size_t)CI * K * CO;
+  if (smem > 48 * 1024 || N > 65535LL * 32768LL) return cudaErrorInvalidValue;
+  // gridDim.y is limited to 65535 rows: walk larger batches in slabs
+  for (long long n0 = 0; n0 < N; n0 += 65535) {
+    const long long rows = N - n0 < 65535 ? N - n0 : 65535;
+    dim3 grid((unsigned)((Tout + 127) / 128), (unsigned)rows);
+    stg_conv1d_kernel<<<grid, 128, smem, stream>>>(x + n0 * (long long)CI * Tin, w, b, CI, CO, Tin, Tout, K, stride, pad,
+                                                   transposed, y + n0 * (long long)CO * Tout);
+  }
   return cudaGetLastError();
 }
 

@@ -6,7 +6,7 @@
 #define UPD_HID 128           // hidden width of the conditional MLP denoiser (denoise.py:28-30)
 #define UPD_MAX_F 4
 #define UPD_MAX_T 64
-#define UPD_ABI_VERSION 7
+#define UPD_ABI_VERSION 8
 
 #ifdef __CUDACC__
 #define UPD_HD __host__ __device__ __forceinline__

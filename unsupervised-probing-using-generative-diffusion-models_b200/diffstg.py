@@ -224,6 +224,20 @@ def gated_aggregate(kqvs, rowptr, col, bias, V, C, relu=True):
     return out
 
 
+def conv1d_time(x, w, b, k, stride=1, pad=0, transposed=False):
+    """Narrow convolution along the last axis of x [N, CI, Tin] (upd_stg_conv1d): w [CO, CI, k] (or [CI, CO, k] when
+    ``transposed``), b [CO] -> [N, CO, Tout].  The 1x1 projections, DownSample and UpSample of UGnet."""
+    x = x.contiguous()
+    N, CI, Tin = x.shape
+    CO = w.shape[1] if transposed else w.shape[0]
+    Tout = (Tin - 1) * stride - 2 * pad + k if transposed else (Tin + 2 * pad - k) // stride + 1
+    y = torch.empty((N, CO, Tout), dtype=torch.float32, device=x.device)
+    rc = _lib.lib().upd_stg_conv1d(_lib.ptr(x), _lib.ptr(w), _lib.ptr(b), N, CI, CO, Tin, k, stride, pad,
+                                   1 if transposed else 0, _lib.ptr(y), _lib.stream_ptr(x.device))
+    _lib.check(rc, "upd_stg_conv1d")
+    return y
+
+
 class PreparedUGnet:
     """Inference-time weight layout of UGnet (fp32 on the device, built once per model load)."""
 
@@ -296,7 +310,9 @@ class PreparedUGnet:
             self.blocks[pre] = b
         self.xproj_w, self.xproj_b = sd["x_proj.weight"][:, :, 0, :].contiguous(), sd["x_proj.bias"]
         self.out0_w, self.out0_b = sd["out.0.weight"][:, :, 0, :].contiguous(), sd["out.0.bias"]
-        self.out1_w, self.out1_b = sd["out.1.weight"], sd["out.1.bias"]
+        self.out1_w, self.out1_b = sd["out.1.weight"].contiguous(), sd["out.1.bias"].contiguous()
+        # out.1 (Linear over the time axis) as a split-operand tensor-core GEMM when its width allows it
+        self.out1_w3 = _W3Cache().get([(self.out1_w, self.out1_b)]) if self.out1_w.shape[1] % 8 == 0 and dev.type == "cuda" else None
 
     def _front(self, b, x, t, c_in, c_out, T_in, as_operand):
         """tcn1 (+ step embedding) -> tcn2 -> LayerNorm over channels: x [N, c_in, T] -> hn [N, c_out*T] fp32, or -- when
@@ -368,30 +384,32 @@ class PreparedUGnet:
     def trunk(self, x, t, rowptr, col, V, projected=False):
         """x [N, C_in, T_total] (or, with ``projected``, already x_proj(x) [N, d_h, T_total]) -> the out block's result
         [N, C_out, T_out]; t: index into the step-embedding table."""
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
-            # the 1x1 projections are plain (batched) matmuls: no cuDNN algorithm choice on these tiny-channel shapes
-            if not projected:
-                x = torch.matmul(self.xproj_w[:, :, 0], x) + self.xproj_b[None, :, None]
-            hs = [x]
+        # the narrow convolutions (1x1 projections, DownSample, UpSample) run on upd_stg_conv1d; out.1 on upd_gemm3
+        if not projected:
+            x = conv1d_time(x, self.xproj_w, self.xproj_b, 1)
+        hs = [x]
 
-            def run(blk, x):
-                pre, kind, c_in, c_out, T_in = blk
-                if kind == "res":
-                    return self._res(pre, x, t, c_in, c_out, T_in, rowptr, col, V)
-                b = self.blocks[pre]
-                if kind == "downsample":
-                    return F.conv1d(x, b["w"], b["b"], stride=2, padding=1)
-                return F.conv_transpose1d(x, b["w"], b["b"], stride=2, padding=1)
+        def run(blk, x):
+            pre, kind, c_in, c_out, T_in = blk
+            if kind == "res":
+                return self._res(pre, x, t, c_in, c_out, T_in, rowptr, col, V)
+            b = self.blocks[pre]
+            if kind == "downsample":
+                return conv1d_time(x, b["w"], b["b"], 3, stride=2, pad=1)
+            return conv1d_time(x, b["w"], b["b"], 4, stride=2, pad=1, transposed=True)
 
-            for blk in self.down:
-                x = run(blk, x)
-                hs.append(x)
-            for blk in self.middle:
-                x = run(blk, x)
-            for blk in self.up:
-                x = run(blk, x if blk[1] == "upsample" else (x, hs.pop()))      # (x, skip): concatenated inside the kernel
-            e = torch.matmul(self.out0_w[:, :, 0], x) + self.out0_b[None, :, None]
-            return F.linear(e, self.out1_w, self.out1_b)
+        for blk in self.down:
+            x = run(blk, x)
+            hs.append(x)
+        for blk in self.middle:
+            x = run(blk, x)
+        for blk in self.up:
+            x = run(blk, x if blk[1] == "upsample" else (x, hs.pop()))      # (x, skip): concatenated inside the kernel
+        e = conv1d_time(x, self.out0_w, self.out0_b, 1)                      # [N, F, T_total]
+        if self.out1_w3 is not None:
+            N, nf, Tt = e.shape
+            return gemm3(a3_split(e.view(N * nf, Tt)), self.out1_w3, self.out1_w.shape[0]).view(N, nf, -1)
+        return F.linear(e, self.out1_w, self.out1_b)
 
 
 class GraphedForward:
