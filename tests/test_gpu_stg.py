@@ -227,3 +227,30 @@ def test_narrow_convolution_kernel_against_library_ops(CI, CO, T, k, stride, pad
     out = conv1d_time(x, w, b, k, stride=stride, pad=pad, transposed=transposed)
     assert tuple(out.shape) == tuple(ref.shape)
     assert _rel(out, ref) < 1e-5, _rel(out, ref)
+
+
+@pytest.mark.gpu
+def test_gated_aggregate_kernel_full_size_graph_against_oracle():
+    """The shared-memory form of upd_stg_gated_aggregate at the BASELINE graph size (100 nodes, ~2300 directed edges, 160
+    channels = five 32-channel slabs) against the oracle's scatter-add form."""
+    from updgm_b200 import _lib
+    from updgm_b200.diffstg import graph_csr
+    import networkx as nx
+    torch.manual_seed(1)
+    V, C, reps = 100, 160, 5
+    G = nx.barabasi_albert_graph(V, 12, seed=0)
+    ei = torch.tensor(list(G.to_directed().edges)).t().contiguous()
+    sd = {"g.lin_%s.weight" % n: torch.randn(C, C) * 0.1 for n in ("key", "query", "value", "skip")}
+    sd.update({"g.lin_%s.bias" % n: torch.randn(C) * 0.1 for n in ("key", "query", "value")})
+    sd["g.bias"] = torch.randn(C) * 0.1
+    x = torch.randn(reps * V, C)
+    ref = torch.relu(so.res_gated_graph_conv(sd, "g.", x, so.duplicate_edge_index(reps, ei, V)))
+    rowptr, col = graph_csr(ei, V)
+    w = torch.cat([sd["g.lin_key.weight"], sd["g.lin_query.weight"], sd["g.lin_value.weight"], sd["g.lin_skip.weight"]], 0)
+    bb = torch.cat([sd["g.lin_key.bias"], sd["g.lin_query.bias"], sd["g.lin_value.bias"], torch.zeros(C)], 0)
+    kqvs = torch.addmm(bb, x, w.t()).to(DEV).contiguous()         # the projections in fp32 on the host: only the aggregation is under test
+    out = torch.empty(reps * V, C, device=DEV)
+    bias, rp, cl = sd["g.bias"].to(DEV), rowptr.to(DEV), col.to(DEV)
+    _lib.check(_lib.lib().upd_stg_gated_aggregate(_lib.ptr(kqvs), _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(bias), reps * V, V, C,
+                                                  1, _lib.ptr(out), _lib.stream_ptr(torch.device(DEV))), "agg")
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)

@@ -52,6 +52,47 @@ __global__ void stg_gated_aggregate_kernel(const float* __restrict__ kqvs, const
   }
 }
 
+
+// The same aggregation with a replica's query / value rows staged in shared memory: every node of a replica reads the
+// q and v rows of ~2E/V neighbours, so the gather version above moves 2E/V times the tensor through L2 (measured: 11 % of
+// a DiffSTG step, L2-bound).  One CTA per (replica, slab of CS channels): q and v of all V nodes of the slab -> shared
+// (coalesced), then a warp per node, a lane per channel; arithmetic and edge order as above (bit-identical results).
+template <int CS>
+__global__ void __launch_bounds__(256) stg_gated_aggregate_smem_kernel(const float* __restrict__ kqvs, const int* __restrict__ rowptr,
+                                                                       const int* __restrict__ col, const float* __restrict__ bias,
+                                                                       int V, int C, int relu, float* __restrict__ out) {
+  extern __shared__ float sqv[];                     // q [V][CS] | v [V][CS]
+  float* sq = sqv;
+  float* sv = sqv + V * CS;
+  const long long base = (long long)blockIdx.x * V;  // first node of this replica
+  const int c0 = blockIdx.y * CS;
+  const int lane = threadIdx.x % CS, grp = threadIdx.x / CS, ngrp = blockDim.x / CS;
+  const int ch = c0 + lane;
+  const bool ok = ch < C;
+  for (int v = grp; v < V; v += ngrp) {
+    const float* src = kqvs + (base + v) * 4 * C;
+    sq[v * CS + lane] = ok ? src[C + ch] : 0.0f;
+    sv[v * CS + lane] = ok ? src[2 * C + ch] : 0.0f;
+  }
+  __syncthreads();
+  if (!ok) return;
+  for (int v = grp; v < V; v += ngrp) {
+    const float* self = kqvs + (base + v) * 4 * C;
+    const float ki = self[ch];
+    float acc = 0.0f;
+    const int e0 = rowptr[v], e1 = rowptr[v + 1];
+    for (int e = e0; e < e1; ++e) {
+      const int j = __ldg(col + e);
+      float g = __fadd_rn(ki, sq[j * CS + lane]);
+      float s = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-g)));
+      acc = __fadd_rn(acc, __fmul_rn(s, sv[j * CS + lane]));
+    }
+    acc = __fadd_rn(acc, self[3 * C + ch]);
+    if (bias) acc = __fadd_rn(acc, bias[ch]);
+    out[(base + v) * C + ch] = relu ? fmaxf(acc, 0.0f) : acc;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // Front half of a ResidualBlock (ugnet.py:117-127) in one pass over the activations:
 //     h1 = causal_conv3(x) + b1[step]     (TcnBlock 1: conv + 1x1 shortcut folded into tap 2, + t_conv(time emb))
@@ -392,6 +433,19 @@ cudaError_t upd_launch_nsx_step(const float* e, const float* w4, const float* b4
 
 cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr, const int* col, const float* bias,
                                            long long N, int V, int C, int relu, float* out, int sms, cudaStream_t stream) {
+  // replicas of up to 768 nodes: q / v slab of the replica in shared memory (UPD_STG_AGG=gather forces the gather kernel)
+  constexpr int CS = 32;
+  static const bool gather_env = getenv("UPD_STG_AGG") && getenv("UPD_STG_AGG")[0] == 'g';
+  const size_t smem = sizeof(float) * 2 * (size_t)V * CS;
+  const long long reps = N / V;
+  if (!gather_env && smem <= 192 * 1024 && reps <= 0x7fffffffLL && (C + CS - 1) / CS <= 65535) {
+    auto kern = stg_gated_aggregate_smem_kernel<CS>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((unsigned)reps, (unsigned)((C + CS - 1) / CS));
+    kern<<<grid, 256, smem, stream>>>(kqvs, rowptr, col, bias, V, C, relu, out);
+    return cudaGetLastError();
+  }
   stg_gated_aggregate_kernel<<<stream_grid(N * C, 256, sms), 256, 0, stream>>>(kqvs, rowptr, col, bias, N, V, C, relu, out);
   return cudaGetLastError();
 }
