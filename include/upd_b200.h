@@ -298,7 +298,7 @@ int upd_stg_gated_aggregate(const float* kqvs_dev, const int* rowptr_dev, const 
  *   shortcut bias + t_conv(emb(step)); b2_dev [C]; gamma/beta [C].  Exactly one of hn_dev (fp32) and a3_dev (the row as the
  *   fp16 split operand [N, 3*C*T+8] of the down-sampling GEMM, see the f(x) section) is written; the other is NULL.  wsc_dev [C, CI] / sc_dev [N, C, T] (both or neither): the block's 1x1 shortcut W_sc x
  *   (ugnet.py:129) evaluated in the same pass.  Limits: C in {4, 8, 16}, T even (any length: a row is walked in
- *   segments of 512 positions; T % 4 != 0 takes scalar global accesses).  Rows of T % 4 == 0, T <= 512 positions with
+ *   segments of 512 positions; T % 4 != 0 takes scalar global accesses).  Rows of T <= 512 positions with
  *   C >= 8 and 8 <= CI <= 32 run on the warp-MMA kernel (csrc/stg_tcn_mma.cu: fp16 hi/lo split operands, fp32 accumulate,
  *   ~1e-6 of the output rms from the fp32 FFMA kernel that keeps every other shape). */
 int upd_stg_tcn_ln(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,

@@ -2,8 +2,8 @@
 
     python profiles/make_family_summaries.py r01
 Inputs (gpurun_out/, produced on a B200):
-    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r01_families_launches.csv \
-        python profiles/tools/gpu_prof_families.py
+    ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+        --log-file gpurun_out/r01_families_launches.csv python profiles/tools/gpu_prof_families.py
     ncu --set full --clock-control none --import-source on -k 'regex:stg_tcn_ln|dts_fourier_topk|stg_gated_aggregate|nsx_step' -c 40 \
         -o gpurun_out/prof_families python profiles/tools/gpu_prof_families.py
 The profiled command: 2 DiffSTG denoise steps on 16 384 replica rows (BASELINE config 5 architecture, BA-100 graph) and one
@@ -22,7 +22,8 @@ OWN = ("stg_tcn_ln_kernel", "stg_gated_aggregate_kernel", "stg_posterior_kernel"
        "dts_fourier_topk_fwd_kernel", "dts_fourier_topk_bwd_kernel", "dts_ddim_step_kernel", "dts_adagrad_kernel",
        "dts_infill_kernel", "dts_attn_fwd_kernel", "dts_attn_bwd_kernel", "fx_split_kernel",
        "dts_attn_tc_fwd_kernel", "dts_attn_tc_bwd_kernel", "dts_ln_fwd_a3_kernel", "dts_ln_fwd_kernel", "dts_ln_bwd_kernel",
-       "gemm3_pair_kernel", "gemm3_kernel", "stg_tcn_ln_cat_kernel")
+       "gemm3_pair_kernel", "gemm3_kernel", "stg_tcn_ln_cat_kernel", "stg_tcn_mma_kernel", "stg_conv1d_kernel",
+       "stg_gated_aggregate_smem_kernel")
 lines = [l for l in open("gpurun_out/%s_families_launches.csv" % tag) if not l.startswith("==")]
 rows = list(csv.DictReader(lines))
 # split the launch list at the first DiffusionTS-only kernel: everything before belongs to DiffSTG

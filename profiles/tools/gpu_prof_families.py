@@ -1,6 +1,8 @@
 """Short DiffSTG / DiffusionTS / NsDiff_spatial steps for ncu: 2 DiffSTG denoise steps on 16384 replica rows, one DiffusionTS
 loop iteration (t = 99 -> 98: x0 prediction, DDIM mean, 3 Langevin iterations, infill) on 1000 rows, then f(x) + g(x) and a
-2-step NsDiff_spatial chain on 16000 replica rows."""
+2-step NsDiff_spatial chain on 16000 replica rows.  Every family runs once un-profiled first (weight preparation, CUDA-graph
+capture, library heuristics) and once between cudaProfilerStart / Stop: run ncu with --profile-from-start off to list the
+steady state only."""
 import json, os, sys
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
@@ -25,6 +27,10 @@ win = torch.randn(2, 100, 100, 1, device=DEV).cumsum(2) * 0.1
 m.rows_per_launch = 16384
 out = m.sample_windows(win, ei, 100, seed=1, window_base=0)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
+out = m.sample_windows(win, ei, 100, seed=1, window_base=0)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("stg ok", tuple(out.shape), bool(torch.isfinite(out).all()))
 g = np.load("tests/golden/dts_yaml_steps.npz"); cfg = json.loads(str(g["cfg"])); shapes = json.loads(str(g["keys"]))
 d = DiffusionTS_model(dict(cfg, device=DEV)).eval()
@@ -34,6 +40,10 @@ tgt = torch.tanh(torch.randn(1000, 100, 1, device=DEV).cumsum(1) * 0.1)
 gen = torch.Generator(device=DEV).manual_seed(0)
 img = d._sample_rows(tgt, 1000, lambda i, shape: torch.randn(shape, device=DEV, generator=gen))
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
+img = d._sample_rows(tgt, 1000, lambda i, shape: torch.randn(shape, device=DEV, generator=gen))
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("dts ok", tuple(img.shape), bool(torch.isfinite(img).all()))
 
 from updgm_b200.nsdiff_spatial import NsDiff_model_spatial
@@ -47,4 +57,8 @@ x.rows_per_launch = 16000
 win = 5.0 + torch.randn(2, 100, 100, 1, device=DEV).cumsum(2) * 0.05
 out = x.sample_windows(win, ei, 100, seed=1, window_base=0)
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
+out = x.sample_windows(win, ei, 100, seed=1, window_base=0)
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("nsx ok", tuple(out.shape), bool(torch.isfinite(out).all()))

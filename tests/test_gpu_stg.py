@@ -116,7 +116,8 @@ def test_gated_aggregate_kernel_against_oracle():
 
 
 @pytest.mark.parametrize("C,CI,T", [(8, 4, 400), (16, 32, 200), (4, 12, 40), (16, 16, 20), (8, 4, 2000), (16, 32, 1200),
-                                    (16, 32, 50), (8, 16, 514), (4, 4, 6)])
+                                    (16, 32, 50), (8, 16, 514), (4, 4, 6), (8, 8, 400), (8, 24, 100), (16, 8, 100), (16, 12, 36),
+                                    (8, 9, 12), (16, 17, 510)])
 def test_fused_tcn_layernorm_kernel_against_library_ops(C, CI, T):
     """upd_stg_tcn_ln == causal conv -> causal conv -> LayerNorm over channels (torch fp32, TF32 off)."""
     import torch.nn.functional as F
@@ -149,7 +150,8 @@ def test_fused_tcn_layernorm_kernel_against_library_ops(C, CI, T):
                                      _lib.ptr(be), N, CI, 5, T, _lib.ptr(out), None, None, None, None) == 2      # UPD_ERR_UNSUPPORTED
 
 
-@pytest.mark.parametrize("C,CI,T,N", [(16, 32, 50, 9), (8, 16, 514, 5), (4, 4, 6, 3), (8, 4, 2000, 4), (16, 16, 1028, 8200)])
+@pytest.mark.parametrize("C,CI,T,N", [(16, 32, 50, 9), (8, 16, 514, 5), (4, 4, 6, 3), (8, 4, 2000, 4), (16, 16, 1028, 8200),
+                                      (16, 16, 200, 700), (8, 24, 50, 9), (8, 8, 398, 11)])
 def test_fused_tcn_kernel_writes_stay_inside_their_buffers(C, CI, T, N):
     """Own bounds check (no sanitizer on this pool): every output sits between sentinel guard bands that must survive, for the
     scalar (T % 4 != 0), segmented (T > 512) and 8-rows-per-CTA (N >= 8192) paths."""

@@ -43,7 +43,7 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
                                   void* a3, const float* wsc, float* sc_out, const float* x2, int CI2, int sms,
                                   cudaStream_t stream);
 cudaError_t upd_launch_stg_conv1d(const float* x, const float* w, const float* b, long long N, int CI, int CO, int Tin, int Tout,
-                                   int K, int stride, int pad, int transposed, float* y, cudaStream_t stream);
+                                   int K, int stride, int pad, int transposed, float* y, int sms, cudaStream_t stream);
 cudaError_t upd_launch_fx_split(const float* x, long long rows, int K, int H, int L, int act, void* a3, cudaStream_t stream);
 cudaError_t upd_launch_fx_add_ln_split(const float* x, const float* res, const float* g1, const float* b1,
                                        const float* g2, const float* b2, long long rows, int K, float* y, void* a3,
@@ -446,8 +446,7 @@ int upd_stg_conv1d(const float* x_dev, const float* w_dev, const float* b_dev, l
   if (Tout < 1) return UPD_ERR_BAD_ARG;
   if ((long long)CI * K * CO > 12288) return UPD_ERR_UNSUPPORTED;
   UPD_DEVICE_OR_RETURN();
-  (void)sms;
-  UPD_FINISH(upd_launch_stg_conv1d(x_dev, w_dev, b_dev, N, CI, CO, Tin, Tout, K, stride, pad, transposed, y_dev,
+  UPD_FINISH(upd_launch_stg_conv1d(x_dev, w_dev, b_dev, N, CI, CO, Tin, Tout, K, stride, pad, transposed, y_dev, sms,
                                    (cudaStream_t)stream));
 }
 

@@ -368,25 +368,31 @@ __global__ void nsx_step_kernel(const float* __restrict__ e, const float* __rest
 //   transposed == 0:  y[co][t] = b[co] + sum_ci sum_k w[co][ci][k] * x[ci][t*stride + k - pad]
 //   transposed == 1:  y[co][t] = b[co] + sum_ci sum_k w[ci][co][k] * x[ci][(t + pad - k) / stride]   (where divisible)
 // HBM / L2-bound (a few FMAs per byte).  These were cuDNN implicit-GEMM / dgrad / magma launches (10 % of a DiffSTG step).
+template <int CB>   // output channels a thread carries at once (1, 4 or 8)
 __global__ void __launch_bounds__(128) stg_conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                         const float* __restrict__ b, int CI, int CO, int Tin, int Tout,
-                                                         int K, int stride, int pad, int transposed, float* __restrict__ y) {
+                                                         const float* __restrict__ b, long long N, int CI, int CO, int Tin,
+                                                         int Tout, int K, int stride, int pad, int transposed,
+                                                         int rows_per_cta, float* __restrict__ y) {
   extern __shared__ float sw[];                       // [CI][K][CO]: channels-out contiguous
   for (int i = threadIdx.x; i < CI * K * CO; i += blockDim.x) {
     const int co = i % CO, r = i / CO, k = r % K, ci = r / K;
     sw[i] = transposed ? w[(ci * CO + co) * K + k] : w[(co * CI + ci) * K + k];
   }
   __syncthreads();
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= Tout) return;
-  const long long n = blockIdx.y;
-  const float* xr = x + n * (long long)CI * Tin;
-  float* yr = y + n * (long long)CO * Tout;
-  for (int c0 = 0; c0 < CO; c0 += 8) {
-    float acc[8];
+  const long long n0 = (long long)blockIdx.x * rows_per_cta;
+  const long long n1 = n0 + rows_per_cta < N ? n0 + rows_per_cta : N;
+  // a CTA walks its rows as one flat index space of output positions
+  const int total = (int)(n1 - n0) * Tout;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int r = idx / Tout, t = idx - r * Tout;
+    const long long n = n0 + r;
+    const float* xr = x + n * (long long)CI * Tin;
+    float* yr = y + n * (long long)CO * Tout;
+    // input positions of the K taps (-1: outside / not on the stride grid)
+    for (int c0 = 0; c0 < CO; c0 += CB) {
+      float acc[CB];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = (b && c0 + j < CO) ? b[c0 + j] : 0.0f;
-    for (int ci = 0; ci < CI; ++ci)
+      for (int j = 0; j < CB; ++j) acc[j] = (b && c0 + j < CO) ? b[c0 + j] : 0.0f;
       for (int k = 0; k < K; ++k) {
         int src;
         if (!transposed) {
@@ -396,15 +402,18 @@ __global__ void __launch_bounds__(128) stg_conv1d_kernel(const float* __restrict
           src = (u >= 0 && u % stride == 0) ? u / stride : -1;
         }
         if (src < 0 || src >= Tin) continue;
-        const float xv = __ldg(xr + ci * Tin + src);
-        const float* wk = sw + (ci * K + k) * CO + c0;
+        for (int ci = 0; ci < CI; ++ci) {
+          const float xv = __ldg(xr + ci * Tin + src);
+          const float* wk = sw + (ci * K + k) * CO + c0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (c0 + j < CO) acc[j] = fmaf(wk[j], xv, acc[j]);
+          for (int j = 0; j < CB; ++j)
+            if (c0 + j < CO) acc[j] = fmaf(wk[j], xv, acc[j]);
+        }
       }
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (c0 + j < CO) yr[(c0 + j) * Tout + t] = acc[j];
+      for (int j = 0; j < CB; ++j)
+        if (c0 + j < CO) yr[(c0 + j) * Tout + t] = acc[j];
+    }
   }
 }
 
@@ -451,16 +460,21 @@ cudaError_t upd_launch_stg_gated_aggregate(const float* kqvs, const int* rowptr,
 }
 
 cudaError_t upd_launch_stg_conv1d(const float* x, const float* w, const float* b, long long N, int CI, int CO, int Tin, int Tout,
-                                   int K, int stride, int pad, int transposed, float* y, cudaStream_t stream) {
+                                   int K, int stride, int pad, int transposed, float* y, int sms, cudaStream_t stream) {
   const size_t smem = sizeof(float) * (size_t)CI * K * CO;
-  if (smem > 48 * 1024 || N > 65535LL * 32768LL) return cudaErrorInvalidValue;
-  // gridDim.y is limited to 65535 rows: walk larger batches in slabs
-  for (long long n0 = 0; n0 < N; n0 += 65535) {
-    const long long rows = N - n0 < 65535 ? N - n0 : 65535;
-    dim3 grid((unsigned)((Tout + 127) / 128), (unsigned)rows);
-    stg_conv1d_kernel<<<grid, 128, smem, stream>>>(x + n0 * (long long)CI * Tin, w, b, CI, CO, Tin, Tout, K, stride, pad,
-                                                   transposed, y + n0 * (long long)CO * Tout);
-  }
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  // ~8 CTAs per SM, every CTA stages the weights once and walks a block of rows
+  long long ctas = (long long)sms * 8;
+  if (ctas > N) ctas = N;
+  const int rpc = (int)((N + ctas - 1) / ctas);
+  if ((long long)rpc * Tout > 0x7fffffffLL) return cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)((N + rpc - 1) / rpc);
+  if (CO >= 8)
+    stg_conv1d_kernel<8><<<grid, 128, smem, stream>>>(x, w, b, N, CI, CO, Tin, Tout, K, stride, pad, transposed, rpc, y);
+  else if (CO >= 2)
+    stg_conv1d_kernel<4><<<grid, 128, smem, stream>>>(x, w, b, N, CI, CO, Tin, Tout, K, stride, pad, transposed, rpc, y);
+  else
+    stg_conv1d_kernel<1><<<grid, 128, smem, stream>>>(x, w, b, N, CI, CO, Tin, Tout, K, stride, pad, transposed, rpc, y);
   return cudaGetLastError();
 }
 
@@ -489,8 +503,8 @@ cudaError_t upd_launch_stg_tcn_ln(const float* x, const float* w1, const float* 
   if ((wsc == nullptr) != (sc_out == nullptr) || (reinterpret_cast<uintptr_t>(sc_out) & 15) != 0) return cudaErrorInvalidValue;
   if (smem > 200 * 1024) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(x) & 15) != 0) return cudaErrorInvalidValue;
-  // Tensor-core kernel (csrc/stg_tcn_mma.cu) for rows of up to 512 positions with T % 4 == 0; the FFMA kernel below keeps
-  // the other shapes (T % 4 == 2, long segmented rows).  UPD_TCN_IMPL=ffma forces the FFMA kernel (measurement / tests).
+  // Tensor-core kernel (csrc/stg_tcn_mma.cu) for rows of up to 512 positions, c_out >= 8 and 8 <= c_in <= 32; the FFMA kernel below keeps
+  // the other shapes (narrow blocks, long segmented rows).  UPD_TCN_IMPL=ffma forces the FFMA kernel (measurement / tests).
   static const bool ffma_env = getenv("UPD_TCN_IMPL") && getenv("UPD_TCN_IMPL")[0] == 'f';
   if (!ffma_env) {
     cudaError_t e = upd_launch_stg_tcn_mma(x, w1, b1, w2, b2, gamma, beta, N, CI, C, T, hn, a3, wsc, sc_out, x2, CI - CI2, sms, stream);

@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
   unsigned char* shh = smem_raw + XREG;      // [ROWS][NCH * 16 B] hi plane of h1
   unsigned char* shl = shh + ROWS * NCH * 16;
   float* sraw = reinterpret_cast<float*>(shl + ROWS * NCH * 16);   // [CI][T] fp32, as in global memory
-  uint4* sw1 = reinterpret_cast<uint4*>(sraw + CI * T);         // [3][KS][NT][32]
+  uint4* sw1 = reinterpret_cast<uint4*>(sraw + ((CI * T + 3) & ~3));   // [3][KS][NT][32]
   uint4* sw2 = sw1 + 3 * KS * NT * 32;       // [3][NT][32]
   uint4* swsc = sw2 + 3 * NT * 32;           // [KS][NT][32]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
       gr[nt][j] = ok ? gamma[c] : 0.0f;
       ber[nt][j] = ok ? beta[c] : 0.0f;
     }
-  const int Q = T >> 2;                      // float4 groups per channel row (T % 4 == 0)
+  const bool vec4 = (T & 3) == 0;            // rows of T % 4 == 2 positions move in 8-byte pieces
+  const int Q = vec4 ? T >> 2 : T >> 1;      // 16-byte (8-byte) groups per channel row
   const int K = C * T;
   // ldmatrix row addresses of this lane (matrix j = lane / 8, row r = lane % 8 of it) per tap and K-slice, and the h1 store
   // offsets of its accumulator fragment, relative to a tile base
@@ -199,8 +200,13 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
     const float* xr2 = x2 ? x2 + n * (long long)(CI - CI1) * T - (long long)CI1 * T : xr;   // indexed by the channel of the concatenation
     for (int ch = warp; ch < CI; ch += TCN_WARPS) {
       const float* src = (ch < CI1 ? xr : xr2) + ch * T;
-      for (int q = lane; q < Q; q += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_a + (uint32_t)(ch * T + 4 * q) * 4u), "l"(src + 4 * q) : "memory");
+      if (vec4) {
+        for (int q = lane; q < Q; q += 32)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(raw_a + (uint32_t)(ch * T + 4 * q) * 4u), "l"(src + 4 * q) : "memory");
+      } else {
+        for (int q = lane; q < Q; q += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(raw_a + (uint32_t)(ch * T + 2 * q) * 4u), "l"(src + 2 * q) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -346,22 +352,40 @@ __global__ void __launch_bounds__(TCN_THREADS) stg_tcn_mma_kernel(
     // ---- copy-out: a warp per channel row, lanes along the positions ----
     if (a3 == nullptr) {
       float* out = hn + n * (long long)K;
-      for (int c = warp; c < C; c += TCN_WARPS)
-        for (int q = lane; q < Q; q += 32)
-          *reinterpret_cast<float4*>(out + c * T + 4 * q) = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
+      for (int c = warp; c < C; c += TCN_WARPS) {
+        if (vec4) {
+          for (int q = lane; q < Q; q += 32)
+            *reinterpret_cast<float4*>(out + c * T + 4 * q) = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
+        } else {
+          for (int q = lane; q < Q; q += 32)
+            *reinterpret_cast<float2*>(out + c * T + 2 * q) = *reinterpret_cast<const float2*>(so + c * TPO + 2 * q);
+        }
+      }
     } else {
       // the row as the split operand [hi | lo | hi | 1 1 0..] (K = C*T) of the fp16 tensor-core GEMM that follows
       __half* row = a3 + n * (long long)(3 * K + 8);
-      for (int c = warp; c < C; c += TCN_WARPS)
-        for (int q = lane; q < Q; q += 32) {
-          const float4 v = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
-          const uint2 e01 = split_pair(v.x, v.y), e23 = split_pair(v.z, v.w);
-          const uint2 hi = make_uint2(e01.x, e23.x), lo = make_uint2(e01.y, e23.y);
-          __half* d = row + c * T + 4 * q;
-          *reinterpret_cast<uint2*>(d) = hi;
-          *reinterpret_cast<uint2*>(d + K) = lo;
-          *reinterpret_cast<uint2*>(d + 2 * K) = hi;
+      for (int c = warp; c < C; c += TCN_WARPS) {
+        if (vec4) {
+          for (int q = lane; q < Q; q += 32) {
+            const float4 v = *reinterpret_cast<const float4*>(so + c * TPO + 4 * q);
+            const uint2 e01 = split_pair(v.x, v.y), e23 = split_pair(v.z, v.w);
+            const uint2 hi = make_uint2(e01.x, e23.x), lo = make_uint2(e01.y, e23.y);
+            __half* d = row + c * T + 4 * q;
+            *reinterpret_cast<uint2*>(d) = hi;
+            *reinterpret_cast<uint2*>(d + K) = lo;
+            *reinterpret_cast<uint2*>(d + 2 * K) = hi;
+          }
+        } else {
+          for (int q = lane; q < Q; q += 32) {
+            const float2 v = *reinterpret_cast<const float2*>(so + c * TPO + 2 * q);
+            const uint2 e = split_pair(v.x, v.y);
+            __half* d = row + c * T + 2 * q;
+            *reinterpret_cast<uint32_t*>(d) = e.x;
+            *reinterpret_cast<uint32_t*>(d + K) = e.y;
+            *reinterpret_cast<uint32_t*>(d + 2 * K) = e.x;
+          }
         }
+      }
       if (tid == 0) *reinterpret_cast<uint4*>(row + 3 * K) = make_uint4(0x3C003C00u, 0u, 0u, 0u);
     }
   }
@@ -373,7 +397,7 @@ size_t tcn_mma_smem(int CI, int T) {
   constexpr int NCX = HALF1 ? 1 : 2 * KS, NCH = (C <= 8) ? 1 : 2;
   const int pairs = (T + 16 * MT - 1) / (16 * MT), TPAD = pairs * 16 * MT, ROWS = TPAD + HALO, TPO = TPAD + 4;
   const size_t xpl = (size_t)ROWS * NCX * 32, st = sizeof(float) * (size_t)CP * TPO;
-  return (xpl > st ? xpl : st) + (size_t)ROWS * NCH * 32 + sizeof(float) * (size_t)CI * T +
+  return (xpl > st ? xpl : st) + (size_t)ROWS * NCH * 32 + sizeof(float) * (size_t)((CI * T + 3) & ~3) +
          sizeof(uint4) * 32 * ((size_t)3 * KS * NT + 3 * NT + KS * NT);
 }
 
@@ -414,7 +438,7 @@ cudaError_t upd_launch_stg_tcn_mma(const float* x, const float* w1, const float*
                                    const float* gamma, const float* beta, long long N, int CI, int C, int T, float* hn,
                                    void* a3, const float* wsc, float* sc_out, const float* x2, int CI1, int sms,
                                    cudaStream_t stream) {
-  if ((T & 3) != 0 || T < 4 || T > 512 || CI < 1 || CI > 32) return cudaErrorNotSupported;
+  if ((T & 1) != 0 || T < 4 || T > 512 || CI < 1 || CI > 32) return cudaErrorNotSupported;
   // measured against the FFMA kernel (profiles/r02_tcn_mma.txt): 2.0-2.5x on the 16-channel blocks, 1.2x at 8 -> 8 channels,
   // level at 4 -> 8 and slower at c_out = 4 (one n-tile is half empty and the MMAs are a minor part of the pass)
   static const bool force = getenv("UPD_TCN_IMPL") && getenv("UPD_TCN_IMPL")[0] == 'm';
