@@ -59,8 +59,9 @@ struct HeadSums {
 
 // One 16-column group of an accumulator -> activations -> fp16 hi/lo A-operand words of one K-slice of the next GEMM
 // (hi words in o[0..7], lo words in o[8..15]).  FIRST: layer 1 (bias rides in the GEMM).  PMASK: bit i = column pair i
-// takes the one-MUFU (polynomial) softplus.
-template <bool FIRST, bool GUARD, bool SUMSQ, int PMASK>
+// takes the one-MUFU (polynomial) softplus.  LO = false: only the hi words are formed (o[8..15] untouched) -- the
+// warp-specialised sampler's two-pass contraction (activation as one fp16 word, weights hi + lo).
+template <bool FIRST, bool GUARD, bool SUMSQ, int PMASK, bool LO = true>
 __device__ __forceinline__ void epilogue_group(const uint32_t* __restrict__ r, uint32_t (&o)[16], const float* __restrict__ e,
                                                const float* __restrict__ b, float2 inv2, float2& ss2) {
   sm::static_for<4>([&](auto jj) {
@@ -72,8 +73,13 @@ __device__ __forceinline__ void epilogue_group(const uint32_t* __restrict__ r, u
     const float2 h0 = sm::softplus2<((PMASK >> (j / 2)) & 1) != 0, GUARD>(z0);
     const float2 h1 = sm::softplus2<((PMASK >> (j / 2 + 1)) & 1) != 0, GUARD>(z1);
     if (SUMSQ) { ss2 = sm::ffma2(h0, h0, ss2); ss2 = sm::ffma2(h1, h1, ss2); }
-    sm::split_f16x2(h0.x, h0.y, o[j / 2], o[8 + j / 2]);
-    sm::split_f16x2(h1.x, h1.y, o[j / 2 + 1], o[8 + j / 2 + 1]);
+    if (LO) {
+      sm::split_f16x2(h0.x, h0.y, o[j / 2], o[8 + j / 2]);
+      sm::split_f16x2(h1.x, h1.y, o[j / 2 + 1], o[8 + j / 2 + 1]);
+    } else {
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o[j / 2]) : "f"(h0.y), "f"(h0.x));
+      asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(o[j / 2 + 1]) : "f"(h1.y), "f"(h1.x));
+    }
   });
 }
 

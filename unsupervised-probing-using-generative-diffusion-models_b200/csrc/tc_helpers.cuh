@@ -219,6 +219,8 @@ __device__ __forceinline__ void issue_layer_f16x3_g16(uint32_t d_tmem, uint32_t 
 // The same contraction restricted to the even (parity 0) or odd (parity 1) K-slices: the warp-specialised sampler issues
 // the even slices of a layer as soon as every epilogue warp has written the first 16 of its 32 columns, so that half of
 // the layer's tensor time is spent while the epilogue of the other 16 columns is still running.
+// A_LO / B_LO: which correction passes are issued besides hi*hi (A_LO: lo(A)*hi(B), B_LO: hi(A)*lo(B)).
+template <bool A_LO = true, bool B_LO = true>
 __device__ __forceinline__ void issue_kparity_f16x3_g16(uint32_t d_tmem, uint32_t a_tmem, uint32_t bhi_smem,
                                                         uint32_t blo_smem, uint32_t lbo, uint32_t sbo, int parity) {
 #pragma unroll
@@ -228,9 +230,10 @@ __device__ __forceinline__ void issue_kparity_f16x3_g16(uint32_t d_tmem, uint32_
     uint32_t a_lo = a_hi + 8u;
     uint64_t b_hi = smem_desc(bhi_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
     uint64_t b_lo = smem_desc(blo_smem + (uint32_t)(2 * j) * 2048u, lbo, sbo);
-    mma_f16_ts(d_tmem, a_lo, b_hi, IDESC_F16_M128_N128, parity != 0 || jj > 0);
-    mma_f16_ts(d_tmem, a_hi, b_lo, IDESC_F16_M128_N128, true);
-    mma_f16_ts(d_tmem, a_hi, b_hi, IDESC_F16_M128_N128, true);
+    const bool first = (parity == 0 && jj == 0);
+    if (A_LO) mma_f16_ts(d_tmem, a_lo, b_hi, IDESC_F16_M128_N128, !first);
+    if (B_LO) mma_f16_ts(d_tmem, a_hi, b_lo, IDESC_F16_M128_N128, !first || A_LO);
+    mma_f16_ts(d_tmem, a_hi, b_hi, IDESC_F16_M128_N128, !first || A_LO || B_LO);
   }
 }
 //   tf32: slice = 8 elements = 8 TMEM columns; A holds hi in columns [0,K1), lo in [K1,2*K1).
