@@ -44,9 +44,10 @@ METRIC = "sampled trajectories/sec (K x windows), NsDiff MPV sweep"
 UNIT = "trajectories/s"
 YAML = os.path.join(ROOT, "tests", "golden", "ews_results", "model_compare", "NsDiff", "biomass", "model_trained.yaml")
 MACS_PER_ROW_STEP_F1 = 3 * 1 * 128 + 2 * 128 * 128 + 2 * 128 * 1          # 33 408 for F = 1
-# tensor work actually issued per row-step: three split passes of the two 128x128 layers (fp16) + of the 8-wide layer 1
-# (tf32, half rate: counted twice); the dense fp16 rate of an SM is 8192 FLOP/clk (2.25 PFLOP/s / 148 SMs / 1.86 GHz)
-ISSUED_F16_FLOPS_PER_ROW_STEP = 3 * 2 * (2 * 128 * 128) + 2 * (3 * 2 * 8 * 128)
+# tensor work actually issued per row-step: two split passes (hi*hi + hi*lo(W)) of the two 128x128 layers (fp16) + three of
+# the 8-wide layer 1 (tf32, half rate: counted twice); the dense fp16 rate of an SM is 8192 FLOP/clk (2.25 PFLOP/s / 148
+# SMs / 1.86 GHz)
+ISSUED_F16_FLOPS_PER_ROW_STEP = 2 * 2 * (2 * 128 * 128) + 2 * (3 * 2 * 8 * 128)
 
 
 def workload_config():
@@ -510,7 +511,7 @@ def run_own_arm(args, rank, world, local_rank):
                      "tensor_active": rs_per_s * ISSUED_F16_FLOPS_PER_ROW_STEP / (148 * 8192 * sm_hz),
                      "note": "per GPU (rank 0's launch).  algorithmic FLOPs = 2*33408 MAC per denoiser row-step (SURVEY 8a7). "
                              "mufu_frac = 772 ex2/lg2 per row-step against 16 MUFU lanes/clk/SM at the sampled SM clock -- the "
-                             "pipe that bounds this MLP; tensor_active = issued MMA work (3 split passes) against the dense "
+                             "pipe that bounds this MLP; tensor_active = issued MMA work (2 split passes in layers 2-3, 3 in layer 1) against the dense "
                              "fp16 rate; both derived from the measured row-steps/s, the ncu captures are in profiles/"},
     }
     if world > 1:

@@ -6,7 +6,7 @@ import updgm_b200
 from updgm_b200 import _lib
 DEV = torch.device("cuda:0")
 L = _lib.lib()
-shapes = ((32768, 16, 16, 200), (32768, 12, 4, 400), (32768, 8, 8, 400))
+shapes = ((32768, 16, 16, 200), (32768, 32, 16, 200), (32768, 8, 8, 400))
 for (N, CI, C, T) in shapes:
     x = torch.randn(N, CI, T, device=DEV)
     w1, b1 = torch.randn(C, CI, 3, device=DEV) * 0.3, torch.randn(C, device=DEV)
