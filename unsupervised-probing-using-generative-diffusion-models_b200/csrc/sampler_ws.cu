@@ -41,12 +41,32 @@ constexpr int EPI_BAR0 = 2;           // + 2*tile + half: 16 epilogue warps arri
                                       //   every warp's 32 operand columns are written: even / odd K-slices of the next GEMM)
 constexpr int HEADS_BAR0 = 6;         // + tile: 16 epilogue warps arrive, the 4 row warps sync (head sums stored)
 
-// pairs of a 16-column group that take the one-MUFU (polynomial) softplus: bit i = pair i (layers 1-2 / layer 3)
-#ifndef UPD_WS_PMASK12
-#define UPD_WS_PMASK12 0x00
+// Pairs of a 16-column group that take the one-MUFU softplus (lg2(1 + u) as a packed-FMA polynomial, sampler_math.cuh):
+// bit i = pair i; layers 1-2 / layer 3, per model kind.  With the two-pass contractions the MUFU pipe is what the
+// epilogue warps wait for (ncu: XU 84 %, issue 48 %, FMA 20 %), so moving part of the lg2 work to the FMA pipe pays:
+// measured on B200 (profiles/r02_pmask_sweep.txt) NsDiff F = 1 4.61 -> 4.82, F = 2 3.84 -> 3.94, TMDM 5.23 -> 5.73 G
+// row-steps/s.  NsDiff's layer 3 keeps the MUFU form (its FMA pipe carries the head sums: any mask there loses);
+// more than half of the pairs in layers 1-2 loses again (the FMA pipe becomes the longer one).
+// -DUPD_WS_PMASK12=m / -DUPD_WS_PMASK3=m override both kinds (0 = the all-MUFU build).
+#ifdef UPD_WS_PMASK12
+#define UPD_WS_PMASK12_NS UPD_WS_PMASK12
+#define UPD_WS_PMASK12_TM UPD_WS_PMASK12
 #endif
-#ifndef UPD_WS_PMASK3
-#define UPD_WS_PMASK3 0x00
+#ifdef UPD_WS_PMASK3
+#define UPD_WS_PMASK3_NS UPD_WS_PMASK3
+#define UPD_WS_PMASK3_TM UPD_WS_PMASK3
+#endif
+#ifndef UPD_WS_PMASK12_NS
+#define UPD_WS_PMASK12_NS 0x33
+#endif
+#ifndef UPD_WS_PMASK3_NS
+#define UPD_WS_PMASK3_NS 0x00
+#endif
+#ifndef UPD_WS_PMASK12_TM
+#define UPD_WS_PMASK12_TM 0x55
+#endif
+#ifndef UPD_WS_PMASK3_TM
+#define UPD_WS_PMASK3_TM 0xff
 #endif
 // Passes of the layer-2 / layer-3 contractions.  The activation operand is ONE fp16 word per element (round to nearest:
 // an unbiased 2^-12 relative perturbation, independent per element and step), the weights stay hi + lo: hi*hi + hi*lo.
@@ -91,18 +111,19 @@ struct WsShape {
 template <bool FIRST, bool GUARD, bool SUMSQ>
 __device__ __forceinline__ float epilogue_quarter(uint32_t acc, const float* __restrict__ e, const float* __restrict__ b,
                                                   float inv, int half_bar) {
+  constexpr int PMASK = SUMSQ ? UPD_WS_PMASK12_NS : UPD_WS_PMASK12_TM;        // SUMSQ <=> NsDiff (L2-normalised layers)
   float2 ss2 = make_float2(0.f, 0.f);
   const float2 inv2 = sm::splat(inv);
   uint32_t r[32], o[16];
   tc::tmem_ld32(acc, r);
   tc::wait_ld();
-  epilogue_group<FIRST, GUARD, SUMSQ, UPD_WS_PMASK12, WS_A_LO>(r, o, e, b, inv2, ss2);
+  epilogue_group<FIRST, GUARD, SUMSQ, PMASK, WS_A_LO>(r, o, e, b, inv2, ss2);
   if (WS_A_LO) tc::tmem_st16(acc, o);
   else tc::tmem_st8(acc, *reinterpret_cast<uint32_t (*)[8]>(&o[0]));
   tc::wait_st();
   tc::fence_before_sync();
   tc::named_bar_arrive(half_bar, EPI_WARPS * 32 + 32);
-  epilogue_group<FIRST, GUARD, SUMSQ, UPD_WS_PMASK12, WS_A_LO>(r + 16, o, e + 16, b + 16, inv2, ss2);
+  epilogue_group<FIRST, GUARD, SUMSQ, PMASK, WS_A_LO>(r + 16, o, e + 16, b + 16, inv2, ss2);
   if (WS_A_LO) tc::tmem_st16(acc + 16u, o);
   else tc::tmem_st8(acc + 16u, *reinterpret_cast<uint32_t (*)[8]>(&o[0]));
   return ss2.x + ss2.y;
@@ -117,8 +138,8 @@ __device__ __forceinline__ void heads_quarter(uint32_t acc, const float* __restr
   uint32_t r[32];
   tc::tmem_ld32(acc, r);
   tc::wait_ld();
-  heads_group<NS, F, GUARD, UPD_WS_PMASK3>(r, e, b, w4, ws, inv2, H);
-  heads_group<NS, F, GUARD, UPD_WS_PMASK3>(r + 16, e + 16, b + 16, w4 + 16, ws + 16, inv2, H);
+  heads_group<NS, F, GUARD, (NS ? UPD_WS_PMASK3_NS : UPD_WS_PMASK3_TM)>(r, e, b, w4, ws, inv2, H);
+  heads_group<NS, F, GUARD, (NS ? UPD_WS_PMASK3_NS : UPD_WS_PMASK3_TM)>(r + 16, e + 16, b + 16, w4 + 16, ws + 16, inv2, H);
 }
 
 #ifdef UPD_TRACE
