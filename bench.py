@@ -490,7 +490,9 @@ def run_own_arm(args, rank, world, local_rank):
     rs_per_s = row_steps_local / (kern_ms * 1e-3)
     clk = clocks.summary()
     sm_hz = (clk.get("sm_mhz") or 1900.0) * 1e6
-    mufu_per_row_step = 2 * 386                                      # 384 hidden softplus + the sigma head's outer one: ex2 + lg2 each
+    # MUFU ops issued per row-step: 386 ex2 (384 hidden softplus + the sigma head's outer one) + the lg2 that stay on the
+    # MUFU pipe: half of layers 1-2 take lg2(1+u) as a packed-FMA polynomial (csrc/sampler_ws.cu, UPD_WS_PMASK12_NS = 0x33)
+    mufu_per_row_step = 386 + (128 + 128 + 2)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": resident_ms / args.steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
@@ -510,8 +512,8 @@ def run_own_arm(args, rank, world, local_rank):
                      "mufu_frac": rs_per_s * mufu_per_row_step / (148 * 16 * sm_hz),
                      "tensor_active": rs_per_s * ISSUED_F16_FLOPS_PER_ROW_STEP / (148 * 8192 * sm_hz),
                      "note": "per GPU (rank 0's launch).  algorithmic FLOPs = 2*33408 MAC per denoiser row-step (SURVEY 8a7). "
-                             "mufu_frac = 772 ex2/lg2 per row-step against 16 MUFU lanes/clk/SM at the sampled SM clock -- the "
-                             "pipe that bounds this MLP; tensor_active = issued MMA work (2 split passes in layers 2-3, 3 in layer 1) against the dense "
+                             "mufu_frac = 644 issued ex2/lg2 per row-step (386 ex2 + 258 lg2; the other 128 lg2 run as FMA-pipe "
+                             "polynomials) against 16 MUFU lanes/clk/SM at the sampled SM clock -- the pipe that bounds this MLP; tensor_active = issued MMA work (2 split passes in layers 2-3, 3 in layer 1) against the dense "
                              "fp16 rate; both derived from the measured row-steps/s, the ncu captures are in profiles/"},
     }
     if world > 1:
