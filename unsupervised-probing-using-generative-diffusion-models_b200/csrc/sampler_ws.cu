@@ -68,6 +68,16 @@ constexpr int HEADS_BAR0 = 6;         // + tile: 16 epilogue warps arrive, the 4
 #ifndef UPD_WS_PMASK3_TM
 #define UPD_WS_PMASK3_TM 0xff
 #endif
+#ifndef UPD_WS_PMASK1_NS               // layer 1 alone (its MUFU form always carries the overflow guard)
+#define UPD_WS_PMASK1_NS UPD_WS_PMASK12_NS
+#endif
+#ifndef UPD_WS_PMASK1_TM
+#ifdef UPD_WS_PMASK12
+#define UPD_WS_PMASK1_TM UPD_WS_PMASK12
+#else
+#define UPD_WS_PMASK1_TM 0x77            // TMDM layer 1: 6 of 8 pairs (5.74 -> 5.86 G row-steps/s); NsDiff: no gain from any layer-1 mask
+#endif
+#endif
 // Passes of the layer-2 / layer-3 contractions.  The activation operand is ONE fp16 word per element (round to nearest:
 // an unbiased 2^-12 relative perturbation, independent per element and step), the weights stay hi + lo: hi*hi + hi*lo.
 // Measured against the oracle on whole windows (tests/test_gpu_parity_full.py, the same bounds as before): NsDiff configs
@@ -111,7 +121,8 @@ struct WsShape {
 template <bool FIRST, bool GUARD, bool SUMSQ>
 __device__ __forceinline__ float epilogue_quarter(uint32_t acc, const float* __restrict__ e, const float* __restrict__ b,
                                                   float inv, int half_bar) {
-  constexpr int PMASK = SUMSQ ? UPD_WS_PMASK12_NS : UPD_WS_PMASK12_TM;        // SUMSQ <=> NsDiff (L2-normalised layers)
+  constexpr int PMASK = FIRST ? (SUMSQ ? UPD_WS_PMASK1_NS : UPD_WS_PMASK1_TM)     // SUMSQ <=> NsDiff (L2-normalised layers)
+                              : (SUMSQ ? UPD_WS_PMASK12_NS : UPD_WS_PMASK12_TM);
   float2 ss2 = make_float2(0.f, 0.f);
   const float2 inv2 = sm::splat(inv);
   uint32_t r[32], o[16];
