@@ -194,3 +194,28 @@ def test_sweep_driver_accepts_the_spatial_model():
     mpv = cache.upd_stats["scaled"]["mpv"]
     want = torch.stack([cache[w].permute(0, 2, 3, 1).var(dim=-1, unbiased=False).mean() for w in range(4)])
     assert _rel(mpv, want) < 1e-4
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_dense_bridge_equals_the_library_convolutions(name):
+    """The f(x) bridge as three tcgen05 GEMMs (the (1, T+1) convolutions re-indexed into dense maps at load time, the
+    K|Q|V|skip projection as one split-operand GEMM) against the same bridge on F.conv1d / F.conv_transpose1d / addmm
+    (mu_backbone.py:203-206, 300-318): the dense path must be the one taken at these shapes, and agree to fp32 rounding."""
+    from updgm_b200.diffstg import graph_csr
+    g, cfg, shapes, seed = _load(name)
+    m, _ = _model(g, cfg, shapes, seed)
+    fx = m.cond_pred_model
+    x, ei = torch.from_numpy(g["x"]), torch.from_numpy(g["edge_index"])
+    V = x.shape[0]
+    rowptr, col = graph_csr(ei, V)
+    fx.set_graph(rowptr.to(DEV), col.to(DEV), V)
+    torch.manual_seed(5)
+    enc = torch.randn(2 * V, cfg["windows"], cfg["d_model"], device=DEV)
+    assert fx._dense_bridge() is not None, "dense bridge not available at the fixture's shape"
+    with torch.no_grad():
+        a = fx.bridge(enc)
+        fx.DENSE_BRIDGE_MAX, fx._dense_key = 0, None                  # force the library path
+        assert fx._dense_bridge() is None
+        b = fx.bridge(enc)
+    assert tuple(a.shape) == tuple(b.shape) == tuple(enc.shape)
+    assert _rel(a, b) < 2e-5, _rel(a, b)

@@ -23,7 +23,7 @@ import torch.nn.functional as F
 from . import _lib, schedules
 from .diffstg import (PreparedUGnet, alias_parameter, block_shapes, gated_aggregate, graph_csr, populate_ugnet)
 from .diffusionts import ParamTree
-from .fx_encoder import NsTransformer
+from .fx_encoder import NsTransformer, _W3Cache, a3_split, gemm3
 from .nsdiff import EPS, SigmaEstimation
 
 ROWS_PER_LAUNCH = 32768
@@ -71,7 +71,13 @@ class GatedGraphConvParams(nn.Module):
             b = torch.cat([self.lin_key.bias, self.lin_query.bias, self.lin_value.bias,
                            torch.zeros(C, device=dev)], 0).detach().contiguous()
             self._fused, self._fused_key = (w, b), key
+            self._fused_w3 = _W3Cache().get([(w, b)]) if (C % 8 == 0 and dev.type == "cuda") else None
         return self._fused
+
+    def fused_w3(self):
+        """The same K|Q|V|skip layer as the split-operand fp16 weight of upd_gemm3 (None when C % 8 != 0: 3C + 8 must be a multiple of 8)."""
+        self.fused_weights()
+        return self._fused_w3
 
 
 class SpatialBlockParams(nn.Module):
@@ -99,6 +105,41 @@ class NsTransformerSpatial(NsTransformer):
         self.downsampling = nn.Conv2d(d, d, (1, self.T + 1), (1, 1), (0, self.fT_h // 2))
         self.upsampling = nn.ConvTranspose2d(d, d, (1, self.T + 1), (1, 1), (0, self.fT_h // 2))
         self._graph = None
+        self._dense_key, self._dense = None, None
+
+    DENSE_BRIDGE_MAX = 1 << 26          # elements of one dense (1, T+1) map above which the library convolution is kept
+
+    def _dense_bridge(self):
+        """The two (1, T+1) convolutions as dense maps on the activations' own layouts, built once per parameter version:
+        down  [L*d -> fT*d]: (s, ci) -> (tau, co), M = W_down[co, ci, s - tau + pad]   (Conv2d, mu_backbone.py:203-206)
+        up    [fT*d -> L*d]: (tau, ci) -> (s, co), M = W_up[ci, co, s - tau + pad]     (ConvTranspose2d)
+        zero where the tap index leaves 0..T, as split-operand fp16 weights for upd_gemm3 (3e-6 accuracy, bias inside the
+        GEMM).  A (1, T+1) kernel over T positions is dense anyway -- the matrix form only re-indexes the weight (fT x
+        its size), and the whole bridge then runs on the tcgen05 GEMM instead of cuDNN / magma kernels.  None when the
+        shapes do not fit (odd fT, K not a multiple of 8, or a map beyond DENSE_BRIDGE_MAX elements)."""
+        wd, wu = self.downsampling.weight, self.upsampling.weight
+        key = (wd.device, wd._version, wu._version, self.downsampling.bias._version, self.upsampling.bias._version)
+        if key != self._dense_key:
+            d, L, fT = self.d_model, self.T, self.fT_h
+            ok_shape = (wd.device.type == "cuda" and fT % 2 == 0 and (L * d) % 8 == 0 and (fT * d) % 8 == 0
+                        and L * d * fT * d <= self.DENSE_BRIDGE_MAX)
+            if not ok_shape:
+                self._dense = None
+            else:
+                dev, pad = wd.device, fT // 2
+                sidx = torch.arange(L, device=dev)[:, None]
+                tau = torch.arange(fT, device=dev)[None, :]
+                k = sidx - tau + pad                                                   # [L, fT]
+                ok = ((k >= 0) & (k <= L)).to(torch.float32)
+                kc = k.clamp(0, L)
+                md = wd.detach()[:, :, 0, :][:, :, kc] * ok                            # [co, ci, s, tau]
+                down = md.permute(3, 0, 2, 1).reshape(fT * d, L * d)                   # rows (tau, co), columns (s, ci)
+                mu = wu.detach()[:, :, 0, :][:, :, kc] * ok                            # [ci, co, s, tau]
+                up = mu.permute(2, 1, 3, 0).reshape(L * d, fT * d)                     # rows (s, co), columns (tau, ci)
+                self._dense = (_W3Cache().get([(down.contiguous(), self.downsampling.bias.detach().repeat(fT))]),
+                               _W3Cache().get([(up.contiguous(), self.upsampling.bias.detach().repeat(L))]))
+            self._dense_key = key
+        return self._dense
 
     def set_graph(self, rowptr, col, num_nodes):
         self._graph = (rowptr, col, int(num_nodes))
@@ -111,6 +152,14 @@ class NsTransformerSpatial(NsTransformer):
         if B % V != 0:
             raise ValueError("{} rows are not whole replicas of the {}-node graph".format(B, V))
         fT, pad = self.fT_h, self.fT_h // 2
+        dense = self._dense_bridge() if L == self.T and d == self.d_model else None
+        if dense is not None and all(blk.gnn.fused_w3() is not None for blk in self.spatial_encoder):
+            # library-free bridge: three kinds of launches (operand split, tcgen05 GEMM, gated aggregation)
+            s = gemm3(a3_split(enc_out.reshape(B, L * d).contiguous()), dense[0], fT * d)
+            for blk in self.spatial_encoder:
+                kqvs = gemm3(a3_split(s), blk.gnn.fused_w3(), 4 * fT * d)
+                s = gated_aggregate(kqvs, rowptr, col, blk.gnn.bias, V, fT * d)
+            return gemm3(a3_split(s), dense[1], L * d).view(B, L, d)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             h = F.conv1d(enc_out.transpose(1, 2), self.downsampling.weight[:, :, 0, :], self.downsampling.bias, padding=pad)
             s = h.transpose(1, 2).reshape(B, fT * d)
