@@ -304,7 +304,7 @@ def other_configs(dev, peaks):
         return {"workload": "configs[3] truncated: DiffusionTS SIS, 1 window x 100 nodes x K=10 (of 199 windows x K=100), "
                             "seq 200, 100 sampling steps with Langevin infill",
                 "e2e": {"value": n / sec, "unit": UNIT, "ms_per_sweep": sec * 1e3},
-                "dominant_kernel": "dts_attn_tc_bwd_kernel / dts_attn_tc_fwd_kernel, 20 % + 12 % of a step (profiles/r02b_families_launches_summary.txt)",
+                "dominant_kernel": "dts_attn_tc_bwd_kernel / dts_attn_tc_fwd_kernel, 20 % + 12 % of a step (profiles/r02c_families_launches_summary.txt)",
                 "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16, "unit": "TFLOP/s", "frac": tf / bf16,
                              "note": "whole sweep, algorithmic 208 GFLOP per trajectory (SURVEY 8a14)"}}
 
@@ -327,7 +327,7 @@ def other_configs(dev, peaks):
         return {"workload": "configs[4] at (T_h, T_p) = (100, 100): DiffSTG biomass, BA-100 graph, 4 windows x 100 nodes x "
                             "100 samples (10 rounds x 10 replicas), 20 DDIM steps",
                 "e2e": {"value": n / (e2e_ms * 1e-3), "unit": "node-trajectories/s", "ms_per_sweep": e2e_ms},
-                "dominant_kernel": "stg_tcn_mma_kernel, 32 % of a step (gemm3_* 29 %, gated aggregation 18 %; profiles/r02b_families_launches_summary.txt)",
+                "dominant_kernel": "stg_tcn_mma_kernel, 32 % of a step (gemm3_* 29 %, gated aggregation 18 %; profiles/r02c_families_launches_summary.txt)",
                 "roofline": {"bound": "tensor", "achieved": tf, "peak": bf16, "unit": "TFLOP/s", "frac": tf / bf16,
                              "note": "whole sweep, ~1 GFLOP per node-trajectory (SURVEY 8a15 estimate)"}}
 
