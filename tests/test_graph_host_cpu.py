@@ -175,3 +175,27 @@ def test_diffstg_sampler_orchestration_matches_reference_fixture(cpu_stand_ins):
     b = m.sample_windows(wins, ei, V, seed=5, window_base=7)
     c = m.sample_windows(wins[1:], ei, V, seed=5, window_base=8)
     assert _rel(b, a) < 1e-5 and _rel(c, a[V:]) < 1e-5 and float(a.var(dim=1).mean()) > 0
+
+
+@pytest.mark.parametrize("d,L,fT,B", [(6, 20, 4, 3), (4, 16, 10, 2), (8, 9, 2, 1)])
+def test_dense_time_conv_maps_equal_the_bridge_convolutions(d, L, fT, B):
+    """The NsDiff_spatial f(x) bridge runs its (1, T+1) Conv2d / ConvTranspose2d (mu_backbone.py:203-206) as dense
+    matrices on upd_gemm3; the re-indexing itself is host logic and is checked here in float64 against
+    F.conv1d / F.conv_transpose1d (bit-level agreement is not expected: the summation order differs)."""
+    import torch.nn.functional as F
+    from updgm_b200.nsdiff_spatial import dense_time_conv_maps
+    torch.manual_seed(d * 100 + L)
+    down = torch.nn.Conv2d(d, d, (1, L + 1), (1, 1), (0, fT // 2)).double()
+    up = torch.nn.ConvTranspose2d(d, d, (1, L + 1), (1, 1), (0, fT // 2)).double()
+    x = torch.randn(B, L, d, dtype=torch.float64)
+    Dn, Up = dense_time_conv_maps(down.weight.detach()[:, :, 0, :], up.weight.detach()[:, :, 0, :], L, fT)
+    assert tuple(Dn.shape) == (fT * d, L * d) and tuple(Up.shape) == (L * d, fT * d)
+    h = F.conv1d(x.transpose(1, 2), down.weight[:, :, 0, :], down.bias, padding=fT // 2)
+    assert h.shape[-1] == fT
+    s_ref = h.transpose(1, 2).reshape(B, fT * d)
+    s = x.reshape(B, L * d) @ Dn.t() + down.bias.detach().repeat(fT)
+    assert float((s - s_ref).abs().max()) < 1e-12
+    o_ref = F.conv_transpose1d(s_ref.reshape(B, fT, d).transpose(1, 2), up.weight[:, :, 0, :], up.bias,
+                               padding=fT // 2).transpose(1, 2)
+    o = (s_ref @ Up.t() + up.bias.detach().repeat(L)).view(B, L, d)
+    assert tuple(o_ref.shape) == (B, L, d) and float((o - o_ref).abs().max()) < 1e-12

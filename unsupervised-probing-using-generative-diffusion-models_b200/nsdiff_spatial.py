@@ -80,6 +80,26 @@ class GatedGraphConvParams(nn.Module):
         return self._fused_w3
 
 
+def dense_time_conv_maps(w_down, w_up, L, fT):
+    """The bridge's two convolutions along time as dense matrices on row-major [time, channel] activations
+    (mu_backbone.py:203-206: Conv2d / ConvTranspose2d(d, d, (1, T+1), stride 1, padding (0, fT//2)) with T = L, fT even):
+        down [fT*d, L*d]: rows (tau, co), columns (s, ci), entry w_down[co, ci, s - tau + pad]
+        up   [L*d, fT*d]: rows (s, co), columns (tau, ci), entry w_up[ci, co, s - tau + pad]
+    and zero where the tap index s - tau + pad leaves 0..L.  y = x.reshape(B, L*d) @ down.T (+ bias repeated fT times)
+    equals conv1d(x^T).transpose(1, 2).reshape(B, fT*d); z = y @ up.T (+ bias repeated L times) equals
+    conv_transpose1d(y as [B, d, fT]).transpose(1, 2).  w_down [co, ci, L+1], w_up [ci, co, L+1]."""
+    d, pad, dev = w_down.shape[0], fT // 2, w_down.device
+    sidx = torch.arange(L, device=dev)[:, None]
+    tau = torch.arange(fT, device=dev)[None, :]
+    k = sidx - tau + pad                                                   # [L, fT]
+    ok = ((k >= 0) & (k <= L)).to(w_down.dtype)
+    kc = k.clamp(0, L)
+    md = w_down[:, :, kc] * ok                                             # [co, ci, s, tau]
+    mu = w_up[:, :, kc] * ok                                               # [ci, co, s, tau]
+    return (md.permute(3, 0, 2, 1).reshape(fT * d, L * d).contiguous(),
+            mu.permute(2, 1, 3, 0).reshape(L * d, fT * d).contiguous())
+
+
 class SpatialBlockParams(nn.Module):
     """SpatialBlock (mu_backbone.py:43-51): relu(gnn(x, edge_index)); the arithmetic is in NsTransformerSpatial.bridge."""
 
@@ -126,18 +146,9 @@ class NsTransformerSpatial(NsTransformer):
             if not ok_shape:
                 self._dense = None
             else:
-                dev, pad = wd.device, fT // 2
-                sidx = torch.arange(L, device=dev)[:, None]
-                tau = torch.arange(fT, device=dev)[None, :]
-                k = sidx - tau + pad                                                   # [L, fT]
-                ok = ((k >= 0) & (k <= L)).to(torch.float32)
-                kc = k.clamp(0, L)
-                md = wd.detach()[:, :, 0, :][:, :, kc] * ok                            # [co, ci, s, tau]
-                down = md.permute(3, 0, 2, 1).reshape(fT * d, L * d)                   # rows (tau, co), columns (s, ci)
-                mu = wu.detach()[:, :, 0, :][:, :, kc] * ok                            # [ci, co, s, tau]
-                up = mu.permute(2, 1, 3, 0).reshape(L * d, fT * d)                     # rows (s, co), columns (tau, ci)
-                self._dense = (_W3Cache().get([(down.contiguous(), self.downsampling.bias.detach().repeat(fT))]),
-                               _W3Cache().get([(up.contiguous(), self.upsampling.bias.detach().repeat(L))]))
+                down, up = dense_time_conv_maps(wd.detach()[:, :, 0, :], wu.detach()[:, :, 0, :], L, fT)
+                self._dense = (_W3Cache().get([(down, self.downsampling.bias.detach().repeat(fT))]),
+                               _W3Cache().get([(up, self.upsampling.bias.detach().repeat(L))]))
             self._dense_key = key
         return self._dense
 
