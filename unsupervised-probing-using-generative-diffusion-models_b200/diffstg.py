@@ -298,8 +298,9 @@ class PreparedUGnet:
                       torch.zeros(C, device=dev)]
                 b["kqvs_w"], b["kqvs_b"] = torch.cat(ws, 0).contiguous(), torch.cat(bs, 0).contiguous()
                 b["gnn_bias"] = sd.get(g + "bias")
-                # split-operand weights of the three dense maps for the fp16 tensor-core path (K multiple of 4)
-                if (c_out * T_in) % 4 == 0 and C % 4 == 0:
+                # split-operand weights of the three dense maps for the fp16 tensor-core path (upd_gemm3 wants 3K + 8 to be a
+                # multiple of 8, i.e. K a multiple of 8 -- e.g. Td_h = 5 with 4 channels keeps the fp32 library GEMMs)
+                if (c_out * T_in) % 8 == 0 and C % 8 == 0:
                     b["down_w3"] = _W3Cache().get([(b["down_w"].t().contiguous(), b["down_b"])])
                     b["kqvs_w3"] = _W3Cache().get([(b["kqvs_w"], b["kqvs_b"])])
                     b["up_w3"] = _W3Cache().get([(b["up_w"].t().contiguous(), b["up_b_full"])])
