@@ -446,3 +446,29 @@ def test_fresh_stats_are_dropped_when_the_cache_or_the_scaler_changes():
     elems[1].mul_(2.0)                                           # in-place edit of one element: views share the version
     assert U._fresh_stats_for(elems, elems[0].shape) is None
     assert not U._FRESH_STATS
+
+
+def test_polynomial_lg2_coefficients_in_the_sampler_source():
+    """The warp-specialised sampler evaluates lg2(1 + u), u = 2^-|z| in (0, 1], as a Horner polynomial on the FMA pipe for
+    part of the hidden units (csrc/sampler_math.cuh, softplus2_poly_b; the reference is F.softplus, denoise.py:47-51).
+    The coefficients are read out of the source and evaluated in numpy, in exact arithmetic and as the kernel's chain of
+    fp32 FMAs (float64 product-sum rounded to fp32 once per step): |error| <= 3.2e-7 / 4.5e-7 for degree 7 (the default),
+    <= 1e-7 / 2.5e-7 for degree 8, over the whole argument range."""
+    import re
+    src = open(os.path.join(ROOT, "unsupervised-probing-using-generative-diffusion-models_b200", "csrc", "sampler_math.cuh")).read()
+    body = src[src.index("softplus2_poly_b(float2 u, float2 z)"):]
+    deg8, deg7 = body[body.index("#if UPD_LG2_DEG == 8"):body.index("#else")], body[body.index("#else"):body.index("#endif")]
+    assert re.search(r"#define UPD_LG2_DEG 7", src), "default degree changed: update DESIGN 4.1 and the parity numbers"
+    u = np.linspace(0.0, 1.0, 200001, dtype=np.float32)
+    want = np.log2(1.0 + u.astype(np.float64))
+    u64 = u.astype(np.float64)
+    for text, n_coef, bound_exact, bound_fma in ((deg8, 9, 1e-7, 2.5e-7), (deg7, 8, 3.2e-7, 4.5e-7)):
+        coef = [np.float32(c) for c in re.findall(r"splat\((-?[0-9.]+e[-+][0-9]+)f\)", text)]
+        assert len(coef) == n_coef, (len(coef), n_coef)
+        exact = np.full(u.shape, float(coef[0]))
+        fma = np.full_like(u, coef[0])
+        for c in coef[1:]:
+            exact = exact * u64 + float(c)
+            fma = (fma.astype(np.float64) * u64 + float(c)).astype(np.float32)
+        assert np.abs(exact - want).max() <= bound_exact, (n_coef - 1, np.abs(exact - want).max())
+        assert np.abs(fma.astype(np.float64) - want).max() <= bound_fma, (n_coef - 1, np.abs(fma.astype(np.float64) - want).max())

@@ -84,7 +84,9 @@ __device__ __forceinline__ float2 softplus2_mufu_b(float2 w, float2 z) {
 // minimax polynomial on the FMA pipe in packed Horner form.  It trades one MUFU op (8 clk of the SMSP's MUFU pipe)
 // for ~9 packed FMA-pipe instructions per pair (measured 2.1-2.4 clk each, profiles/r02_pipe_rates.txt); the epilogues
 // mix the two forms pair by pair (PMASK) so that the MUFU pipe and the FMA pipe run out together.  |error| of the
-// polynomial: degree 7: 2.8e-7, degree 8: 4.2e-8 (lg2.approx itself is good to ~1e-7 on these arguments).  Degree 7 is
+// polynomial with these fp32 coefficients: degree 7: 3.0e-7 in exact arithmetic, 3.9e-7 as the fp32 FMA chain below;
+// degree 8: 0.9e-7 / 1.9e-7 (tests/test_host_cpu.py evaluates both from this source; lg2.approx itself is good to ~1e-7
+// on these arguments, and 1 + u rounds u to 6e-8 before it).  Degree 7 is
 // the default: full-size oracle parity is the same to three digits with either (tests/test_gpu_parity_full.py: NsDiff
 // 3.0-5.5e-6 of rms, TMDM 1.24e-5, MPV 1e-7..5e-7) and it is 1 % (NsDiff) / 2.6 % (TMDM) faster.
 #ifndef UPD_LG2_DEG
