@@ -35,7 +35,7 @@ for row in csv.DictReader(lines):
     tot += v
 with open("profiles/%s_bench_launches_summary.txt" % tag, "w") as f:
     f.write("# ncu --metrics gpu__time_duration.sum --clock-control none -c 9000   python bench.py --steps 1 --warmup 1\n")
-    f.write("# (UPD_BENCH_SKIP_CPU=1: the CPU baseline leg is skipped under the profiler).  Per-launch times are\n")
+    f.write("# (UPD_BENCH_SKIP_CPU=1 UPD_BENCH_SKIP_CONFIGS=1: the CPU baseline / parity and other-configs legs are skipped under the profiler).  Per-launch times are\n")
     f.write("# cold-cache and serialised: compare SHARES.  The command runs 2 resident sweeps + 2 end-to-end sweeps\n# + the one sweep of the wall-time measurement (5 sampler launches).\n")
     f.write("# total GPU time %.1f ms over %d launches\n" % (tot / 1e6, sum(a[0] for a in agg.values())))
     f.write("%12s %8s %7s  %s\n" % ("time_ms", "share", "n", "kernel"))
