@@ -86,7 +86,10 @@ def test_one_loop_iteration_matches_reference():
         d = (out.cpu()[:, L:] - ref[:, L:]).abs()          # the observed part is overwritten with the target at the end
         K, lr = m.langevin_schedule(time, 0.05)
         bad = (d > 1e-3)
-        assert float(bad.float().mean()) <= 0.005, (time, float(bad.float().mean()))
+        flip = float(bad.float().mean())
+        print("DiffusionTS loop iteration t=%d: %.4f %% of the elements beyond 1e-3 (sign flips of the Adagrad step; bound 0.5 %%), "
+              "max |d| %.3e" % (time, 100.0 * flip, float(d.max())))
+        assert flip <= 0.005, "t={}: measured sign-flip rate {:.4%} exceeds 0.5 %".format(time, flip)
         assert float(d.max()) <= 2 * lr * max(K, 1) + 1e-3, (time, float(d.max()))
         # the q_sample'd observed part, checked through a second model call path: img before the final overwrite
         assert torch.equal(out.cpu()[:, :L], target[:, :L])
